@@ -1,0 +1,319 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the PSGD hot path of lixilinx/psgd_torch.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module, and only as the checker / the timed CPU baseline.  The product path
+(psgd_torch_b200/) never imports it.
+
+It restates, in plain torch-CPU tensor ops (explicit matmuls instead of opt_einsum expressions),
+the functions of the reference that are on the hot path named by BASELINE.json:north_star.
+Every function cites the reference lines it follows.  All random draws are EXPLICIT inputs
+(the reference draws them internally from the torch generators); `draw_kron_noise` /
+`draw_lra_noise` reproduce the reference's draw order so that, after `torch.manual_seed(s)`,
+the oracle consumes exactly the numbers the reference would.
+
+Parity pin: the reference holds no golden vectors or known-answer tests.  This
+restatement is pinned against the *unmodified reference itself*, imported in the build container
+through oracle/opt_einsum_shim.py, by tests/golden/make_golden.py; the resulting input/output
+vectors are committed under tests/golden/ and checked by tests/test_oracle_golden.py.
+
+Rounding points follow the reference: every matmul / elementwise result is materialised in the
+tensor dtype (bf16 or fp32), the Lipschitz constants L are fp32 0-dim tensors (psgd.py:96-98,207).
+"""
+import math
+
+import torch
+
+
+# --------------------------------------------------------------------------------------
+# helpers (psgd.py:46-124)
+# --------------------------------------------------------------------------------------
+def lift2single(x):
+    """psgd.py:96-98"""
+    return x.to(torch.float32) if torch.finfo(x.dtype).eps > 1e-6 else x
+
+
+def _norm_lower_bound(A, normalizing_factor, V0, half_iters=2):
+    """Shared body of psgd.py:60-68 / 85-93 with the probe V0 (k x s) passed in."""
+    smallest_normal = torch.finfo(A.dtype).smallest_normal
+    A = A / normalizing_factor
+    j = torch.argmax(torch.linalg.vector_norm(A, dim=1))
+    V = V0
+    V = A[j] + torch.sgn(torch.sum(A[j] * V, dim=1, keepdim=True)) * V
+    for _ in range(half_iters):
+        V = V @ A
+        V = V / (torch.linalg.vector_norm(V, dim=1, keepdim=True) + smallest_normal)
+        V = V @ A
+    return normalizing_factor * torch.amax(torch.linalg.vector_norm(V, dim=1))
+
+
+def norm_lower_bound_spd(A, V0, half_iters=2):
+    """psgd.py:46-68 (real A). V0 replaces the internal torch.randn(k, s) of line 62."""
+    nf = A.diagonal().amax() + torch.finfo(A.dtype).smallest_normal
+    return _norm_lower_bound(A, nf, V0, half_iters)
+
+
+def norm_lower_bound_skh(A, V0, half_iters=2):
+    """psgd.py:71-93 (real A). V0 replaces the internal torch.randn(k, s) of line 87."""
+    nf = A.abs().amax() + torch.finfo(A.dtype).smallest_normal
+    return _norm_lower_bound(A, nf, V0, half_iters)
+
+
+def procrustes_step2(Q, V0, max_step_size=1 / 8):
+    """psgd.py:101-124, in place on Q. V0 is the probe of the inner norm_lower_bound_skh."""
+    R = Q.T - Q
+    R = R / (norm_lower_bound_skh(R, V0) + torch.finfo(R.dtype).smallest_normal)
+    RQ = R @ Q
+    RRQ = R @ RQ
+    tr_RQ = RQ.diagonal().sum()
+    tr_RRQ = RRQ.diagonal().sum()
+    a = torch.where(tr_RRQ < 0, torch.clamp(-tr_RQ / tr_RRQ, max=max_step_size), max_step_size)
+    Q.add_(a * (RQ + 0.5 * a * RRQ))
+
+
+# --------------------------------------------------------------------------------------
+# Kron: init / apply / update (psgd.py:161-263, 266-275, 322-327, 394-419)
+# --------------------------------------------------------------------------------------
+def init_kron(t, Scale=1.0, max_size=float("inf"), max_skew=1.0):
+    """psgd.py:161-263 for dQ="Q0.5EQ1.5": returns [Q, L]; Q[i] is 2-D (dense) or 1-D (diagonal).
+    The einsum expressions of the reference are replaced by explicit mode products below."""
+    shape = t.shape
+    if len(shape) == 0:  # psgd.py:189-195
+        return [[Scale * torch.ones_like(t)], [lift2single(torch.zeros_like(t))]]
+    scale = Scale ** (1 / len(shape))  # psgd.py:200
+    Q, L = [], []
+    for size in shape:
+        L.append(lift2single(torch.zeros([], dtype=t.dtype, device=t.device)))  # psgd.py:207
+        if size <= 1 or size > max_size or size ** 2 > max_skew * t.numel():  # psgd.py:208
+            Q.append(scale * torch.ones(size, dtype=t.dtype, device=t.device))
+        else:
+            Q.append(scale * torch.eye(size, dtype=t.dtype, device=t.device))
+    return [Q, L]
+
+
+def _mode_apply(q, X, i, transpose):
+    """Apply factor q along dim i of X: dense q: sum_b q[a,b] X[..b..] (or q^T), diagonal q: scaling."""
+    if q.dim() < 2:
+        shp = [1] * X.dim()
+        shp[i] = -1
+        return X * q.reshape(shp) if X.dim() > 0 else X * q
+    Xi = X.movedim(i, 0)
+    s = Xi.shape[0]
+    Y = (q.T if transpose else q) @ Xi.reshape(s, -1)
+    return Y.reshape(Xi.shape).movedim(0, i)
+
+
+def precond_grad_kron(Q, G):
+    """psgd.py:322-327: exprP(Q*, Q, G) = (kron_i Q_i^T Q_i) G  (real tensors)."""
+    X = G
+    for i, q in enumerate(Q):
+        X = _mode_apply(q, X, i, transpose=False)
+    for i, q in enumerate(Q):
+        X = _mode_apply(q, X, i, transpose=True)
+    return X
+
+
+def _gram(Pg, i, dense):
+    """exprGs[i](Pg, Pg*) psgd.py:221-223 (diag: 'row' sums of squares) / 240-243 (dense: Gram)."""
+    if Pg.dim() == 0:
+        return Pg * Pg
+    M = Pg.movedim(i, 0).reshape(Pg.shape[i], -1)
+    return M @ M.T if dense else torch.sum(M * M, dim=1)
+
+
+def balance_kron_precond(Q):
+    """psgd.py:266-275"""
+    order = len(Q)
+    if order > 1:
+        norms = [torch.max(torch.abs(q)) for q in Q]
+        gmean = torch.prod(torch.stack(norms)) ** (1 / order)
+        for i, q in enumerate(Q):
+            q.mul_(gmean / norms[i])
+
+
+def draw_kron_noise(G, Q):
+    """Draw, from the torch global generators and in the reference's order, every random number one
+    update_precond_kron_whiten_q0p5eq1p5 call consumes (SURVEY.md 8b 'RNG contract'):
+      (1) randn_like(G) psgd.py:403; per dense factor (2) randn(32,s) psgd.py:62 then (3) randn(32,s)
+      psgd.py:87 (inside procrustes_step2, line 118); finally (4) torch.rand([]) psgd.py:418."""
+    noise = {"N": torch.randn_like(G), "spd": [], "skh": []}
+    for q in Q:
+        if q.dim() == 2:
+            noise["spd"].append(torch.randn(32, q.shape[1], dtype=q.dtype, device=q.device))
+            noise["skh"].append(torch.randn(32, q.shape[1], dtype=q.dtype, device=q.device))
+        else:
+            noise["spd"].append(None)
+            noise["skh"].append(None)
+    noise["balance"] = bool(torch.rand([]) < 0.01)
+    return noise
+
+
+def update_precond_kron_whiten_q0p5eq1p5(QL, G, noise, lr=0.1, betaL=0.9, damping=1e-9):
+    """psgd.py:394-419, in place on Q and L; `noise` from draw_kron_noise."""
+    Q, L = QL
+    total_numel = G.numel()
+    damp = damping + torch.finfo(G.dtype).eps * G.abs()  # psgd.py:402
+    Pg = precond_grad_kron(Q, G + damp * noise["N"])  # psgd.py:403
+    for i, q in enumerate(Q):
+        if q.dim() < 2:  # psgd.py:406-410
+            term1 = _gram(Pg, i, dense=False)
+            term2 = total_numel / q.numel()
+            ell = torch.max(term1) + term2
+            L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+            q.mul_(1 - lr / L[i] * (term1 - term2))
+        else:  # psgd.py:411-416
+            term1 = _gram(Pg, i, dense=True)
+            term2 = total_numel / q.shape[0]
+            ell = norm_lower_bound_spd(term1, noise["spd"][i]) + term2
+            L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+            q.sub_(lr / L[i] * (term1 @ q - term2 * q))
+            procrustes_step2(q, noise["skh"][i])
+    if noise.get("balance", False):  # psgd.py:418-419
+        balance_kron_precond(Q)
+
+
+# --------------------------------------------------------------------------------------
+# LRA (psgd.py:987-1072)
+# --------------------------------------------------------------------------------------
+def IpUVtmatvec(U, V, x):
+    """psgd.py:987-991"""
+    return x + U.mm(V.t().mm(x))
+
+
+def update_precond_lra(UVd, Luvd, v, h, lr=0.1, betaL=0.9, update_U=True):
+    """psgd.py:994-1052, in place. `update_U` replaces the coin flip torch.rand([]) < 0.5 (line 1035)."""
+    U, V, d = UVd
+    Lu, Lv, Ld = Luvd
+    UtU, VtV = U.t() @ U, V.t() @ V
+    trUtU, trVtV = torch.sum(UtU.diagonal()), torch.sum(VtV.diagonal())
+    rho = (trUtU / trVtV) ** (1 / 4)
+    rho2 = rho * rho
+    E = 0.1 * (UtU / rho2 - VtV * rho2) / (trUtU / rho2 + trVtV * rho2)
+    E2 = 0.5 * E @ E
+    U.div_(rho)
+    V.mul_(rho)
+    U.sub_(U @ (E - E2))
+    V.add_(V @ (E + E2))
+
+    Qh = IpUVtmatvec(U, V, d * h)
+    Ph = d * IpUVtmatvec(V, U, Qh)
+
+    IpVtU = V.t().mm(U)
+    IpVtU.diagonal().add_(1)
+    invQtv = v / d
+    LU, pivots = torch.linalg.lu_factor(lift2single(IpVtU))
+    invQtv = invQtv - V.mm(torch.linalg.lu_solve(LU, pivots, lift2single(U.t().mm(invQtv)), adjoint=True).to(V.dtype))
+    invPv = invQtv - U.mm(torch.linalg.lu_solve(LU, pivots, lift2single(V.t().mm(invQtv))).to(U.dtype))
+    invPv = invPv / d
+
+    Phh, vinvPv = Ph * h, v * invPv
+    ell = torch.max(torch.abs(Phh)) + torch.max(torch.abs(vinvPv))
+    Ld.copy_(torch.max(betaL * Ld + (1 - betaL) * ell, ell))
+    d.sub_(lr / Ld * (Phh - vinvPv) * d)
+
+    a, b = Qh, invQtv
+    if update_U:  # psgd.py:1036-1043
+        atV = a.t().mm(V)
+        btV = b.t().mm(V)
+        atVVt = atV.mm(V.t())
+        btVVt = btV.mm(V.t())
+        ell = (torch.linalg.vector_norm(a) * torch.linalg.vector_norm(atVVt)
+               + torch.linalg.vector_norm(b) * torch.linalg.vector_norm(btVVt))
+        Lu.copy_(torch.max(betaL * Lu + (1 - betaL) * ell, ell))
+        U.sub_(lr / Lu * (a.mm(atV.mm(IpVtU)) - b.mm(btV.mm(IpVtU))))
+    else:  # psgd.py:1045-1052
+        atU = a.t().mm(U)
+        btU = b.t().mm(U)
+        UUta = U.mm(atU.t())
+        UUtb = U.mm(btU.t())
+        ell = (torch.linalg.vector_norm(a) * torch.linalg.vector_norm(UUta)
+               + torch.linalg.vector_norm(b) * torch.linalg.vector_norm(UUtb))
+        Lv.copy_(torch.max(betaL * Lv + (1 - betaL) * ell, ell))
+        V.sub_(lr / Lv * ((a + V.mm(atU.t())).mm(atU) - (b + V.mm(btU.t())).mm(btU)))
+
+
+def precond_grad_lra(UVd, g):
+    """psgd.py:1055-1063"""
+    U, V, d = UVd
+    g = IpUVtmatvec(U, V, d * g)
+    g = d * IpUVtmatvec(V, U, g)
+    return g
+
+
+def draw_lra_noise(g):
+    """RNG order of update_precond_lra_whiten: randn_like(g) psgd.py:1070, torch.rand([]) psgd.py:1035."""
+    v = torch.randn_like(g)
+    update_U = bool(torch.rand([]) < 0.5)
+    return {"v": v, "update_U": update_U}
+
+
+def update_precond_lra_whiten(UVd, Luvd, g, noise, lr=0.1, betaL=0.9, damping=1e-9):
+    """psgd.py:1066-1072: the same v is both the probe and the damping noise."""
+    v = noise["v"]
+    damp = damping + torch.finfo(g.dtype).eps * g.abs()
+    update_precond_lra(UVd, Luvd, v, g + damp * v, lr=lr, betaL=betaL, update_U=noise["update_U"])
+
+
+# --------------------------------------------------------------------------------------
+# KWNS4 per-parameter step glue (wrapped_as_torch_optimizer_for_ddp.py:112-161)
+# --------------------------------------------------------------------------------------
+def kwns4_param_step(p, grad, state, noise, *, lr_params=2e-4, lr_preconditioner=0.5, betaL=0.9, damping=1e-9,
+                     momentum=0.9, weight_decay=0.05, decoupled_weight_decay=True, grad_clip_max_amps=(2.0, 10.0),
+                     preconditioner_dtype=torch.bfloat16, update_preconditioner_first=True, whiten_grad=False,
+                     do_update=True, preconditioner_init_scale=1.0, max_size=float("inf"), max_skew=1.0):
+    """One iteration of the per-parameter loop body of KWNS4.step (ddp.py:112-161), on CPU tensors.
+    `state` is a dict (empty on first touch); `noise` from draw_kron_noise (drawn only if do_update)."""
+    max_avg_amp, max_element_amp = grad_clip_max_amps
+    if weight_decay > 0.0:  # ddp.py:117-122
+        if decoupled_weight_decay:
+            p.mul_(1.0 - weight_decay * lr_params)
+        else:
+            grad = grad.add(p, alpha=weight_decay)
+    grad = grad.squeeze()  # ddp.py:124
+    if preconditioner_dtype:
+        grad = grad.to(preconditioner_dtype)  # ddp.py:125-127
+    if len(state) == 0:  # ddp.py:130-137
+        state["QL"] = init_kron(grad, Scale=preconditioner_init_scale, max_size=max_size, max_skew=max_skew)
+        state["step"] = 0
+        state["ema"] = None if momentum == 0.0 else torch.zeros_like(grad)
+    t = state["step"]
+    if momentum > 0.0:  # ddp.py:139-143
+        beta = min(t / (t + 1), momentum)
+        state["ema"].mul_(beta).add_(grad, alpha=1.0 - beta)
+    state["step"] += 1
+    to_be_whitened = grad if whiten_grad else state["ema"]
+    if do_update and update_preconditioner_first:  # ddp.py:146-148
+        update_precond_kron_whiten_q0p5eq1p5(state["QL"], to_be_whitened, noise, lr=lr_preconditioner, betaL=betaL, damping=damping)
+    to_be_preconded = grad if momentum == 0.0 else state["ema"]
+    h = precond_grad_kron(state["QL"][0], to_be_preconded)  # ddp.py:150-151
+    avg_amp = torch.sqrt(torch.mean(h * h))  # ddp.py:153-156
+    if avg_amp > max_avg_amp:
+        h = h * (max_avg_amp / avg_amp)
+    h = h.clamp(min=-max_element_amp, max=max_element_amp)
+    p.subtract_(h.view_as(p), alpha=lr_params)  # ddp.py:157
+    if do_update and not update_preconditioner_first:  # ddp.py:159-161
+        update_precond_kron_whiten_q0p5eq1p5(state["QL"], to_be_whitened, noise, lr=lr_preconditioner, betaL=betaL, damping=damping)
+    return h
+
+
+# --------------------------------------------------------------------------------------
+# Algorithmic work per unit -- used by bench.py for the roofline line
+# --------------------------------------------------------------------------------------
+def kron_unit_flops(m, n, dense_l, dense_r):
+    """Full-GEMM algorithmic FLOPs (min-flop contraction order, no credit for Gram symmetry) of one
+    update + one apply on an m x n tensor. Returns (update_flops, apply_flops)."""
+    chain = 0.0
+    if dense_l:
+        chain += 2.0 * m * m * n + 2.0 * m * m * min(m, n)
+    if dense_r:
+        chain += 2.0 * m * n * n + 2.0 * n * n * min(m, n)
+    upd = chain
+    if dense_l:
+        upd += 2.0 * m * m * n + 6.0 * m ** 3
+    if dense_r:
+        upd += 2.0 * m * n * n + 6.0 * n ** 3
+    return upd, chain
+
+
+def lra_unit_bytes(n, r, elem_bytes):
+    """Compulsory HBM traffic of one LRA update / apply."""
+    return 6.0 * n * r * elem_bytes, 4.0 * n * r * elem_bytes

@@ -1,0 +1,173 @@
+"""Generate the golden input/output vectors under tests/golden/ by running the UNMODIFIED reference
+(/root/reference/psgd.py and wrapped_as_torch_optimizer_for_ddp.py) on CPU through
+oracle/opt_einsum_shim.py.  Only runnable where /root/reference exists (the build container); the
+resulting *.pt files are committed and are what travels to the GPU box.
+
+    python tests/golden/make_golden.py
+
+For every case the reference call is made after torch.manual_seed(seed); the random numbers it
+consumed are then re-drawn with the same seed by oracle.psgd_oracle.draw_*_noise (same call order,
+shapes and dtypes) and stored, so that the oracle restatement and the CUDA engine can be driven with
+exactly the numbers the reference used.
+"""
+import copy
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import opt_einsum_shim  # noqa: E402
+from oracle import psgd_oracle as orc  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+ref = opt_einsum_shim.load_reference("/root/reference")
+
+
+def structured_grad(shape, dtype, gen_seed):
+    """G = H_L^{1/2} Z H_R^{1/2}-like correlated gradient (cf. misc/psgd_kron_verification.py:185-194) so
+    that the preconditioner has something to whiten."""
+    g = torch.Generator().manual_seed(gen_seed)
+    Z = torch.randn(*shape, generator=g)
+    if len(shape) == 2:
+        m, n = shape
+        WL = torch.randn(m, m, generator=g) / m ** 0.5 + 0.5 * torch.eye(m)
+        WR = torch.randn(n, n, generator=g) / n ** 0.5 + 0.5 * torch.eye(n)
+        Z = WL @ Z @ WR
+    return (0.1 * Z).to(dtype)
+
+
+def kron_case(name, shape, dtype, steps=3, max_skew=1.0, lr=0.5, want_balance_step=None):
+    t0 = torch.zeros(*shape, dtype=dtype)
+    QL_ref, exprs = ref.init_kron(t0, Scale=1.0, max_size=float("inf"), max_skew=max_skew, dQ="Q0.5EQ1.5")
+    QL_o = orc.init_kron(t0, Scale=1.0, max_size=float("inf"), max_skew=max_skew)
+    for a, b in zip(QL_ref[0], QL_o[0]):
+        assert torch.equal(a, b)
+    case = {"name": name, "shape": list(shape), "dtype": str(dtype), "max_skew": max_skew, "lr": lr,
+            "betaL": 0.9, "damping": 1e-9, "Q0": [q.clone() for q in QL_ref[0]], "L0": [l.clone() for l in QL_ref[1]],
+            "steps": []}
+    worst = 0.0
+    for s in range(steps):
+        G = structured_grad(shape, dtype, 1000 + s)
+        seed = 4242 + 17 * s
+        if want_balance_step == s:  # find a seed whose 4th draw triggers balance_kron_precond
+            while True:
+                torch.manual_seed(seed)
+                if orc.draw_kron_noise(G, QL_ref[0])["balance"]:
+                    break
+                seed += 1
+        torch.manual_seed(seed)
+        ref.update_precond_kron_whiten_q0p5eq1p5(QL_ref, exprs, G, lr=lr, betaL=0.9, damping=1e-9)
+        Pg = ref.precond_grad_kron(QL_ref, exprs, G)
+        torch.manual_seed(seed)
+        noise = orc.draw_kron_noise(G, QL_o[0])
+        orc.update_precond_kron_whiten_q0p5eq1p5(QL_o, G, noise, lr=lr, betaL=0.9, damping=1e-9)
+        Pg_o = orc.precond_grad_kron(QL_o[0], G)
+        for a, b in zip(QL_ref[0], QL_o[0]):
+            worst = max(worst, float((a.float() - b.float()).norm() / a.float().norm()))
+        worst = max(worst, float((Pg.float() - Pg_o.float()).norm() / Pg.float().norm()))
+        case["steps"].append({"G": G, "seed": seed, "noise": noise,
+                              "Q": [q.clone() for q in QL_ref[0]], "L": [l.clone() for l in QL_ref[1]],
+                              "Pg": Pg.clone()})
+    print(f"{name:28s} shape={tuple(shape)} {dtype}: oracle-vs-reference worst normwise rel err {worst:.3e}")
+    torch.save(case, os.path.join(OUT, f"kron_{name}.pt"))
+    return worst
+
+
+def lra_case(name, n, r, dtype, steps=4, lr=0.1):
+    g0 = torch.Generator().manual_seed(7)
+    U = torch.randn(n, r, generator=g0)
+    U = (U * (0.1 ** 0.5 / torch.linalg.vector_norm(U))).to(dtype)  # psgd.py:1115-1118
+    V = torch.randn(n, r, generator=g0)
+    V = (V * (0.1 ** 0.5 / torch.linalg.vector_norm(V))).to(dtype)
+    d = torch.ones(n, 1, dtype=dtype)
+    Luvd_r = [torch.zeros([], dtype=torch.float32) for _ in range(3)]
+    UVd_r = [U.clone(), V.clone(), d.clone()]
+    UVd_o, Luvd_o = [U.clone(), V.clone(), d.clone()], [l.clone() for l in Luvd_r]
+    case = {"name": name, "n": n, "r": r, "dtype": str(dtype), "lr": lr, "betaL": 0.9, "damping": 1e-9,
+            "U0": U, "V0": V, "d0": d, "steps": []}
+    worst = 0.0
+    for s in range(steps):
+        g = structured_grad((n, 1), dtype, 2000 + s)
+        g = g * (1 + torch.arange(n).reshape(n, 1) % 7).to(dtype)
+        seed = 999 + 31 * s
+        torch.manual_seed(seed)
+        ref.update_precond_lra_whiten(UVd_r, Luvd_r, g, lr=lr, betaL=0.9, damping=1e-9)
+        Pg = ref.precond_grad_lra(UVd_r, g)
+        torch.manual_seed(seed)
+        noise = orc.draw_lra_noise(g)
+        orc.update_precond_lra_whiten(UVd_o, Luvd_o, g, noise, lr=lr, betaL=0.9, damping=1e-9)
+        Pg_o = orc.precond_grad_lra(UVd_o, g)
+        for a, b in zip(UVd_r + [Pg], UVd_o + [Pg_o]):
+            worst = max(worst, float((a.float() - b.float()).norm() / a.float().norm()))
+        case["steps"].append({"g": g, "seed": seed, "noise": noise, "U": UVd_r[0].clone(), "V": UVd_r[1].clone(),
+                              "d": UVd_r[2].clone(), "L": [l.clone() for l in Luvd_r], "Pg": Pg.clone()})
+    print(f"{name:28s} n={n} r={r} {dtype}: oracle-vs-reference worst normwise rel err {worst:.3e}")
+    torch.save(case, os.path.join(OUT, f"lra_{name}.pt"))
+    return worst
+
+
+def kwns4_case(name, shape, pdtype, steps=5, **kw):
+    """Run the reference KWNS4 (ddp.py) single-process on CPU and the oracle step glue side by side."""
+    sys.modules["psgd"] = ref  # ddp.py does `import psgd`
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kwns4_reference", "/root/reference/wrapped_as_torch_optimizer_for_ddp.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    del sys.modules["psgd"]
+    g0 = torch.Generator().manual_seed(5)
+    p_ref = torch.nn.Parameter(torch.randn(*shape, generator=g0))
+    p_orc = p_ref.detach().clone()
+    opt = mod.KWNS4([p_ref], preconditioner_dtype=pdtype, **kw)
+    state = {}
+    case = {"name": name, "shape": list(shape), "pdtype": str(pdtype), "kw": kw, "p0": p_ref.detach().clone(), "steps": []}
+    worst = 0.0
+    for s in range(steps):
+        grad = structured_grad(shape, torch.float32, 3000 + s)
+        seed = 31337 + s
+        p_ref.grad = grad.clone()
+        torch.manual_seed(seed)
+        opt.step()
+        # oracle side: same RNG order: group coin flip (ddp.py:110) then the update's draws
+        torch.manual_seed(seed)
+        do_update = bool(torch.rand([]) < kw.get("preconditioner_update_probability", 1.0))
+        gq = grad.squeeze().to(pdtype) if pdtype else grad.squeeze()
+        if len(state) == 0:
+            Qtmp = orc.init_kron(gq, Scale=kw.get("preconditioner_init_scale", 1.0))[0]
+        else:
+            Qtmp = state["QL"][0]
+        noise = orc.draw_kron_noise(gq, Qtmp) if do_update else None
+        okw = {k: v for k, v in kw.items() if k not in ("preconditioner_update_probability",)}
+        orc.kwns4_param_step(p_orc, grad.clone(), state, noise, preconditioner_dtype=pdtype, do_update=do_update, **okw)
+        worst = max(worst, float((p_ref.detach() - p_orc).norm() / p_ref.detach().norm()))
+        st = opt.state[p_ref]
+        case["steps"].append({"grad": grad, "seed": seed, "do_update": do_update, "noise": noise,
+                              "p": p_ref.detach().clone(), "Q": [q.clone() for q in st["QL"][0]],
+                              "L": [l.clone() for l in st["QL"][1]], "ema": None if st["ema"] is None else st["ema"].clone()})
+    print(f"{name:28s} shape={tuple(shape)} {pdtype}: oracle-vs-reference worst param rel err {worst:.3e}")
+    torch.save(case, os.path.join(OUT, f"kwns4_{name}.pt"))
+    return worst
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)  # deterministic reduction order
+    f32, bf16 = torch.float32, torch.bfloat16
+    kron_case("dd_f32", (24, 40), f32)
+    kron_case("dd_bf16", (24, 40), bf16)
+    kron_case("dd_f32_balance", (16, 16), f32, steps=2, want_balance_step=1)
+    kron_case("dense_diag_f32", (8, 300), f32)
+    kron_case("diag_dense_f32", (300, 8), f32)
+    kron_case("dense_diag_bf16", (8, 300), bf16)
+    kron_case("vec_f32", (50,), f32)
+    kron_case("vec_bf16", (64,), bf16)
+    kron_case("big_dd_f32", (136, 200), f32, steps=2)
+    kron_case("big_dd_bf16", (136, 200), bf16, steps=2)
+    kron_case("order3_f32", (2, 3, 4), f32)
+    lra_case("r4_f32", 300, 4, f32)
+    lra_case("r4_bf16", 300, 4, bf16)
+    lra_case("r16_f32", 1000, 16, f32)
+    kwns4_case("f32", (16, 24), f32, steps=5, lr_params=1e-2)
+    kwns4_case("bf16", (16, 24), bf16, steps=5, lr_params=1e-2)
+    kwns4_case("bf16_squeeze", (1, 12, 1, 20), bf16, steps=4, lr_params=1e-2, momentum=0.0, whiten_grad=True,
+               weight_decay=0.0, update_preconditioner_first=False)
