@@ -1,0 +1,164 @@
+"""ctypes binding of libpsgd_b200.so (include/psgd_b200.h).
+
+The product path has exactly one implementation: the CUDA library.  If the shared object is missing or the
+device is not a B200-class GPU (compute capability 10.x) every entry point raises -- there is no CPU or
+PyTorch fallback (and nothing under oracle/ is ever imported from here).
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsgd_b200.so")
+
+PSGD_BF16, PSGD_F32 = 0, 1
+PSGD_DIAG, PSGD_DENSE = 0, 1
+
+_DTYPES = {torch.bfloat16: PSGD_BF16, torch.float32: PSGD_F32}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class KronT(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("kind_l", C.c_int32), ("kind_r", C.c_int32), ("dtype", C.c_int32),
+                ("has_r", C.c_int32), ("QL", C.c_void_p), ("QR", C.c_void_p), ("LL", C.c_void_p), ("LR", C.c_void_p)]
+
+
+class KronNoiseT(C.Structure):
+    _fields_ = [("N", C.c_void_p), ("V0_spd_l", C.c_void_p), ("V0_skh_l", C.c_void_p), ("V0_spd_r", C.c_void_p),
+                ("V0_skh_r", C.c_void_p)]
+
+
+class LraT(C.Structure):
+    _fields_ = [("n", C.c_int64), ("r", C.c_int32), ("dtype", C.c_int32), ("U", C.c_void_p), ("V", C.c_void_p),
+                ("d", C.c_void_p), ("Lu", C.c_void_p), ("Lv", C.c_void_p), ("Ld", C.c_void_p)]
+
+
+# every symbol include/psgd_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+SYMBOLS = {
+    "psgd_abi_version": (_i, []),
+    "psgd_status_string": (C.c_char_p, [_i]),
+    "psgd_last_error": (C.c_char_p, [_vp]),
+    "psgd_create": (_i, [C.POINTER(_vp), _i]),
+    "psgd_destroy": (None, [_vp]),
+    "psgd_set_gemm_path": (_i, [_vp, _i]),
+    "psgd_launch_count": (_i64, [_vp]),
+    "psgd_kron_workspace_bytes": (_sz, [_vp, C.POINTER(KronT)]),
+    "psgd_kron_whiten_q0p5eq1p5_update": (_i, [_vp, C.POINTER(KronT), _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),
+    "psgd_kron_precond_grad": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "psgd_kron_balance": (_i, [_vp, C.POINTER(KronT), _vp, _sz, _vp]),
+    "psgd_helper_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "psgd_norm_lower_bound_spd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "psgd_norm_lower_bound_skh": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "psgd_procrustes_step2": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _sz, _vp]),
+    "psgd_kwns4_head": (_i, [_vp, _i64, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp, _i, _f, _vp]),
+    "psgd_kwns4_tail": (_i, [_vp, _i64, _vp, _i, _vp, _i, _vp, _f, _f, _f, _vp]),
+    "psgd_lra_workspace_bytes": (_sz, [_vp, C.POINTER(LraT)]),
+    "psgd_lra_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _i, _vp, _sz, _vp]),
+    "psgd_lra_whiten_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _f, _i, _vp, _sz, _vp]),
+    "psgd_lra_precond_grad": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "psgd_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _f, _vp, _i, _f, _vp]),
+    "psgd_debug_set_mn_desc": (_i, [_vp, _i, _i]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_handles = {}
+_workspaces = {}
+
+
+def load_library():
+    """dlopen the in-tree shared object (works without a GPU: the CUDA runtime is linked statically and the driver
+    entry points are resolved lazily in psgd_create)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise EngineError(f"{LIB_PATH} not found: build it with `python -m psgd_torch_b200.build` "
+                                  "(there is no fallback implementation)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            if lib.psgd_abi_version() != 1:
+                raise EngineError("libpsgd_b200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def check(handle, rc, what):
+    if rc != 0:
+        lib = load_library()
+        msg = lib.psgd_status_string(rc).decode()
+        extra = lib.psgd_last_error(handle).decode() if handle else ""
+        raise EngineError(f"{what} failed: {msg} ({rc}) {extra}")
+
+
+def handle_for(device):
+    """One engine context per CUDA device."""
+    lib = load_library()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise EngineError(f"psgd_torch_b200 runs on CUDA (sm_100a) tensors only, got a tensor on '{dev}'")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    h = _handles.get(idx)
+    if h is None:
+        with _lock:
+            h = _handles.get(idx)
+            if h is None:
+                out = C.c_void_p()
+                rc = lib.psgd_create(C.byref(out), idx)
+                check(None, rc, f"psgd_create(device={idx})")
+                h = out
+                _handles[idx] = h
+    return h
+
+
+def workspace(device, nbytes):
+    """A per-device scratch tensor, grown geometrically; all engine calls on a device are stream-ordered on the
+    current stream, so one buffer per (device, stream) is enough."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _workspaces[key] = None
+        ws = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", idx))
+        _workspaces[key] = ws
+    return ws
+
+
+def free_workspaces():
+    _workspaces.clear()
+
+
+def dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise EngineError(f"unsupported preconditioner dtype {t.dtype}; the engine computes in bfloat16 or float32")
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def stream_ptr(device):
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+def launch_count(device=None):
+    if device is None:
+        return sum(load_library().psgd_launch_count(h) for h in _handles.values())
+    return load_library().psgd_launch_count(handle_for(device))

@@ -1,0 +1,620 @@
+// api.cu -- C-ABI of libpsgd_b200.so (include/psgd_b200.h): context, workspace layout and the stream-ordered
+// orchestration of one Kron update / apply out of the GEMM and bandwidth kernels.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "kron_kernels.cuh"
+
+namespace psgd {
+
+int check_cuda(Ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return PSGD_OK;
+  if (ctx) snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", what, cudaGetErrorString(e));
+  return PSGD_ERR_CUDA;
+}
+
+int launch_gemm(Ctx* ctx, const GemmDesc& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return PSGD_OK;
+  if (ctx->gemm_path == 1) return launch_gemm_simt(ctx, g, st);
+  if (tc_eligible(g)) return launch_gemm_tc_group(ctx, &g, 1, st);
+  if (ctx->gemm_path == 2) return PSGD_ERR_UNSUPPORTED;
+  return launch_gemm_simt(ctx, g, st);
+}
+
+// two independent GEMMs; one grouped tcgen05 launch when both qualify
+int launch_gemm_pair(Ctx* ctx, const GemmDesc& g0, const GemmDesc& g1, cudaStream_t st) {
+  if (ctx->gemm_path != 1 && tc_eligible(g0) && tc_eligible(g1)) {
+    GemmDesc gs[2] = {g0, g1};
+    return launch_gemm_tc_group(ctx, gs, 2, st);
+  }
+  int rc = launch_gemm(ctx, g0, st);
+  if (rc) return rc;
+  return launch_gemm(ctx, g1, st);
+}
+
+static GemmDesc gemm_desc(int dt, const void* A, int lda, int ta, const void* B, int ldb, int tb, int M, int N, int K,
+                          void* C, int ldc) {
+  GemmDesc g;
+  g.A = A; g.B = B; g.lda = lda; g.ldb = ldb; g.ta = ta; g.tb = tb; g.M = M; g.N = N; g.K = K; g.in_dtype = dt;
+  g.epi = make_epi(C, ldc, dt);
+  return g;
+}
+
+static inline int ew_blocks(Ctx* ctx, size_t numel, int threads = 256) {
+  size_t b = (numel + threads - 1) / threads;
+  size_t cap = (size_t)ctx->num_sms * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define LAUNCH_CHECK(ctx, what)                                  \
+  do {                                                           \
+    (ctx)->launches++;                                           \
+    int rc__ = check_cuda((ctx), cudaGetLastError(), what);      \
+    if (rc__) return rc__;                                       \
+  } while (0)
+
+#define DISPATCH_T(dt, ...)                      \
+  do {                                           \
+    if ((dt) == PSGD_BF16) { typedef bf16 T; __VA_ARGS__; } \
+    else { typedef float T; __VA_ARGS__; }      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+struct Bump {
+  char* base;
+  size_t off;
+  explicit Bump(void* b) : base(reinterpret_cast<char*>(b)), off(0) {}
+  void* take(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return base ? base + o : reinterpret_cast<void*>(o + 256);  // sizing mode: fake non-null pointers
+  }
+};
+
+struct BoundWs {          // scratch of one norm_lower_bound_* evaluation
+  float* scal;            // SC_COUNT
+  float* rn1; float* rn3; float* rn4;  // 32 each
+  float* sc1; float* sc3;              // 32 each
+};
+
+struct FactorWs {
+  float* row_sumsq;   // s  (Gram row norms^2)
+  float* diag_max;    // 1
+  float* r_row_sumsq; // s  (R row norms^2)
+  float* r_abs_max;   // 1
+  float* fs;          // FS_COUNT
+  BoundWs b_spd, b_skh;
+  float* term1;       // s (diagonal factor: sums of squares)
+};
+
+struct KronWs {
+  // zeroed region
+  char* zero_begin; size_t zero_bytes;
+  FactorWs f[2];
+  float* bal;       // 2 floats (max|QL|, max|QR|)
+  // buffers
+  float* qsq[2];    // fp32 squares of diagonal factors
+  void* B0; void* B1; void* B2;   // m x n
+  void* S[5];       // smax x smax: T, Qn, R, RQ, RRQ   (R / RQ slots double as P_L / P_R before the Grams)
+  void* Va; void* Vb;             // 32 x smax
+  size_t total;
+};
+
+static void layout_bound(Bump& b, BoundWs& w) {
+  w.scal = (float*)b.take(SC_COUNT * 4);
+  w.rn1 = (float*)b.take(32 * 4); w.rn3 = (float*)b.take(32 * 4); w.rn4 = (float*)b.take(32 * 4);
+  w.sc1 = (float*)b.take(32 * 4); w.sc3 = (float*)b.take(32 * 4);
+}
+
+static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
+  Bump b(base);
+  const int es = dtype_size(k->dtype);
+  const size_t m = k->m, n = k->has_r ? k->n : 1;
+  const int sdim[2] = {k->m, k->has_r ? k->n : 0};
+  const int dense[2] = {k->kind_l == PSGD_DENSE, k->has_r && k->kind_r == PSGD_DENSE};
+  size_t smax = 0;
+  for (int i = 0; i < 2; ++i) if (dense[i] && (size_t)sdim[i] > smax) smax = sdim[i];
+  w.zero_begin = (char*)b.take(0);
+  size_t z0 = b.off;
+  for (int i = 0; i < 2; ++i) {
+    FactorWs& f = w.f[i];
+    size_t s = sdim[i] > 0 ? sdim[i] : 1;
+    f.row_sumsq = (float*)b.take(s * 4);
+    f.diag_max = (float*)b.take(4);
+    f.r_row_sumsq = (float*)b.take(s * 4);
+    f.r_abs_max = (float*)b.take(4);
+    f.fs = (float*)b.take(FS_COUNT * 4);
+    layout_bound(b, f.b_spd);
+    layout_bound(b, f.b_skh);
+    f.term1 = (float*)b.take(s * 4);
+  }
+  w.bal = (float*)b.take(2 * 4);
+  w.zero_bytes = b.off - z0;
+  w.qsq[0] = (float*)b.take(m * 4);
+  w.qsq[1] = (float*)b.take(n * 4);
+  w.B0 = b.take(m * n * es); w.B1 = b.take(m * n * es); w.B2 = b.take(m * n * es);
+  for (int i = 0; i < 5; ++i) w.S[i] = b.take(smax * smax * es);
+  w.Va = b.take(32 * smax * es); w.Vb = b.take(32 * smax * es);
+  w.total = b.off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// norm_lower_bound_{spd,skh}  (psgd.py:46-93): A s x s, row_sumsq / nf_src already reduced
+// ---------------------------------------------------------------------------------------------
+static int run_bound(Ctx* ctx, int dt, const void* A, int s, const void* V0, const float* row_sumsq, const float* nf_src,
+                     BoundWs& w, void* Va, void* Vb, cudaStream_t st) {
+  const float tiny = dtype_tiny(dt);
+  k_bound_prep<<<1, 1024, 0, st>>>(row_sumsq, s, nf_src, tiny, w.scal);
+  LAUNCH_CHECK(ctx, "k_bound_prep");
+  DISPATCH_T(dt, (k_probe_init<T><<<32, 256, 0, st>>>((const T*)A, s, (const T*)V0, w.scal, (T*)Va)));
+  LAUNCH_CHECK(ctx, "k_probe_init");
+  // W1 = V1 A / nf  (+ row norms)
+  GemmDesc g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
+  g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn1;
+  int rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  k_rowscale<<<1, 32, 0, st>>>(w.rn1, w.scal, tiny, w.sc1, 32);
+  LAUNCH_CHECK(ctx, "k_rowscale");
+  // W2 = (W1 / |W1|) A / nf
+  g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
+  g.epi.row_scale = w.sc1;
+  rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  // W3 = W2 A / nf (+ row norms)
+  g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
+  g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn3;
+  rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  k_rowscale<<<1, 32, 0, st>>>(w.rn3, w.scal, tiny, w.sc3, 32);
+  LAUNCH_CHECK(ctx, "k_rowscale");
+  // W4 = (W3 / |W3|) A / nf (+ row norms)
+  g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
+  g.epi.row_scale = w.sc3; g.epi.row_sumsq = w.rn4;
+  rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  k_bound_final<<<1, 32, 0, st>>>(w.rn4, 32, w.scal, dt);
+  LAUNCH_CHECK(ctx, "k_bound_final");
+  return PSGD_OK;
+}
+
+// procrustes_step2 (psgd.py:101-124) on Qn -> writes Q.  S buffers: R, RQ, RRQ
+static int run_procrustes(Ctx* ctx, int dt, const void* Qn, void* Q, int s, const void* V0, float max_step, FactorWs& f,
+                          void* R, void* RQ, void* RRQ, void* Va, void* Vb, cudaStream_t st) {
+  dim3 grid((s + 31) / 32, (s + 31) / 32), block(32, 8);
+  DISPATCH_T(dt, (k_skew<T><<<grid, block, 0, st>>>((const T*)Qn, (T*)R, s, f.r_abs_max, f.r_row_sumsq)));
+  LAUNCH_CHECK(ctx, "k_skew");
+  int rc = run_bound(ctx, dt, R, s, V0, f.r_row_sumsq, f.r_abs_max, f.b_skh, Va, Vb, st);
+  if (rc) return rc;
+  k_procrustes_scal<<<1, 32, 0, st>>>(f.b_skh.scal, dtype_tiny(dt), f.fs);
+  LAUNCH_CHECK(ctx, "k_procrustes_scal");
+  GemmDesc g = gemm_desc(dt, R, s, 0, Qn, s, 0, s, s, s, RQ, s);
+  g.epi.alpha_ptr = f.fs + FS_INV_SR; g.epi.trace = f.fs + FS_TR1;
+  rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  g = gemm_desc(dt, R, s, 0, RQ, s, 0, s, s, s, RRQ, s);
+  g.epi.alpha_ptr = f.fs + FS_INV_SR; g.epi.trace = f.fs + FS_TR2;
+  rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  size_t numel = (size_t)s * s;
+  DISPATCH_T(dt, (k_procrustes_finish<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)Qn, (const T*)RQ, (const T*)RRQ,
+                                                                                 (T*)Q, numel, f.fs, max_step)));
+  LAUNCH_CHECK(ctx, "k_procrustes_finish");
+  return PSGD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out = (Q_L^T Q_L) X (Q_R^T Q_R)   psgd.py:322-327 / 403, min-flop contraction order
+// reductions (on out): row_sumsq / col_sumsq / total_sumsq, any may be null
+// ---------------------------------------------------------------------------------------------
+static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, void* out, float* row_sumsq, float* col_sumsq,
+                     float* total_sumsq, cudaStream_t st) {
+  const int dt = k->dtype;
+  const int m = k->m, n = k->has_r ? k->n : 1;
+  const bool dl = k->kind_l == PSGD_DENSE, dr = k->has_r && k->kind_r == PSGD_DENSE;
+  int rc;
+  if (!dl) { DISPATCH_T(dt, (k_square_to_f32<T><<<(m + 255) / 256, 256, 0, st>>>((const T*)k->QL, w.qsq[0], m))); LAUNCH_CHECK(ctx, "k_square"); }
+  if (k->has_r && !dr) { DISPATCH_T(dt, (k_square_to_f32<T><<<(n + 255) / 256, 256, 0, st>>>((const T*)k->QR, w.qsq[1], n))); LAUNCH_CHECK(ctx, "k_square"); }
+  const float* rs = dl ? nullptr : w.qsq[0];
+  const float* cs = (!k->has_r || dr) ? nullptr : w.qsq[1];
+  if (!dl && !dr) {
+    size_t numel = (size_t)m * n;
+    DISPATCH_T(dt, (k_scale2d<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)X, (T*)out, m, n, rs, cs, row_sumsq, col_sumsq,
+                                                                       total_sumsq)));
+    LAUNCH_CHECK(ctx, "k_scale2d");
+    return PSGD_OK;
+  }
+  void* PL = w.S[2];
+  void* PR = w.S[3];
+  // ---- left side ----
+  // scratch: B0 and B2 (out is B1 or caller memory, X is B0 or caller memory).  X is dead once the first product
+  // of the chain form has consumed it, so B0 may be overwritten afterwards; the P-first form reads X last.
+  const void* Y = X;  // result of the left stage
+  GemmDesc g;
+  auto set_final = [&](GemmDesc& gd) {
+    gd.epi.row_scale = rs; gd.epi.col_scale = cs;
+    gd.epi.row_sumsq = row_sumsq; gd.epi.col_sumsq = col_sumsq; gd.epi.total_sumsq = total_sumsq;
+  };
+  if (dl) {
+    if (m < n) {  // P_L = Q_L^T Q_L first: 2m^3 + 2m^2 n
+      void* dstL = dr ? ((X == w.B0) ? w.B2 : w.B0) : out;
+      g = gemm_desc(dt, k->QL, m, 1, k->QL, m, 0, m, m, m, PL, m);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      g = gemm_desc(dt, PL, m, 0, X, n, 0, m, n, m, dstL, n);
+      if (!dr) set_final(g);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      Y = dstL;
+    } else {      // chain: Q_L X then Q_L^T (.): 4 m^2 n
+      void* dstL = dr ? w.B0 : out;
+      g = gemm_desc(dt, k->QL, m, 0, X, n, 0, m, n, m, w.B2, n);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      g = gemm_desc(dt, k->QL, m, 1, w.B2, n, 0, m, n, m, dstL, n);
+      if (!dr) set_final(g);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      Y = dstL;
+    }
+  }
+  // ---- right side ----
+  if (dr) {
+    if (n < m) {  // P_R = Q_R^T Q_R first
+      g = gemm_desc(dt, k->QR, n, 1, k->QR, n, 0, n, n, n, PR, n);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      g = gemm_desc(dt, Y, n, 0, PR, n, 0, m, n, n, out, n);
+      set_final(g);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    } else {      // Y Q_R^T then (.) Q_R
+      void* tr = (Y == w.B2) ? w.B0 : w.B2;
+      g = gemm_desc(dt, Y, n, 0, k->QR, n, 1, m, n, n, tr, n);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      g = gemm_desc(dt, tr, n, 0, k->QR, n, 0, m, n, n, out, n);
+      set_final(g);
+      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    }
+  }
+  return PSGD_OK;
+}
+
+static int validate_kron(const psgd_kron_t* k) {
+  if (!k || k->m < 1 || !k->QL || !k->LL) return PSGD_ERR_INVALID_ARG;
+  if (k->dtype != PSGD_BF16 && k->dtype != PSGD_F32) return PSGD_ERR_INVALID_ARG;
+  if (k->has_r && (k->n < 1 || !k->QR || !k->LR)) return PSGD_ERR_INVALID_ARG;
+  return PSGD_OK;
+}
+
+static int run_balance(Ctx* ctx, const psgd_kron_t* k, KronWs& w, cudaStream_t st) {
+  if (!k->has_r) return PSGD_OK;  // order-1: nothing to balance (psgd.py:271)
+  const int dt = k->dtype;
+  size_t nl = k->kind_l == PSGD_DENSE ? (size_t)k->m * k->m : (size_t)k->m;
+  size_t nr = k->kind_r == PSGD_DENSE ? (size_t)k->n * k->n : (size_t)k->n;
+  int rc = check_cuda(ctx, cudaMemsetAsync(w.bal, 0, 8, st), "memset"); if (rc) return rc;
+  DISPATCH_T(dt, (k_absmax<T><<<ew_blocks(ctx, nl), 256, 0, st>>>((const T*)k->QL, nl, w.bal)));
+  LAUNCH_CHECK(ctx, "k_absmax");
+  DISPATCH_T(dt, (k_absmax<T><<<ew_blocks(ctx, nr), 256, 0, st>>>((const T*)k->QR, nr, w.bal + 1)));
+  LAUNCH_CHECK(ctx, "k_absmax");
+  DISPATCH_T(dt, (k_balance_scale<T><<<ew_blocks(ctx, nl), 256, 0, st>>>((T*)k->QL, nl, w.bal, w.bal + 1, dt)));
+  LAUNCH_CHECK(ctx, "k_balance_scale");
+  DISPATCH_T(dt, (k_balance_scale<T><<<ew_blocks(ctx, nr), 256, 0, st>>>((T*)k->QR, nr, w.bal + 1, w.bal, dt)));
+  LAUNCH_CHECK(ctx, "k_balance_scale");
+  return PSGD_OK;
+}
+
+}  // namespace psgd
+
+using namespace psgd;
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+int psgd_abi_version(void) { return PSGD_B200_ABI_VERSION; }
+
+const char* psgd_status_string(int s) {
+  switch (s) {
+    case PSGD_OK: return "ok";
+    case PSGD_ERR_INVALID_ARG: return "invalid argument";
+    case PSGD_ERR_UNSUPPORTED: return "unsupported shape/dtype for the requested path";
+    case PSGD_ERR_WORKSPACE: return "workspace too small";
+    case PSGD_ERR_CUDA: return "CUDA error (see psgd_last_error)";
+    case PSGD_ERR_NOT_SM100: return "device is not compute capability 10.x (B200); this engine has no other code path";
+    default: return "unknown status";
+  }
+}
+
+const char* psgd_last_error(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->last_error : ""; }
+
+int psgd_create(psgd_handle_t* out, int device) {
+  if (!out) return PSGD_ERR_INVALID_ARG;
+  *out = nullptr;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return PSGD_ERR_CUDA;
+  if (prop.major != 10) return PSGD_ERR_NOT_SM100;
+  Ctx* ctx = new (std::nothrow) Ctx();
+  if (!ctx) return PSGD_ERR_CUDA;
+  memset(ctx, 0, sizeof(Ctx));
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->gemm_path = 0;
+  ctx->mn_lbo = 8192;
+  ctx->mn_sbo = 1024;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
+  ctx->encode_tiled = fn;
+  *out = reinterpret_cast<psgd_handle_t>(ctx);
+  return PSGD_OK;
+}
+
+void psgd_destroy(psgd_handle_t h) { delete reinterpret_cast<Ctx*>(h); }
+
+int psgd_set_gemm_path(psgd_handle_t h, int p) {
+  if (!h || p < 0 || p > 2) return PSGD_ERR_INVALID_ARG;
+  reinterpret_cast<Ctx*>(h)->gemm_path = p;
+  return PSGD_OK;
+}
+
+int64_t psgd_launch_count(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->launches : 0; }
+
+int psgd_debug_set_mn_desc(psgd_handle_t h, int lbo, int sbo) {
+  if (!h) return PSGD_ERR_INVALID_ARG;
+  reinterpret_cast<Ctx*>(h)->mn_lbo = lbo;
+  reinterpret_cast<Ctx*>(h)->mn_sbo = sbo;
+  return PSGD_OK;
+}
+
+size_t psgd_kron_workspace_bytes(psgd_handle_t, const psgd_kron_t* k) {
+  if (validate_kron(k)) return 0;
+  KronWs w;
+  layout_kron(k, nullptr, w);
+  return w.total;
+}
+
+int psgd_kron_whiten_q0p5eq1p5_update(psgd_handle_t h, const psgd_kron_t* k, const void* G, float lr, float betaL, float damping,
+                                      const psgd_kron_noise_t* noise, int do_balance, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !G || !noise || !noise->N) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_kron(k); if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  KronWs w;
+  layout_kron(k, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  const int dt = k->dtype;
+  const int m = k->m, n = k->has_r ? k->n : 1;
+  const size_t numel = (size_t)m * n;
+  const bool dense[2] = {k->kind_l == PSGD_DENSE, k->has_r && k->kind_r == PSGD_DENSE};
+  if ((dense[0] && (!noise->V0_spd_l || !noise->V0_skh_l)) || (dense[1] && (!noise->V0_spd_r || !noise->V0_skh_r)))
+    return PSGD_ERR_INVALID_ARG;
+  rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+
+  // G' = G + (damping + eps|G|) N      psgd.py:402-403
+  DISPATCH_T(dt, (k_add_noise<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)G, (const T*)noise->N, (T*)w.B0, numel, damping,
+                                                                        dtype_eps(dt))));
+  LAUNCH_CHECK(ctx, "k_add_noise");
+  // Pg = P G'  with the sums of squares the diagonal factors need fused into the last product
+  void* Pg = w.B1;
+  rc = run_chain(ctx, k, w, w.B0, Pg, dense[0] ? nullptr : w.f[0].term1, (k->has_r && !dense[1]) ? w.f[1].term1 : nullptr, nullptr, st);
+  if (rc) return rc;
+
+  // Grams of the dense factors (psgd.py:405) -- one grouped launch when both exist
+  void* TL = w.S[0];
+  void* TR = w.S[1];
+  GemmDesc gl, gr;
+  if (dense[0]) {
+    gl = gemm_desc(dt, Pg, n, 0, Pg, n, 1, m, m, n, TL, m);
+    gl.epi.row_sumsq = w.f[0].row_sumsq; gl.epi.diag_max = w.f[0].diag_max;
+  }
+  if (dense[1]) {
+    gr = gemm_desc(dt, Pg, n, 1, Pg, n, 0, n, n, m, TR, n);
+    gr.epi.row_sumsq = w.f[1].row_sumsq; gr.epi.diag_max = w.f[1].diag_max;
+  }
+  if (dense[0] && dense[1]) rc = launch_gemm_pair(ctx, gl, gr, st);
+  else if (dense[0]) rc = launch_gemm(ctx, gl, st);
+  else if (dense[1]) rc = launch_gemm(ctx, gr, st);
+  if (rc) return rc;
+
+  for (int i = 0; i < 2; ++i) {
+    if (i == 1 && !k->has_r) break;
+    const int s = i == 0 ? m : n;
+    void* q = i == 0 ? k->QL : k->QR;
+    float* L = i == 0 ? k->LL : k->LR;
+    FactorWs& f = w.f[i];
+    const float t2 = (float)((double)numel / (double)s);  // psgd.py:407 / 412
+    if (!dense[i]) {
+      DISPATCH_T(dt, (k_diag_update<T><<<1, 1024, 0, st>>>((T*)q, f.term1, s, t2, lr, betaL, L)));
+      LAUNCH_CHECK(ctx, "k_diag_update");
+      continue;
+    }
+    void* Tm = i == 0 ? TL : TR;
+    const void* v_spd = i == 0 ? noise->V0_spd_l : noise->V0_spd_r;
+    const void* v_skh = i == 0 ? noise->V0_skh_l : noise->V0_skh_r;
+    // ell = norm_lower_bound_spd(term1) + t2 ; L update ; step size     psgd.py:413-414
+    rc = run_bound(ctx, dt, Tm, s, v_spd, f.row_sumsq, f.diag_max, f.b_spd, w.Va, w.Vb, st); if (rc) return rc;
+    k_dense_L_update<<<1, 32, 0, st>>>(f.b_spd.scal, t2, lr, betaL, L, f.fs, dt);
+    LAUNCH_CHECK(ctx, "k_dense_L_update");
+    // Qn = Q - lr/L (term1 Q - t2 Q)    psgd.py:415   (out of place: Q is an operand of the product)
+    void* Qn = w.S[2];
+    GemmDesc g = gemm_desc(dt, Tm, s, 0, q, s, 0, s, s, s, Qn, s);
+    g.epi.alpha_ptr = f.fs + FS_ALPHA; g.epi.D = q; g.epi.ldd = s; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.beta_ptr = f.fs + FS_BETA;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    // procrustes_step2(Q)    psgd.py:416 ; the Gram buffer of this factor is dead now and is reused for R
+    rc = run_procrustes(ctx, dt, Qn, q, s, v_skh, 0.125f, f, Tm, w.S[3], w.S[4], w.Va, w.Vb, st); if (rc) return rc;
+  }
+  if (do_balance) { rc = run_balance(ctx, k, w, st); if (rc) return rc; }
+  return PSGD_OK;
+}
+
+int psgd_kron_precond_grad(psgd_handle_t h, const psgd_kron_t* k, const void* X, void* H, float* sumsq_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !X || !H) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_kron(k); if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  KronWs w;
+  layout_kron(k, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4, st), "memset"); if (rc) return rc; }
+  return run_chain(ctx, k, w, X, H, nullptr, nullptr, sumsq_out, st);
+}
+
+int psgd_kron_balance(psgd_handle_t h, const psgd_kron_t* k, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_kron(k); if (rc) return rc;
+  KronWs w;
+  layout_kron(k, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  return run_balance(ctx, k, w, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------- helpers exposed like the reference exposes them -------------------------------
+struct HelperWs {
+  float* row_sumsq; float* nf; FactorWs f; void* R; void* RQ; void* RRQ; void* Qn; void* Va; void* Vb;
+  char* zero_begin; size_t zero_bytes; size_t total;
+};
+static void layout_helper(int s, int dt, void* base, HelperWs& w) {
+  Bump b(base);
+  const int es = dtype_size(dt);
+  w.zero_begin = (char*)b.take(0);
+  size_t z0 = b.off;
+  w.row_sumsq = (float*)b.take((size_t)s * 4);
+  w.nf = (float*)b.take(4);
+  w.f.row_sumsq = w.row_sumsq; w.f.diag_max = w.nf;
+  w.f.r_row_sumsq = (float*)b.take((size_t)s * 4);
+  w.f.r_abs_max = (float*)b.take(4);
+  w.f.fs = (float*)b.take(FS_COUNT * 4);
+  layout_bound(b, w.f.b_spd);
+  layout_bound(b, w.f.b_skh);
+  w.f.term1 = nullptr;
+  w.zero_bytes = b.off - z0;
+  w.R = b.take((size_t)s * s * es); w.RQ = b.take((size_t)s * s * es); w.RRQ = b.take((size_t)s * s * es);
+  w.Qn = b.take((size_t)s * s * es);
+  w.Va = b.take((size_t)32 * s * es); w.Vb = b.take((size_t)32 * s * es);
+  w.total = b.off;
+}
+
+size_t psgd_helper_workspace_bytes(psgd_handle_t, int s, int dtype) {
+  if (s < 1) return 0;
+  HelperWs w;
+  layout_helper(s, dtype, nullptr, w);
+  return w.total;
+}
+
+}  // extern "C"
+// row sums of squares + max diag / max abs of an s x s matrix (standalone bound entry points only)
+template <typename T>
+__global__ void k_rowstats(const T* __restrict__ A, int s, float* row_sumsq, float* diag_max, float* abs_max) {
+  __shared__ float red[32];
+  int i = blockIdx.x;
+  float ss = 0.f, am = 0.f;
+  for (int c = threadIdx.x; c < s; c += blockDim.x) { float v = to_f<T>(A[(size_t)i * s + c]); ss += v * v; am = fmaxf(am, fabsf(v)); }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0) row_sumsq[i] = ss;
+  am = block_max(am, red);
+  if (threadIdx.x == 0) {
+    if (abs_max) atomic_max_nonneg(abs_max, am);
+    if (diag_max) atomic_max_nonneg(diag_max, to_f<T>(A[(size_t)i * s + i]));
+  }
+}
+__global__ void k_copy_scalar(const float* src, float* dst) { if (threadIdx.x == 0) *dst = *src; }
+
+static int bound_entry(psgd_handle_t h, int dt, const void* A, int s, const void* V0, float* out, void* workspace, size_t wsb,
+                       void* stream, bool spd) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !A || !V0 || !out || s < 1) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HelperWs w;
+  layout_helper(s, dt, workspace, w);
+  if (!workspace || wsb < w.total) return PSGD_ERR_WORKSPACE;
+  int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+  DISPATCH_T(dt, (k_rowstats<T><<<s, 256, 0, st>>>((const T*)A, s, w.row_sumsq, spd ? w.nf : nullptr, spd ? nullptr : w.nf)));
+  LAUNCH_CHECK(ctx, "k_rowstats");
+  rc = run_bound(ctx, dt, A, s, V0, w.row_sumsq, w.nf, w.f.b_spd, w.Va, w.Vb, st); if (rc) return rc;
+  k_copy_scalar<<<1, 32, 0, st>>>(w.f.b_spd.scal + SC_BOUND, out);
+  LAUNCH_CHECK(ctx, "k_copy_scalar");
+  return PSGD_OK;
+}
+
+extern "C" {
+int psgd_norm_lower_bound_spd(psgd_handle_t h, int dt, const void* A, int s, const void* V0, float* out, void* ws, size_t wsb, void* stream) {
+  return bound_entry(h, dt, A, s, V0, out, ws, wsb, stream, true);
+}
+int psgd_norm_lower_bound_skh(psgd_handle_t h, int dt, const void* A, int s, const void* V0, float* out, void* ws, size_t wsb, void* stream) {
+  return bound_entry(h, dt, A, s, V0, out, ws, wsb, stream, false);
+}
+
+int psgd_procrustes_step2(psgd_handle_t h, int dt, void* Q, int s, const void* V0, float max_step_size, void* workspace, size_t wsb,
+                          void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !Q || !V0 || s < 1) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HelperWs w;
+  layout_helper(s, dt, workspace, w);
+  if (!workspace || wsb < w.total) return PSGD_ERR_WORKSPACE;
+  int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+  rc = check_cuda(ctx, cudaMemcpyAsync(w.Qn, Q, (size_t)s * s * dtype_size(dt), cudaMemcpyDeviceToDevice, st), "memcpy"); if (rc) return rc;
+  return run_procrustes(ctx, dt, w.Qn, Q, s, V0, max_step_size, w.f, w.R, w.RQ, w.RRQ, w.Va, w.Vb, st);
+}
+
+}  // extern "C"
+// ------------------------------------------- KWNS4 glue -------------------------------------------
+template <typename TP, typename TG>
+static int head_dispatch_q(Ctx* ctx, int64_t numel, void* p, const void* grad, float wd, float lr, int dec, void* ema, void* g_out,
+                           int pre_dtype, float beta, cudaStream_t st) {
+  int blocks = ew_blocks(ctx, (size_t)numel);
+  if (pre_dtype == PSGD_BF16)
+    k_kwns4_head<TP, TG, bf16><<<blocks, 256, 0, st>>>((TP*)p, (const TG*)grad, (size_t)numel, wd, lr, dec, (bf16*)ema, (bf16*)g_out, beta);
+  else
+    k_kwns4_head<TP, TG, float><<<blocks, 256, 0, st>>>((TP*)p, (const TG*)grad, (size_t)numel, wd, lr, dec, (float*)ema, (float*)g_out, beta);
+  LAUNCH_CHECK(ctx, "k_kwns4_head");
+  return PSGD_OK;
+}
+
+extern "C" {
+int psgd_kwns4_head(psgd_handle_t h, int64_t numel, void* p, int p_dtype, const void* grad, int grad_dtype, float weight_decay,
+                    float lr_params, int decoupled, void* ema, void* g_out, int pre_dtype, float beta, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || numel < 0 || !p || !grad) return PSGD_ERR_INVALID_ARG;
+  if (numel == 0) return PSGD_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p_dtype == PSGD_BF16 && grad_dtype == PSGD_BF16) return head_dispatch_q<bf16, bf16>(ctx, numel, p, grad, weight_decay, lr_params, decoupled, ema, g_out, pre_dtype, beta, st);
+  if (p_dtype == PSGD_BF16 && grad_dtype == PSGD_F32) return head_dispatch_q<bf16, float>(ctx, numel, p, grad, weight_decay, lr_params, decoupled, ema, g_out, pre_dtype, beta, st);
+  if (p_dtype == PSGD_F32 && grad_dtype == PSGD_BF16) return head_dispatch_q<float, bf16>(ctx, numel, p, grad, weight_decay, lr_params, decoupled, ema, g_out, pre_dtype, beta, st);
+  return head_dispatch_q<float, float>(ctx, numel, p, grad, weight_decay, lr_params, decoupled, ema, g_out, pre_dtype, beta, st);
+}
+
+int psgd_kwns4_tail(psgd_handle_t h, int64_t numel, void* p, int p_dtype, void* hbuf, int h_dtype, const float* sumsq,
+                    float max_avg_amp, float max_elem_amp, float lr_params, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || numel < 0 || !p || !hbuf || !sumsq) return PSGD_ERR_INVALID_ARG;
+  if (numel == 0) return PSGD_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int blocks = ew_blocks(ctx, (size_t)numel);
+  if (p_dtype == PSGD_BF16 && h_dtype == PSGD_BF16) k_kwns4_tail<bf16, bf16><<<blocks, 256, 0, st>>>((bf16*)p, (bf16*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  else if (p_dtype == PSGD_BF16) k_kwns4_tail<bf16, float><<<blocks, 256, 0, st>>>((bf16*)p, (float*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  else if (h_dtype == PSGD_BF16) k_kwns4_tail<float, bf16><<<blocks, 256, 0, st>>>((float*)p, (bf16*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  else k_kwns4_tail<float, float><<<blocks, 256, 0, st>>>((float*)p, (float*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  LAUNCH_CHECK(ctx, "k_kwns4_tail");
+  return PSGD_OK;
+}
+
+// ------------------------------------------- GEMM building block -------------------------------------------
+int psgd_gemm(psgd_handle_t h, int path, int in_dtype, int out_dtype, int trans_a, int trans_b, int M, int N, int K, const void* A,
+              int lda, const void* B, int ldb, void* C, int ldc, float alpha, const void* D, int ldd, float beta, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !A || !B || !C || M < 0 || N < 0 || K < 0) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmDesc g = gemm_desc(in_dtype, A, lda, trans_a, B, ldb, trans_b, M, N, K, C, ldc);
+  g.epi.out_dtype = out_dtype;
+  g.epi.alpha = alpha;
+  if (D) { g.epi.D = D; g.epi.ldd = ldd; g.epi.d_dtype = in_dtype; g.epi.beta = beta; }
+  int saved = ctx->gemm_path;
+  ctx->gemm_path = path;
+  int rc = launch_gemm(ctx, g, st);
+  ctx->gemm_path = saved;
+  return rc;
+}
+
+}  // extern "C"

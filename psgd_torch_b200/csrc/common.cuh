@@ -1,0 +1,160 @@
+// common.cuh -- shared types of the PSGD engine kernels: dtypes, the fused GEMM epilogue spec, reductions.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/psgd_b200.h"
+
+namespace psgd {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int dtype_size(int dt) { return dt == PSGD_BF16 ? 2 : 4; }
+
+__device__ __forceinline__ float ld_as_float(const void* p, int dt, size_t idx) {
+  return dt == PSGD_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(p)[idx])
+                         : reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void st_from_float(void* p, int dt, size_t idx, float v) {
+  if (dt == PSGD_BF16)
+    reinterpret_cast<bf16*>(p)[idx] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<float*>(p)[idx] = v;
+}
+// value after rounding to the storage dtype (what a consumer of the stored tensor would read)
+__device__ __forceinline__ float round_to(int dt, float v) {
+  return dt == PSGD_BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : v;
+}
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__host__ __device__ inline float dtype_eps(int dt) { return dt == PSGD_BF16 ? 0.0078125f : 1.1920928955078125e-07f; }
+// torch.finfo(dtype).smallest_normal: identical for bf16 and fp32 (same exponent range)
+__host__ __device__ inline float dtype_tiny(int) { return 1.1754943508222875e-38f; }
+
+// ---------------------------------------------------------------------------------------------
+// Fused GEMM epilogue, shared by the SIMT and the tcgen05 kernels:
+//   v        = acc * alpha * (*alpha_ptr) * row_scale[i] * col_scale[j]  +  beta * (*beta_ptr) * D[i,j]
+//   C[i,j]   = round_to(out_dtype, v)
+//   reductions below are taken over the ROUNDED values (the reference computes its norms / traces on the
+//   materialised low-precision tensors), accumulated with atomics into fp32 device buffers that the caller
+//   zeroed beforehand.
+// ---------------------------------------------------------------------------------------------
+struct Epi {
+  void* C;
+  int ldc;
+  int out_dtype;
+  float alpha;
+  const float* alpha_ptr;
+  const void* D;
+  int ldd;
+  int d_dtype;
+  float beta;
+  const float* beta_ptr;
+  const float* row_scale;  // length M (fp32) or null
+  const float* col_scale;  // length N (fp32) or null
+  float* row_sumsq;        // [M] += sum_j C[i,j]^2
+  float* col_sumsq;        // [N] += sum_i C[i,j]^2
+  float* diag_max;         // max_i C[i,i]   (values assumed >= 0; buffer zero-initialised)
+  float* abs_max;          // max |C[i,j]|
+  float* trace;            // += sum_i C[i,i]
+  float* total_sumsq;      // += sum_ij C[i,j]^2
+};
+
+__host__ inline Epi make_epi(void* C, int ldc, int out_dtype) {
+  Epi e;
+  e.C = C; e.ldc = ldc; e.out_dtype = out_dtype;
+  e.alpha = 1.f; e.alpha_ptr = nullptr;
+  e.D = nullptr; e.ldd = 0; e.d_dtype = out_dtype; e.beta = 0.f; e.beta_ptr = nullptr;
+  e.row_scale = nullptr; e.col_scale = nullptr;
+  e.row_sumsq = nullptr; e.col_sumsq = nullptr; e.diag_max = nullptr; e.abs_max = nullptr; e.trace = nullptr;
+  e.total_sumsq = nullptr;
+  return e;
+}
+
+// non-negative float max via integer atomics (buffer initialised to 0)
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+  if (v > 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide reductions (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem32[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = (lane < (int)((blockDim.x + 31) >> 5)) ? smem32[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* smem32) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) smem32[w] = v;
+  __syncthreads();
+  float r = -INFINITY;
+  if (w == 0) {
+    r = (lane < (int)((blockDim.x + 31) >> 5)) ? smem32[lane] : -INFINITY;
+    r = warp_max(r);
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// engine context
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+  int device;
+  int num_sms;
+  int gemm_path;       // 0 auto, 1 simt, 2 tc
+  int mn_lbo, mn_sbo;  // MN-major UMMA descriptor byte offsets
+  int64_t launches;
+  char last_error[256];
+  void* encode_tiled;  // cuTensorMapEncodeTiled entry point
+};
+
+// one GEMM problem: C = epi(op(A) op(B)), op(A) M x K, op(B) K x N
+struct GemmDesc {
+  const void* A;
+  const void* B;
+  int lda, ldb;
+  int ta, tb;  // ta: A stored K x M; tb: B stored N x K
+  int M, N, K;
+  int in_dtype;
+  Epi epi;
+};
+
+// launchers implemented in gemm_simt.cu / gemm_tc.cu / api.cu
+int launch_gemm_simt(Ctx* ctx, const GemmDesc& g, cudaStream_t st);
+bool tc_eligible(const GemmDesc& g);
+int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* g, int n, cudaStream_t st);
+int launch_gemm(Ctx* ctx, const GemmDesc& g, cudaStream_t st);  // picks the path
+int launch_gemm_pair(Ctx* ctx, const GemmDesc& g0, const GemmDesc& g1, cudaStream_t st);
+
+int check_cuda(Ctx* ctx, cudaError_t e, const char* what);
+
+}  // namespace psgd

@@ -1,0 +1,530 @@
+// gemm_tc.cu -- persistent, warp-specialised, grouped bf16 GEMM on the 5th-gen tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (one issuing thread, fp32
+//   accumulators in TMEM, double-buffered) -> tcgen05.ld -> fused PSGD epilogue (common.cuh:Epi) -> global.
+//
+// One launch runs up to TC_MAX_PROBLEMS independent GEMMs ("group"): the left- and right-factor Grams /
+// Newton-Schulz products of one Kron update, or the same product of several parameters.  Their tiles share one
+// flat index space that the persistent CTAs (one per SM) walk round-robin, so small problems fill each other's
+// wave-quantisation bubbles.
+//
+// Operand transposition is done by the tensor core, not by a copy: a row-major matrix whose contraction index
+// runs along its rows ("K-major") and one whose contraction index runs down its columns ("MN-major") are both
+// fed through 128B-swizzled smem tiles; the UMMA instruction descriptor carries the per-operand major bit and
+// the smem descriptor the matching (LBO, SBO) strides.
+//
+// Tile: 128 x BN x 64 (BN = 256 or 128), cta_group::1, UMMA 128 x BN x 16, 4 (BN=256) / 6 (BN=128) smem stages.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
+// (warp w may only touch TMEM lanes 32*(w%4) .. +31).
+#include <cuda.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace psgd {
+
+constexpr int TC_MAX_PROBLEMS = 4;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+
+struct alignas(64) TcProblem {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  Epi epi;
+  int M, N, K;
+  int a_mn, b_mn;  // operand is MN-major in memory
+  int tiles_m, tiles_n;
+  int tile_start;  // first flat tile index of this problem
+};
+
+struct alignas(64) TcGroup {
+  TcProblem p[TC_MAX_PROBLEMS];
+  int num_problems;
+  int total_tiles;
+  int mn_lbo, mn_sbo;
+  int* error_flag;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded spin: a pipeline bug must not hang the GPU (a hung box is a strike) -> trap after ~4 s
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024u) t0 = clock64();
+    if (spins > 1024u && (spins & 1023u) == 0u && clock64() - t0 > 8000000000LL) {
+      if (error_flag) atomicExch(error_flag, 1);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread l of the warp receives row (lane_base + l)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version=1 <<46 | layout SWIZZLE_128B(=2) <<61
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+
+// flat tile -> (problem, tile_m, tile_n); m-grouped rasterisation (8 row-tiles per group) for L2 reuse
+__device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int& pi, int& tm, int& tn) {
+  pi = 0;
+#pragma unroll
+  for (int i = 1; i < TC_MAX_PROBLEMS; ++i)
+    if (i < g.num_problems && t >= g.p[i].tile_start) pi = i;
+  const TcProblem& p = g.p[pi];
+  int lt = t - p.tile_start;
+  const int GROUP = 8;
+  int per_group = GROUP * p.tiles_n;
+  int gidx = lt / per_group;
+  int first_m = gidx * GROUP;
+  int gsz = min(GROUP, p.tiles_m - first_m);
+  int in_g = lt - gidx * per_group;
+  tm = first_m + in_g % gsz;
+  tn = in_g / gsz;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue for one 32-column chunk of one accumulator row
+// ------------------------------------------------------------------------------------------------
+struct RowAcc {
+  float row_sumsq, tot, amax, tr, dmax;
+};
+
+__device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int row, int col0, uint32_t* raw, float alpha,
+                                               float beta, int lane, RowAcc& ra) {
+  float v[32];
+  const bool row_ok = row < M;
+  const float rs = (e.row_scale && row_ok) ? e.row_scale[row] : 1.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * alpha * rs;
+  if (e.col_scale) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < N) ? e.col_scale[col0 + j] : 0.f;
+  }
+  if (e.D && row_ok) {
+    if (e.d_dtype == PSGD_BF16) {
+      const bf16* dp = reinterpret_cast<const bf16*>(e.D) + (size_t)row * e.ldd + col0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (col0 + q * 8 < N) {
+          uint4 u = *reinterpret_cast<const uint4*>(dp + q * 8);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float2 f = __bfloat1622float2(h[t]);
+            v[q * 8 + 2 * t] += beta * f.x;
+            v[q * 8 + 2 * t + 1] += beta * f.y;
+          }
+        }
+      }
+    } else {
+      const float* dp = reinterpret_cast<const float*>(e.D) + (size_t)row * e.ldd + col0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (col0 + q * 4 < N) {
+          float4 f = *reinterpret_cast<const float4*>(dp + q * 4);
+          v[q * 4] += beta * f.x; v[q * 4 + 1] += beta * f.y; v[q * 4 + 2] += beta * f.z; v[q * 4 + 3] += beta * f.w;
+        }
+      }
+    }
+  }
+  // round + store (N is a multiple of 8, so every 8-column vector is fully in or fully out of range)
+  if (e.out_dtype == PSGD_BF16) {
+    bf16* cp = reinterpret_cast<bf16*>(e.C) + (size_t)row * e.ldc + col0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        h[t] = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
+        float2 f = __bfloat1622float2(h[t]);
+        v[q * 8 + 2 * t] = f.x;
+        v[q * 8 + 2 * t + 1] = f.y;
+      }
+      if (row_ok && col0 + q * 8 < N) *reinterpret_cast<uint4*>(cp + q * 8) = u;
+    }
+  } else {
+    float* cp = reinterpret_cast<float*>(e.C) + (size_t)row * e.ldc + col0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (row_ok && col0 + q * 4 < N)
+        *reinterpret_cast<float4*>(cp + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    }
+  }
+  // reductions over the rounded values; out-of-range elements contribute 0
+  const bool need_red = e.row_sumsq || e.col_sumsq || e.total_sumsq || e.abs_max || e.trace || e.diag_max;
+  if (!need_red) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (!row_ok || col0 + j >= N) v[j] = 0.f;
+  float s = 0.f, am = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { s = fmaf(v[j], v[j], s); am = fmaxf(am, fabsf(v[j])); }
+  ra.row_sumsq += s;
+  ra.tot += s;
+  ra.amax = fmaxf(ra.amax, am);
+  if ((e.trace || e.diag_max) && row >= col0 && row < col0 + 32) {
+    float dv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)  // opaque selp: nvcc turns a C++ select chain into a local-memory indexed load
+      asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\tselp.f32 %0, %1, %0, p;\n\t}" : "+f"(dv) : "f"(v[j]), "r"(row - col0), "r"(j));
+    ra.tr += dv;
+    ra.dmax = fmaxf(ra.dmax, dv);
+  }
+  if (e.col_sumsq) {
+    // transpose-reduce: after the 5 halving steps lane l holds sum over the warp's 32 rows of column col0 + l
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
+#define PSGD_TR_STEP(OFF)                                              \
+    {                                                                  \
+      const bool upper = (lane & (OFF)) != 0;                          \
+      _Pragma("unroll") for (int i = 0; i < (OFF); ++i) {              \
+        float send = upper ? v[i] : v[i + (OFF)];                      \
+        float keep = upper ? v[i + (OFF)] : v[i];                      \
+        float recv = __shfl_xor_sync(0xffffffffu, send, (OFF));        \
+        v[i] = keep + recv;                                            \
+      }                                                                \
+    }
+    PSGD_TR_STEP(16) PSGD_TR_STEP(8) PSGD_TR_STEP(4) PSGD_TR_STEP(2) PSGD_TR_STEP(1)
+#undef PSGD_TR_STEP
+    if (col0 + lane < N) atomicAdd(&e.col_sumsq[col0 + lane], v[0]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGroup g) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[S], empty[S], tfull[2], tempty[2], then tmem ptr (4 B)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+    for (int i = 0; i < g.num_problems; ++i) { prefetch_tmap(&g.p[i].map_a); prefetch_tmap(&g.p[i].map_b); }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+        int pi, tm, tn;
+        locate_tile(g, t, pi, tm, tn);
+        const TcProblem& p = g.p[pi];
+        const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, g.error_flag);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(&p.map_a, full_bar(stage), sa, kb * TC_BK, tm * TC_BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 64; ++c)
+              tma_load_2d(&p.map_a, full_bar(stage), sa + c * (TC_BK * 128), tm * TC_BM + c * 64, kb * TC_BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(&p.map_b, full_bar(stage), sb, kb * TC_BK, tn * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(&p.map_b, full_bar(stage), sb + c * (TC_BK * 128), tn * BN + c * 64, kb * TC_BK);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+        int pi, tm, tn;
+        locate_tile(g, t, pi, tm, tn);
+        const TcProblem& p = g.p[pi];
+        const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+        // instruction descriptor: D=f32 (bit4), A=bf16 (bit7), B=bf16 (bit10), a_major bit15, b_major bit16,
+        // N>>3 at bits 17-22, M>>4 at bits 24-28
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.a_mn) << 15) | (uint32_t(p.b_mn) << 16) |
+                               (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
+        const uint32_t a_lbo = p.a_mn ? (uint32_t)g.mn_lbo : 0u, a_sbo = p.a_mn ? (uint32_t)g.mn_sbo : 1024u;
+        const uint32_t b_lbo = p.b_mn ? (uint32_t)g.mn_lbo : 0u, b_sbo = p.b_mn ? (uint32_t)g.mn_sbo : 1024u;
+        const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u;  // bytes to advance per UMMA_K=16
+        const uint32_t b_kstep = p.b_mn ? 16u * 128u : 32u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, g.error_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, g.error_flag);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot is free once these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+      int pi, tm, tn;
+      locate_tile(g, t, pi, tm, tn);
+      const TcProblem& p = g.p[pi];
+      const Epi& e = p.epi;
+      const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
+      const float beta = e.beta * (e.beta_ptr ? *e.beta_ptr : 1.f);
+      mbar_wait(tfull_bar(acc), acc_phase, g.error_flag);
+      tc_fence_after();
+      const int row = tm * TC_BM + quarter * 32 + lane;
+      RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = tn * BN + c * 32;
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, raw);
+        tmem_ld_wait();
+        if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra);
+      }
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      // per-row / per-warp reductions
+      if (e.row_sumsq && row < p.M) atomicAdd(&e.row_sumsq[row], ra.row_sumsq);
+      if (e.total_sumsq) { float s = warp_sum(ra.tot); if (lane == 0) atomicAdd(e.total_sumsq, s); }
+      if (e.abs_max) { float s = warp_max(ra.amax); if (lane == 0) atomic_max_nonneg(e.abs_max, s); }
+      if (e.trace) { float s = warp_sum(ra.tr); if (lane == 0 && s != 0.f) atomicAdd(e.trace, s); }
+      if (e.diag_max) { float s = warp_max(ra.dmax); if (lane == 0) atomic_max_nonneg(e.diag_max, s); }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// row-major bf16 matrix (rows x cols, leading dimension ld elements), box = {64 cols, box_rows}
+static int make_tmap(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  if (!fn) return PSGD_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(ctx->last_error, sizeof(ctx->last_error), "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return PSGD_ERR_CUDA;
+  }
+  return PSGD_OK;
+}
+
+bool tc_eligible(const GemmDesc& g) {
+  if (g.in_dtype != PSGD_BF16) return false;
+  if (g.M < 128 || g.N < 128 || g.K < 64) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!al16(g.A) || !al16(g.B) || !al16(g.epi.C)) return false;
+  if (g.lda % 8 || g.ldb % 8) return false;
+  if (g.N % 8) return false;
+  const int ovec = g.epi.out_dtype == PSGD_BF16 ? 8 : 4;
+  if (g.epi.ldc % ovec) return false;
+  if (g.epi.D) {
+    const int dvec = g.epi.d_dtype == PSGD_BF16 ? 8 : 4;
+    if (!al16(g.epi.D) || g.epi.ldd % dvec) return false;
+  }
+  return true;
+}
+
+template <int BN>
+static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmDesc& g = gs[i];
+    TcProblem& p = grp.p[i];
+    p.epi = g.epi;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.a_mn = g.ta ? 1 : 0;        // A stored K x M: M runs along the contiguous dimension
+    p.b_mn = g.tb ? 0 : 1;        // B stored K x N: N runs along the contiguous dimension
+    int rc;
+    if (!g.ta) rc = make_tmap(ctx, &p.map_a, g.A, g.M, g.K, g.lda, TC_BM);
+    else rc = make_tmap(ctx, &p.map_a, g.A, g.K, g.M, g.lda, TC_BK);
+    if (rc) return rc;
+    if (g.tb) rc = make_tmap(ctx, &p.map_b, g.B, g.N, g.K, g.ldb, BN);
+    else rc = make_tmap(ctx, &p.map_b, g.B, g.K, g.N, g.ldb, TC_BK);
+    if (rc) return rc;
+    p.tiles_m = (g.M + TC_BM - 1) / TC_BM;
+    p.tiles_n = (g.N + BN - 1) / BN;
+    p.tile_start = tiles;
+    tiles += p.tiles_m * p.tiles_n;
+  }
+  grp.num_problems = n;
+  grp.total_tiles = tiles;
+  grp.mn_lbo = ctx->mn_lbo;
+  grp.mn_sbo = ctx->mn_sbo;
+  grp.error_flag = nullptr;
+  static bool attr_set[2] = {false, false};
+  const int ai = (BN == 256) ? 0 : 1;
+  if (!attr_set[ai]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(gemm_tc)");
+    attr_set[ai] = true;
+  }
+  int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
+  ctx->launches++;
+  return check_cuda(ctx, cudaGetLastError(), "gemm_tc");
+}
+
+int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
+  if (n < 1 || n > TC_MAX_PROBLEMS) return PSGD_ERR_INVALID_ARG;
+  int max_n = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!tc_eligible(gs[i])) return PSGD_ERR_UNSUPPORTED;
+    if (gs[i].N > max_n) max_n = gs[i].N;
+  }
+  TcGroup grp;
+  memset(&grp, 0, sizeof(grp));
+  if (max_n > 128) return launch_tc<256>(ctx, grp, gs, n, st);
+  return launch_tc<128>(ctx, grp, gs, n, st);
+}
+
+}  // namespace psgd

@@ -1,0 +1,290 @@
+// kron_kernels.cuh -- the bandwidth-bound kernels of the Kron path (everything that is not a big GEMM).
+// Each kernel cites the reference lines it implements. All are stream-ordered and branch on device scalars
+// only (no host synchronisation anywhere in an update, cf. SURVEY.md 7 hard part 7).
+#pragma once
+#include "common.cuh"
+
+namespace psgd {
+
+// slots of the per-bound scalar block (floats)
+enum { SC_INV_NF = 0, SC_NF = 1, SC_J = 2, SC_BOUND = 3, SC_COUNT = 8 };
+// slots of the per-factor update scalars
+enum { FS_ALPHA = 0, FS_BETA = 1, FS_INV_SR = 2, FS_TR1 = 3, FS_TR2 = 4, FS_COUNT = 8 };
+
+// G' = G + (damping + eps*|G|) * N     psgd.py:402-403
+template <typename T>
+__global__ void k_add_noise(const T* __restrict__ G, const T* __restrict__ Nz, T* __restrict__ out, size_t numel,
+                            float damping, float eps) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride) {
+    float g = to_f<T>(G[i]);
+    // the reference rounds (damping + eps|G|) and the product to the tensor dtype before the add
+    float d = to_f<T>(from_f<T>(damping + to_f<T>(from_f<T>(eps * fabsf(g)))));
+    float dn = to_f<T>(from_f<T>(d * to_f<T>(Nz[i])));
+    out[i] = from_f<T>(g + dn);
+  }
+}
+
+// q2[i] = float(q[i])^2  (diagonal factor applied twice: Q^T Q)   psgd.py:327 with 1-D q
+template <typename T>
+__global__ void k_square_to_f32(const T* __restrict__ q, float* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float v = to_f<T>(q[i]); out[i] = v * v; }
+}
+
+// out[i,j] = X[i,j] * rs[i] * cs[j] (+ reductions). Used when no dense factor exists (1-D tensors, diag x diag).
+template <typename T>
+__global__ void k_scale2d(const T* __restrict__ X, T* __restrict__ out, int m, int n, const float* __restrict__ rs,
+                          const float* __restrict__ cs, float* row_sumsq, float* col_sumsq, float* total_sumsq) {
+  size_t numel = (size_t)m * n;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  float tot = 0.f;
+  for (; i < numel; i += stride) {
+    int r = (int)(i / n), c = (int)(i % n);
+    float v = to_f<T>(X[i]) * (rs ? rs[r] : 1.f) * (cs ? cs[c] : 1.f);
+    T o = from_f<T>(v);
+    out[i] = o;
+    float f = to_f<T>(o);
+    tot += f * f;
+    if (row_sumsq) atomicAdd(&row_sumsq[r], f * f);
+    if (col_sumsq) atomicAdd(&col_sumsq[c], f * f);
+  }
+  if (total_sumsq) { tot = warp_sum(tot); if ((threadIdx.x & 31) == 0) atomicAdd(total_sumsq, tot); }
+}
+
+// R = Q^T - Q  (psgd.py:117) with max|R| (psgd.py:84) and row sums of squares (psgd.py:86) fused.
+// 32x32 tiles, block (32, 8).
+template <typename T>
+__global__ void k_skew(const T* __restrict__ Q, T* __restrict__ R, int s, float* abs_max, float* row_sumsq) {
+  __shared__ float tA[32][33];
+  __shared__ float tB[32][33];
+  __shared__ float red[32];
+  int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  int tx = threadIdx.x, ty = threadIdx.y;
+  for (int y = ty; y < 32; y += 8) {
+    int i = i0 + y, j = j0 + tx;
+    tA[y][tx] = (i < s && j < s) ? to_f<T>(Q[(size_t)i * s + j]) : 0.f;
+    int i2 = j0 + y, j2 = i0 + tx;
+    tB[y][tx] = (i2 < s && j2 < s) ? to_f<T>(Q[(size_t)i2 * s + j2]) : 0.f;
+  }
+  __syncthreads();
+  float am = 0.f;
+  for (int y = ty; y < 32; y += 8) {
+    int i = i0 + y, j = j0 + tx;
+    float r = tB[tx][y] - tA[y][tx];
+    T o = from_f<T>(r);
+    float f = to_f<T>(o);
+    if (i < s && j < s) R[(size_t)i * s + j] = o; else f = 0.f;
+    am = fmaxf(am, fabsf(f));
+    float rsq = warp_sum(f * f);
+    if (tx == 0 && i < s && row_sumsq) atomicAdd(&row_sumsq[i], rsq);
+  }
+  am = warp_max(am);
+  if (tx == 0) red[ty] = am;
+  __syncthreads();
+  if (ty == 0) {
+    float v = tx < 8 ? red[tx] : 0.f;
+    v = warp_max(v);
+    if (tx == 0 && abs_max) atomic_max_nonneg(abs_max, v);
+  }
+}
+
+// j = argmax_i rowsumsq[i]; nf = *nf_src + tiny   (psgd.py:58-61 / 83-86). One block.
+__global__ void k_bound_prep(const float* __restrict__ row_sumsq, int s, const float* __restrict__ nf_src, float tiny,
+                             float* scal) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  float best = -1.f;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) {
+    float v = row_sumsq[i];
+    if (v > best) { best = v; bi = i; }  // first occurrence within this thread's strided subsequence
+  }
+  // warp argmax (ties -> smallest index, torch.argmax returns the first maximal element)
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    best = lane < nw ? sv[lane] : -1.f;
+    bi = lane < nw ? si[lane] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      float nf = *nf_src + tiny;
+      scal[SC_NF] = nf;
+      scal[SC_INV_NF] = 1.f / nf;
+      reinterpret_cast<int*>(scal)[SC_J] = (bi == 0x7fffffff) ? 0 : bi;
+    }
+  }
+}
+
+// V[p,:] = A[j,:]/nf + sgn(<A[j,:]/nf, V0[p,:]>) * V0[p,:]     psgd.py:62-63. grid = k (one block per probe row)
+template <typename T>
+__global__ void k_probe_init(const T* __restrict__ A, int s, const T* __restrict__ V0, const float* __restrict__ scal,
+                             T* __restrict__ V) {
+  __shared__ float red[32];
+  __shared__ float sgn_s;
+  const int p = blockIdx.x;
+  const int j = reinterpret_cast<const int*>(scal)[SC_J];
+  const float inv_nf = scal[SC_INV_NF];
+  const T* arow = A + (size_t)j * s;
+  const T* v0 = V0 + (size_t)p * s;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < s; c += blockDim.x) {
+    float a = to_f<T>(from_f<T>(to_f<T>(arow[c]) * inv_nf));
+    dot += to_f<T>(from_f<T>(a * to_f<T>(v0[c])));
+  }
+  dot = block_sum(dot, red);
+  if (threadIdx.x == 0) sgn_s = (dot > 0.f) ? 1.f : ((dot < 0.f) ? -1.f : 0.f);
+  __syncthreads();
+  const float sg = sgn_s;
+  for (int c = threadIdx.x; c < s; c += blockDim.x) {
+    float a = to_f<T>(from_f<T>(to_f<T>(arow[c]) * inv_nf));
+    V[(size_t)p * s + c] = from_f<T>(a + sg * to_f<T>(v0[c]));
+  }
+}
+
+// sc[p] = inv_nf / (sqrt(rn[p]) + tiny): normalisation of psgd.py:66 folded with the /nf of the next product
+__global__ void k_rowscale(const float* __restrict__ rn, const float* __restrict__ scal, float tiny, float* sc, int k) {
+  int p = threadIdx.x;
+  if (p < k) sc[p] = scal[SC_INV_NF] / (sqrtf(rn[p]) + tiny);
+}
+
+// bound = nf * max_p sqrt(rn[p])   psgd.py:68.  mode 0: just store.  One warp.
+__global__ void k_bound_final(const float* __restrict__ rn, int k, float* scal, int dtype) {
+  float v = threadIdx.x < k ? rn[threadIdx.x] : 0.f;
+  v = warp_max(v);
+  if (threadIdx.x == 0) scal[SC_BOUND] = round_to(dtype, scal[SC_NF] * round_to(dtype, sqrtf(v)));
+}
+
+// dense factor: ell = bound + t2; L = max(betaL*L + (1-betaL)*ell, ell); c = lr/L   psgd.py:412-415
+//   fs[FS_ALPHA] = -c, fs[FS_BETA] = 1 + c*t2   so that  Q' = beta*Q + alpha*(term1 @ Q)
+__global__ void k_dense_L_update(const float* __restrict__ bound_scal, float t2, float lr, float betaL, float* L, float* fs,
+                                 int dtype) {
+  if (threadIdx.x == 0) {
+    float ell = round_to(dtype, bound_scal[SC_BOUND] + t2);
+    float Lo = *L;
+    float Ln = fmaxf(betaL * Lo + (1.f - betaL) * ell, ell);
+    *L = Ln;
+    float c = lr / Ln;
+    fs[FS_ALPHA] = -c;
+    fs[FS_BETA] = 1.f + c * t2;
+  }
+}
+
+// inv_sR = 1 / (bound(R) + tiny)    psgd.py:118
+__global__ void k_procrustes_scal(const float* __restrict__ bound_scal, float tiny, float* fs) {
+  if (threadIdx.x == 0) fs[FS_INV_SR] = 1.f / (bound_scal[SC_BOUND] + tiny);
+}
+
+// a = tr_RRQ < 0 ? min(-tr_RQ/tr_RRQ, max_step) : max_step;  Q = Qn + a*(RQ + 0.5*a*RRQ)   psgd.py:121-124
+template <typename T>
+__global__ void k_procrustes_finish(const T* __restrict__ Qn, const T* __restrict__ RQ, const T* __restrict__ RRQ,
+                                    T* __restrict__ Q, size_t numel, const float* __restrict__ fs, float max_step) {
+  float tr1 = fs[FS_TR1], tr2 = fs[FS_TR2];
+  float a = (tr2 < 0.f) ? fminf(-tr1 / tr2, max_step) : max_step;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride)
+    Q[i] = from_f<T>(to_f<T>(Qn[i]) + a * (to_f<T>(RQ[i]) + 0.5f * a * to_f<T>(RRQ[i])));
+}
+
+// diagonal factor (psgd.py:406-410): ell = max(term1) + t2; L = max(betaL*L+(1-betaL)*ell, ell);
+// q *= 1 - lr/L*(term1 - t2).  term1 (fp32, length s) = sums of squares of Pg along the other axes.  One block.
+template <typename T>
+__global__ void k_diag_update(T* __restrict__ q, const float* __restrict__ term1, int s, float t2, float lr, float betaL,
+                              float* L) {
+  __shared__ float red[32];
+  __shared__ float c_s;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) mx = fmaxf(mx, to_f<T>(from_f<T>(term1[i])));
+  mx = block_max(mx, red);
+  if (threadIdx.x == 0) {
+    float ell = to_f<T>(from_f<T>(mx + t2));
+    float Ln = fmaxf(betaL * (*L) + (1.f - betaL) * ell, ell);
+    *L = Ln;
+    c_s = lr / Ln;
+  }
+  __syncthreads();
+  const float c = c_s;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) {
+    float t1 = to_f<T>(from_f<T>(term1[i]));
+    q[i] = from_f<T>(to_f<T>(q[i]) * (1.f - c * (t1 - t2)));
+  }
+}
+
+// max |x| over a tensor (balance_kron_precond psgd.py:272)
+template <typename T>
+__global__ void k_absmax(const T* __restrict__ x, size_t numel, float* out) {
+  __shared__ float red[32];
+  float m = 0.f;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride) m = fmaxf(m, fabsf(to_f<T>(x[i])));
+  m = block_max(m, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(out, m);
+}
+
+// q *= gmean / norm_self, gmean = sqrt(norm_a * norm_b)   psgd.py:273-275 (order-2 Q)
+template <typename T>
+__global__ void k_balance_scale(T* __restrict__ q, size_t numel, const float* __restrict__ norm_self,
+                                const float* __restrict__ norm_other, int dtype) {
+  float ns = round_to(dtype, *norm_self), no = round_to(dtype, *norm_other);
+  float g = round_to(dtype, sqrtf(round_to(dtype, ns * no)));
+  float f = round_to(dtype, g / ns);
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride) q[i] = from_f<T>(to_f<T>(q[i]) * f);
+}
+
+// ------------------------------ KWNS4 glue (ddp.py:117-157) ------------------------------
+// weight decay + cast + EMA, one pass.   TP: param dtype, TG: grad dtype, TQ: preconditioner dtype
+template <typename TP, typename TG, typename TQ>
+__global__ void k_kwns4_head(TP* __restrict__ p, const TG* __restrict__ grad, size_t numel, float wd, float lr_params,
+                             int decoupled, TQ* __restrict__ ema, TQ* __restrict__ g_out, float beta) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride) {
+    float g = to_f<TG>(grad[i]);
+    if (wd > 0.f) {
+      if (decoupled) p[i] = from_f<TP>(to_f<TP>(p[i]) * (1.f - wd * lr_params));   // ddp.py:120
+      else g = to_f<TG>(from_f<TG>(g + wd * to_f<TP>(p[i])));                     // ddp.py:122
+    }
+    TQ gq = from_f<TQ>(g);                                                         // ddp.py:127
+    if (g_out) g_out[i] = gq;
+    if (ema) {                                                                     // ddp.py:142
+      float e = to_f<TQ>(from_f<TQ>(to_f<TQ>(ema[i]) * beta));
+      ema[i] = from_f<TQ>(e + (1.f - beta) * to_f<TQ>(gq));
+    }
+  }
+}
+
+// clip + clamp + parameter update (ddp.py:153-157)
+template <typename TP, typename TQ>
+__global__ void k_kwns4_tail(TP* __restrict__ p, TQ* __restrict__ h, size_t numel, const float* __restrict__ sumsq,
+                             float max_avg_amp, float max_elem_amp, float lr_params, int h_dtype) {
+  float avg_amp = round_to(h_dtype, sqrtf(round_to(h_dtype, *sumsq / (float)numel)));
+  float scale = (avg_amp > max_avg_amp) ? round_to(h_dtype, max_avg_amp / avg_amp) : 1.f;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride) {
+    float v = to_f<TQ>(h[i]);
+    if (scale != 1.f) v = to_f<TQ>(from_f<TQ>(v * scale));
+    v = fminf(fmaxf(v, -max_elem_amp), max_elem_amp);
+    h[i] = from_f<TQ>(v);
+    p[i] = from_f<TP>(to_f<TP>(p[i]) - lr_params * v);
+  }
+}
+
+}  // namespace psgd

@@ -1,0 +1,701 @@
+// lra.cu -- LRA preconditioner Q = (I + U V^T) diag(d)   (psgd.py:987-1072), HBM-streaming formulation.
+//
+// The reference makes ~25 separate passes over the n x r factors.  Here one update is
+//   sweep 1 (read U,V,h,v,d):  r x r Grams U^T U, V^T V, V^T U and the r-vectors U^T x, V^T x for x in {d.h, v/d}
+//   small   (one CTA, fp32):   everything of size r -- balancing rotation, LU solves, Lipschitz constants, step --
+//                              follows algebraically from the sweep-1 products
+//   sweep 2 (read+write U,V):  balancing rotation U<-U Au, V<-V Av fused with the rank-2 update of U or V and with
+//                              the per-row quantities of the d update
+//   d pass  (n-vector only)
+// and the apply is three row sweeps (V, U, V).  fp32 arithmetic throughout; storage dtype bf16 or fp32.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace psgd {
+
+// ---- parameter block produced by the small kernel, consumed by sweep 2 (floats) ----
+// layout for padded rank RP:  [Au RP*RP][Av RP*RP][vec 0..11 each RP][scalars 16]
+enum { LV_AUC1 = 0, LV_AVC2, LV_AVS1, LV_AUS2, LV_AVATU, LV_AVBTU, LV_WA, LV_WB, LV_ATU, LV_BTU, LV_P1, LV_P2, LV_NVEC };
+enum { LS_STEP = 0, LS_STEP_D = 1, LS_MAX_PHH = 2, LS_MAX_VINV = 3, LS_NSCAL = 16 };
+// accumulator block of sweep 1 (floats): [UtU RP*RP][VtV RP*RP][VtU RP*RP][Utx1 RP][Vtx1 RP][Utx2 RP][Vtx2 RP][x1sq][x2sq]
+
+__host__ __device__ inline size_t lra_acc_floats(int RP) { return (size_t)3 * RP * RP + 4 * RP + 2; }
+__host__ __device__ inline size_t lra_par_floats(int RP) { return (size_t)2 * RP * RP + (size_t)LV_NVEC * RP + LS_NSCAL; }
+
+template <typename T, int RP>
+__device__ __forceinline__ void load_row(const T* __restrict__ base, long long row, int r, float* x) {
+  const T* p = base + row * (long long)r;
+  if (r == RP && (RP * sizeof(T)) % 16 == 0) {
+    constexpr int NV = (RP * sizeof(T)) / 16;
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      uint4 u = reinterpret_cast<const uint4*>(p)[q];
+      const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+      for (int t = 0; t < PER; ++t) x[q * PER + t] = to_f<T>(e[t]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < RP; ++c) x[c] = (c < r) ? to_f<T>(p[c]) : 0.f;
+  }
+}
+template <typename T, int RP>
+__device__ __forceinline__ void store_row(T* __restrict__ base, long long row, int r, const float* x) {
+  T* p = base + row * (long long)r;
+  if (r == RP && (RP * sizeof(T)) % 16 == 0) {
+    constexpr int NV = (RP * sizeof(T)) / 16;
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      uint4 u;
+      T* e = reinterpret_cast<T*>(&u);
+#pragma unroll
+      for (int t = 0; t < PER; ++t) e[t] = from_f<T>(x[q * PER + t]);
+      reinterpret_cast<uint4*>(p)[q] = u;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < RP; ++c)
+      if (c < r) p[c] = from_f<T>(x[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep 1: Grams and projections.  256 threads; tiles of 64 rows staged in smem as fp32; each thread owns 4x4
+// blocks of the three RP x RP Grams (register tiling) and, for tid < 4*RP, one entry of the projection vectors.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RP>
+__global__ void __launch_bounds__(256) k_lra_sweep1(const T* __restrict__ U, const T* __restrict__ V, const T* __restrict__ d,
+                                                    const T* __restrict__ hvec, const T* __restrict__ vvec, long long n, int r,
+                                                    float* __restrict__ acc_out) {
+  constexpr int TR = 64;
+  constexpr int LD = RP + 4;  // keeps float4 alignment, skews banks
+  __shared__ __align__(16) float Us[TR][LD];
+  __shared__ __align__(16) float Vs[TR][LD];
+  __shared__ float x1s[TR], x2s[TR];
+  constexpr int NT = RP / 4;                 // 4x4 tiles per side
+  constexpr int TILES = 3 * NT * NT;         // over the three Grams
+  constexpr int PER = (TILES + 255) / 256;   // tiles per thread
+  float acc[PER][16];
+#pragma unroll
+  for (int t = 0; t < PER; ++t)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[t][e] = 0.f;
+  float pv = 0.f;      // projection entry
+  float sq1 = 0.f, sq2 = 0.f;
+  const int tid = threadIdx.x;
+  const long long ntiles = (n + TR - 1) / TR;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TR;
+    __syncthreads();
+    // stage: thread-per-row loads (64 rows -> threads 0..63 load U, 64..127 load V, 128..191 the vectors)
+    if (tid < TR) {
+      long long row = row0 + tid;
+      float x[RP];
+      if (row < n) load_row<T, RP>(U, row, r, x); else {
+#pragma unroll
+        for (int c = 0; c < RP; ++c) x[c] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < RP; ++c) Us[tid][c] = x[c];
+    } else if (tid < 2 * TR) {
+      int rr = tid - TR;
+      long long row = row0 + rr;
+      float x[RP];
+      if (row < n) load_row<T, RP>(V, row, r, x); else {
+#pragma unroll
+        for (int c = 0; c < RP; ++c) x[c] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < RP; ++c) Vs[rr][c] = x[c];
+    } else if (tid < 3 * TR) {
+      int rr = tid - 2 * TR;
+      long long row = row0 + rr;
+      float a = 0.f, b = 0.f;
+      if (row < n) {
+        float dd = to_f<T>(d[row]);
+        a = to_f<T>(from_f<T>(dd * to_f<T>(hvec[row])));   // d*h   psgd.py:1017
+        b = to_f<T>(from_f<T>(to_f<T>(vvec[row]) / dd));   // v/d   psgd.py:1022
+      }
+      x1s[rr] = a; x2s[rr] = b;
+      sq1 += a * a; sq2 += b * b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+      const int tl = tid + t * 256;
+      if (tl < TILES) {
+        const int which = tl / (NT * NT);
+        const int ij = tl - which * NT * NT;
+        const int ti = ij / NT, tj = ij - ti * NT;
+        const float(*A)[LD] = (which == 0) ? Us : Vs;   // UtU: U,U ; VtV: V,V ; VtU: V,U
+        const float(*B)[LD] = (which == 1) ? Vs : Us;
+#pragma unroll 4
+        for (int rr = 0; rr < TR; ++rr) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&A[rr][ti * 4]);
+          const float4 b4 = *reinterpret_cast<const float4*>(&B[rr][tj * 4]);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i * 4 + j] = fmaf(av[i], bv[j], acc[t][i * 4 + j]);
+        }
+      }
+    }
+    if (tid < 4 * RP) {
+      const int which = tid / RP, c = tid - which * RP;   // 0: U^T x1, 1: V^T x1, 2: U^T x2, 3: V^T x2
+      const float(*A)[LD] = (which & 1) ? Vs : Us;
+      const float* xs = (which & 2) ? x2s : x1s;
+      float s = 0.f;
+#pragma unroll 8
+      for (int rr = 0; rr < TR; ++rr) s = fmaf(A[rr][c], xs[rr], s);
+      pv += s;
+    }
+  }
+  // flush
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const int tl = tid + t * 256;
+    if (tl < TILES) {
+      const int which = tl / (NT * NT);
+      const int ij = tl - which * NT * NT;
+      const int ti = ij / NT, tj = ij - ti * NT;
+      float* G = acc_out + (size_t)which * RP * RP;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&G[(ti * 4 + i) * RP + tj * 4 + j], acc[t][i * 4 + j]);
+    }
+  }
+  if (tid < 4 * RP) atomicAdd(&acc_out[(size_t)3 * RP * RP + tid], pv);
+  if (tid >= 2 * 64 && tid < 3 * 64) {
+    float a = warp_sum(sq1), b = warp_sum(sq2);
+    if ((tid & 31) == 0) { atomicAdd(&acc_out[(size_t)3 * RP * RP + 4 * RP], a); atomicAdd(&acc_out[(size_t)3 * RP * RP + 4 * RP + 1], b); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernel: one CTA, all r x r / r-vector algebra in fp32 in shared memory  (psgd.py:1006-1052)
+// ------------------------------------------------------------------------------------------------
+__device__ inline void mm_small(const float* A, const float* B, float* Cm, int r, int RP, bool ta, bool tb) {
+  // C = op(A) op(B), all RP-strided r x r, block-cooperative
+  for (int e = threadIdx.x; e < r * r; e += blockDim.x) {
+    int i = e / r, j = e - i * r;
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(ta ? A[k * RP + i] : A[i * RP + k], tb ? B[j * RP + k] : B[k * RP + j], s);
+    Cm[i * RP + j] = s;
+  }
+  __syncthreads();
+}
+__device__ inline void mv_small(const float* A, const float* x, float* y, int r, int RP, bool ta) {
+  for (int i = threadIdx.x; i < r; i += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(ta ? A[k * RP + i] : A[i * RP + k], x[k], s);
+    y[i] = s;
+  }
+  __syncthreads();
+}
+__device__ inline float dot_small(const float* a, const float* b, int r) {  // every thread computes it (r <= 64)
+  float s = 0.f;
+  for (int k = 0; k < r; ++k) s = fmaf(a[k], b[k], s);
+  return s;
+}
+
+// grid 1, block 256. dyn smem: 8 RPxRP matrices + 24 vectors
+__global__ void k_lra_small(const float* __restrict__ acc, float* __restrict__ par, int r, int RP, float lr, float betaL, int update_U,
+                            float* Lu, float* Lv, int dtype) {
+  extern __shared__ float sm[];
+  const int MM = RP * RP;
+  float* Guu = sm; float* Gvv = Guu + MM; float* Gvu = Gvv + MM; float* E = Gvu + MM; float* Au = E + MM; float* Av = Au + MM;
+  float* T1 = Av + MM; float* Mx = T1 + MM;   // Mx = I + V'^T U'
+  float* vec = Mx + MM;
+  float* Utx1 = vec; float* Vtx1 = vec + RP; float* Utx2 = vec + 2 * RP; float* Vtx2 = vec + 3 * RP;
+  float* c1 = vec + 4 * RP; float* c2 = vec + 5 * RP; float* s1 = vec + 6 * RP; float* s2 = vec + 7 * RP;
+  float* t = vec + 8 * RP; float* atX = vec + 9 * RP; float* btX = vec + 10 * RP; float* tmp = vec + 11 * RP;
+  float* tmp2 = vec + 12 * RP; float* upx1 = vec + 13 * RP; float* upx2 = vec + 14 * RP; float* vpx2 = vec + 15 * RP;
+  __shared__ int piv[64];
+  __shared__ float LUm[64 * 64];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 3 * MM; e += blockDim.x) sm[e] = acc[e];
+  for (int e = tid; e < 4 * RP; e += blockDim.x) vec[e] = acc[3 * MM + e];
+  __syncthreads();
+  const float x1sq = acc[3 * MM + 4 * RP], x2sq = acc[3 * MM + 4 * RP + 1];
+  // --- balancing (psgd.py:1006-1015) ---
+  float trU = 0.f, trV = 0.f;
+  for (int k = 0; k < r; ++k) { trU += Guu[k * RP + k]; trV += Gvv[k * RP + k]; }
+  const float rho = sqrtf(sqrtf(trU / trV));
+  const float rho2 = rho * rho;
+  const float den = trU / rho2 + trV * rho2;
+  for (int e = tid; e < r * r; e += blockDim.x) {
+    int i = e / r, j = e - i * r;
+    E[i * RP + j] = 0.1f * (Guu[i * RP + j] / rho2 - Gvv[i * RP + j] * rho2) / den;
+  }
+  __syncthreads();
+  mm_small(E, E, T1, r, RP, false, false);  // T1 = E E
+  for (int e = tid; e < r * r; e += blockDim.x) {
+    int i = e / r, j = e - i * r;
+    float idn = (i == j) ? 1.f : 0.f;
+    float e1 = E[i * RP + j], e2 = 0.5f * T1[i * RP + j];
+    Au[i * RP + j] = (idn - e1 + e2) / rho;   // U' = (U/rho)(I - E + E2)
+    Av[i * RP + j] = (idn + e1 + e2) * rho;   // V' = (V rho)(I + E + E2)
+  }
+  __syncthreads();
+  // balanced Grams: G'uu = Au^T Guu Au etc. (reuse E as scratch)
+  mm_small(Guu, Au, T1, r, RP, false, false); mm_small(Au, T1, E, r, RP, true, false);
+  for (int e = tid; e < r * r; e += blockDim.x) { int i = e / r, j = e - i * r; Guu[i * RP + j] = E[i * RP + j]; }
+  __syncthreads();
+  mm_small(Gvv, Av, T1, r, RP, false, false); mm_small(Av, T1, E, r, RP, true, false);
+  for (int e = tid; e < r * r; e += blockDim.x) { int i = e / r, j = e - i * r; Gvv[i * RP + j] = E[i * RP + j]; }
+  __syncthreads();
+  mm_small(Gvu, Au, T1, r, RP, false, false); mm_small(Av, T1, E, r, RP, true, false);
+  for (int e = tid; e < r * r; e += blockDim.x) {
+    int i = e / r, j = e - i * r;
+    Gvu[i * RP + j] = E[i * RP + j];
+    Mx[i * RP + j] = E[i * RP + j] + ((i == j) ? 1.f : 0.f);   // IpVtU  psgd.py:1020-1021
+  }
+  __syncthreads();
+  // projections of the balanced factors
+  mv_small(Au, Utx1, upx1, r, RP, true);   // U'^T x1
+  mv_small(Av, Vtx1, c1, r, RP, true);     // c1 = V'^T x1          (Qh = x1 + U' c1)
+  mv_small(Au, Utx2, upx2, r, RP, true);   // U'^T x2
+  mv_small(Av, Vtx2, vpx2, r, RP, true);   // V'^T x2
+  mv_small(Guu, c1, tmp, r, RP, false);
+  for (int i = tid; i < r; i += blockDim.x) c2[i] = upx1[i] + tmp[i];   // c2 = U'^T Qh   (Ph = d (Qh + V' c2))
+  __syncthreads();
+  // --- LU with partial pivoting of Mx (fp32; psgd.py:1023) ---
+  for (int e = tid; e < r * r; e += blockDim.x) { int i = e / r, j = e - i * r; LUm[i * 64 + j] = Mx[i * RP + j]; }
+  __syncthreads();
+  for (int k = 0; k < r; ++k) {
+    if (tid == 0) {
+      int p = k; float best = fabsf(LUm[k * 64 + k]);
+      for (int i = k + 1; i < r; ++i) { float v = fabsf(LUm[i * 64 + k]); if (v > best) { best = v; p = i; } }
+      piv[k] = p;
+    }
+    __syncthreads();
+    const int p = piv[k];
+    if (p != k) for (int j = tid; j < r; j += blockDim.x) { float a = LUm[k * 64 + j]; LUm[k * 64 + j] = LUm[p * 64 + j]; LUm[p * 64 + j] = a; }
+    __syncthreads();
+    const float pivv = LUm[k * 64 + k];
+    for (int i = k + 1 + tid; i < r; i += blockDim.x) LUm[i * 64 + k] /= pivv;
+    __syncthreads();
+    for (int e = tid; e < (r - k - 1) * (r - k - 1); e += blockDim.x) {
+      int i = k + 1 + e / (r - k - 1), j = k + 1 + e % (r - k - 1);
+      LUm[i * 64 + j] -= LUm[i * 64 + k] * LUm[k * 64 + j];
+    }
+    __syncthreads();
+  }
+  // s1 = Mx^{-T} (U'^T x2):  (P Mx = L Uu)  =>  Mx^T = Uu^T L^T P  => solve Uu^T y = b, L^T z = y, s1 = P^T z
+  if (tid == 0) {
+    float y[64];
+    for (int i = 0; i < r; ++i) { float s = upx2[i]; for (int k = 0; k < i; ++k) s -= LUm[k * 64 + i] * y[k]; y[i] = s / LUm[i * 64 + i]; }
+    for (int i = r - 1; i >= 0; --i) { float s = y[i]; for (int k = i + 1; k < r; ++k) s -= LUm[k * 64 + i] * y[k]; y[i] = s; }
+    for (int k = r - 1; k >= 0; --k) { int p = piv[k]; if (p != k) { float a = y[k]; y[k] = y[p]; y[p] = a; } }
+    for (int i = 0; i < r; ++i) s1[i] = y[i];
+  }
+  __syncthreads();
+  // t = V'^T invQtv = V'^T x2 - G'vv s1 ;  s2 = Mx^{-1} t
+  mv_small(Gvv, s1, tmp, r, RP, false);
+  for (int i = tid; i < r; i += blockDim.x) t[i] = vpx2[i] - tmp[i];
+  __syncthreads();
+  if (tid == 0) {
+    float y[64];
+    for (int i = 0; i < r; ++i) y[i] = t[i];
+    for (int k = 0; k < r; ++k) { int p = piv[k]; if (p != k) { float a = y[k]; y[k] = y[p]; y[p] = a; } }
+    for (int i = 0; i < r; ++i) { float s = y[i]; for (int k = 0; k < i; ++k) s -= LUm[i * 64 + k] * y[k]; y[i] = s; }
+    for (int i = r - 1; i >= 0; --i) { float s = y[i]; for (int k = i + 1; k < r; ++k) s -= LUm[i * 64 + k] * y[k]; y[i] = s / LUm[i * 64 + i]; }
+    for (int i = 0; i < r; ++i) s2[i] = y[i];
+  }
+  __syncthreads();
+  // ||a||^2 = ||x1 + U' c1||^2 ; ||b||^2 = ||x2 - V' s1||^2
+  mv_small(Guu, c1, tmp, r, RP, false);
+  const float na2 = x1sq + 2.f * dot_small(c1, upx1, r) + dot_small(c1, tmp, r);
+  __syncthreads();
+  mv_small(Gvv, s1, tmp, r, RP, false);
+  const float nb2 = x2sq - 2.f * dot_small(s1, vpx2, r) + dot_small(s1, tmp, r);
+  __syncthreads();
+  const float na = sqrtf(fmaxf(na2, 0.f)), nb = sqrtf(fmaxf(nb2, 0.f));
+  float* pvec = par + 2 * MM;
+  float* pscal = pvec + (size_t)LV_NVEC * RP;
+  if (update_U) {  // psgd.py:1036-1043
+    mv_small(Mx, c1, atX, r, RP, false);                 // atV = V'^T a = (I + V'^T U') c1
+    for (int i = tid; i < r; i += blockDim.x) btX[i] = t[i];   // btV = V'^T b
+    __syncthreads();
+    mv_small(Gvv, atX, tmp, r, RP, false);
+    const float n1 = sqrtf(fmaxf(dot_small(atX, tmp, r), 0.f));
+    __syncthreads();
+    mv_small(Gvv, btX, tmp, r, RP, false);
+    const float n2 = sqrtf(fmaxf(dot_small(btX, tmp, r), 0.f));
+    __syncthreads();
+    const float ell = round_to(dtype, na * n1 + nb * n2);
+    const float Ln = fmaxf(betaL * (*Lu) + (1.f - betaL) * ell, ell);
+    mv_small(Mx, atX, tmp, r, RP, true);    // w_a = atV Mx  (row vector) = Mx^T atV
+    mv_small(Mx, btX, tmp2, r, RP, true);
+    for (int i = tid; i < RP; i += blockDim.x) { pvec[LV_WA * RP + i] = i < r ? tmp[i] : 0.f; pvec[LV_WB * RP + i] = i < r ? tmp2[i] : 0.f; }
+    __syncthreads();
+    if (tid == 0) { *Lu = Ln; pscal[LS_STEP] = lr / Ln; }
+  } else {  // psgd.py:1045-1052
+    for (int i = tid; i < r; i += blockDim.x) atX[i] = c2[i];  // atU = U'^T a
+    mv_small(Gvu, s1, tmp, r, RP, true);                       // (V'^T U')^T s1 = U'^T V' s1
+    for (int i = tid; i < r; i += blockDim.x) btX[i] = upx2[i] - tmp[i];   // btU = U'^T b
+    __syncthreads();
+    mv_small(Guu, atX, tmp, r, RP, false);
+    const float n1 = sqrtf(fmaxf(dot_small(atX, tmp, r), 0.f));
+    __syncthreads();
+    mv_small(Guu, btX, tmp, r, RP, false);
+    const float n2 = sqrtf(fmaxf(dot_small(btX, tmp, r), 0.f));
+    __syncthreads();
+    const float ell = round_to(dtype, na * n1 + nb * n2);
+    const float Ln = fmaxf(betaL * (*Lv) + (1.f - betaL) * ell, ell);
+    for (int i = tid; i < RP; i += blockDim.x) { pvec[LV_ATU * RP + i] = i < r ? atX[i] : 0.f; pvec[LV_BTU * RP + i] = i < r ? btX[i] : 0.f; }
+    mv_small(Av, atX, tmp, r, RP, false);   // Av atU: V'_i . atU = V_i . (Av atU)
+    mv_small(Av, btX, tmp2, r, RP, false);
+    for (int i = tid; i < RP; i += blockDim.x) { pvec[LV_AVATU * RP + i] = i < r ? tmp[i] : 0.f; pvec[LV_AVBTU * RP + i] = i < r ? tmp2[i] : 0.f; }
+    __syncthreads();
+    if (tid == 0) { *Lv = Ln; pscal[LS_STEP] = lr / Ln; }
+  }
+  // row-dot vectors against the UNtransformed rows: U'_i . c = U_i . (Au c)
+  mv_small(Au, c1, tmp, r, RP, false);
+  for (int i = tid; i < RP; i += blockDim.x) pvec[LV_AUC1 * RP + i] = i < r ? tmp[i] : 0.f;
+  __syncthreads();
+  mv_small(Av, c2, tmp, r, RP, false);
+  for (int i = tid; i < RP; i += blockDim.x) pvec[LV_AVC2 * RP + i] = i < r ? tmp[i] : 0.f;
+  __syncthreads();
+  mv_small(Av, s1, tmp, r, RP, false);
+  for (int i = tid; i < RP; i += blockDim.x) pvec[LV_AVS1 * RP + i] = i < r ? tmp[i] : 0.f;
+  __syncthreads();
+  mv_small(Au, s2, tmp, r, RP, false);
+  for (int i = tid; i < RP; i += blockDim.x) pvec[LV_AUS2 * RP + i] = i < r ? tmp[i] : 0.f;
+  __syncthreads();
+  for (int e = tid; e < MM; e += blockDim.x) {
+    int i = e / RP, j = e - i * RP;
+    bool in = i < r && j < r;
+    par[e] = in ? Au[e] : 0.f;
+    par[MM + e] = in ? Av[e] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep 2: thread-per-row; rotation + rank-2 update of U or V; per-row terms of the d update
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RP>
+__global__ void __launch_bounds__(128) k_lra_sweep2(T* __restrict__ U, T* __restrict__ V, const T* __restrict__ d,
+                                                    const T* __restrict__ hvec, const T* __restrict__ vvec, long long n, int r,
+                                                    const float* __restrict__ par, int update_U, float* __restrict__ dd_out,
+                                                    float* __restrict__ scal_out) {
+  extern __shared__ __align__(16) float smp[];
+  float* Au = smp; float* Av = smp + RP * RP; float* pvec = Av + RP * RP;
+  __shared__ float red[32];
+  for (int e = threadIdx.x; e < 2 * RP * RP + LV_NVEC * RP; e += blockDim.x) smp[e] = par[e];
+  __syncthreads();
+  const float step = par[(size_t)2 * RP * RP + (size_t)LV_NVEC * RP + LS_STEP];
+  float mx1 = 0.f, mx2 = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < n; row += stride) {
+    float u[RP], v[RP];
+    load_row<T, RP>(U, row, r, u);
+    load_row<T, RP>(V, row, r, v);
+    const float dd = to_f<T>(d[row]);
+    const float hh = to_f<T>(hvec[row]);
+    const float vv = to_f<T>(vvec[row]);
+    const float x1 = to_f<T>(from_f<T>(dd * hh));
+    const float x2 = to_f<T>(from_f<T>(vv / dd));
+    float duc1 = 0.f, dvc2 = 0.f, dvs1 = 0.f, dus2 = 0.f, dva = 0.f, dvb = 0.f;
+#pragma unroll
+    for (int c = 0; c < RP; ++c) {
+      duc1 = fmaf(u[c], pvec[LV_AUC1 * RP + c], duc1);
+      dus2 = fmaf(u[c], pvec[LV_AUS2 * RP + c], dus2);
+      dvc2 = fmaf(v[c], pvec[LV_AVC2 * RP + c], dvc2);
+      dvs1 = fmaf(v[c], pvec[LV_AVS1 * RP + c], dvs1);
+    }
+    if (!update_U) {
+#pragma unroll
+      for (int c = 0; c < RP; ++c) { dva = fmaf(v[c], pvec[LV_AVATU * RP + c], dva); dvb = fmaf(v[c], pvec[LV_AVBTU * RP + c], dvb); }
+    }
+    const float a = x1 + duc1;                 // Qh_i            psgd.py:1017
+    const float Ph = dd * (a + dvc2);          // Ph_i            psgd.py:1018
+    const float b = x2 - dvs1;                 // invQtv_i        psgd.py:1024
+    const float invPv = (b - dus2) / dd;       // invPv_i         psgd.py:1025-1026
+    const float Phh = Ph * hh, vinv = vv * invPv;   // psgd.py:1029
+    mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
+    dd_out[row] = Phh - vinv;
+    // new rows, 4 output columns at a time (Au/Av read as broadcast float4)
+    const float ca = update_U ? step * a : step * (a + dva);
+    const float cb = update_U ? step * b : step * (b + dvb);
+    float o[RP];
+#pragma unroll
+    for (int c0 = 0; c0 < RP; c0 += 4) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < RP; ++k) {
+        const float4 m = *reinterpret_cast<const float4*>(&Au[k * RP + c0]);
+        s.x = fmaf(u[k], m.x, s.x); s.y = fmaf(u[k], m.y, s.y); s.z = fmaf(u[k], m.z, s.z); s.w = fmaf(u[k], m.w, s.w);
+      }
+      o[c0] = s.x; o[c0 + 1] = s.y; o[c0 + 2] = s.z; o[c0 + 3] = s.w;
+    }
+    if (update_U) {
+#pragma unroll
+      for (int c = 0; c < RP; ++c) o[c] -= ca * pvec[LV_WA * RP + c] - cb * pvec[LV_WB * RP + c];
+    }
+    store_row<T, RP>(U, row, r, o);
+#pragma unroll
+    for (int c0 = 0; c0 < RP; c0 += 4) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < RP; ++k) {
+        const float4 m = *reinterpret_cast<const float4*>(&Av[k * RP + c0]);
+        s.x = fmaf(v[k], m.x, s.x); s.y = fmaf(v[k], m.y, s.y); s.z = fmaf(v[k], m.z, s.z); s.w = fmaf(v[k], m.w, s.w);
+      }
+      o[c0] = s.x; o[c0 + 1] = s.y; o[c0 + 2] = s.z; o[c0 + 3] = s.w;
+    }
+    if (!update_U) {
+#pragma unroll
+      for (int c = 0; c < RP; ++c) o[c] -= ca * pvec[LV_ATU * RP + c] - cb * pvec[LV_BTU * RP + c];
+    }
+    store_row<T, RP>(V, row, r, o);
+  }
+  mx1 = block_max(mx1, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(&scal_out[LS_MAX_PHH], mx1);
+  mx2 = block_max(mx2, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(&scal_out[LS_MAX_VINV], mx2);
+}
+
+// Ld update + step (psgd.py:1030-1031)
+__global__ void k_lra_Ld(float* scal, float lr, float betaL, float* Ld, int dtype) {
+  if (threadIdx.x == 0) {
+    float ell = round_to(dtype, scal[LS_MAX_PHH] + scal[LS_MAX_VINV]);
+    float Ln = fmaxf(betaL * (*Ld) + (1.f - betaL) * ell, ell);
+    *Ld = Ln;
+    scal[LS_STEP_D] = lr / Ln;
+  }
+}
+// d -= lr/Ld * (Phh - vinvPv) * d   (psgd.py:1032)
+template <typename T>
+__global__ void k_lra_d_update(T* __restrict__ d, const float* __restrict__ dd, long long n, const float* __restrict__ scal) {
+  const float step = scal[LS_STEP_D];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float x = to_f<T>(d[i]);
+    d[i] = from_f<T>(x - step * to_f<T>(from_f<T>(dd[i])) * x);
+  }
+}
+// h = g + (damping + eps|g|) v   (psgd.py:1071-1072)
+template <typename T>
+__global__ void k_lra_damp(const T* __restrict__ g, const T* __restrict__ v, T* __restrict__ out, long long n, float damping, float eps) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gg = to_f<T>(g[i]);
+    float dmp = to_f<T>(from_f<T>(damping + to_f<T>(from_f<T>(eps * fabsf(gg)))));
+    out[i] = from_f<T>(gg + to_f<T>(from_f<T>(dmp * to_f<T>(v[i]))));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply (psgd.py:1055-1063): three thread-per-row sweeps
+//   mode 0: p1 += V_i * (d_i g_i)
+//   mode 1: g2_i = d_i g_i + U_i . p1 (stored fp32) ; p2 += U_i * g2_i
+//   mode 2: out_i = d_i * (g2_i + V_i . p2) ; sumsq
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RP>
+__global__ void __launch_bounds__(128) k_lra_apply(const T* __restrict__ Mtx, const T* __restrict__ d, const T* __restrict__ g,
+                                                   float* __restrict__ g2, T* __restrict__ out, long long n, int r, int mode,
+                                                   const float* __restrict__ pin, float* __restrict__ pout, float* sumsq) {
+  __shared__ float ps[RP];
+  __shared__ float accs[4][RP];
+  if (threadIdx.x < RP) ps[threadIdx.x] = (mode > 0 && threadIdx.x < r) ? pin[threadIdx.x] : 0.f;
+  __syncthreads();
+  float acc[RP];
+#pragma unroll
+  for (int c = 0; c < RP; ++c) acc[c] = 0.f;
+  float ssq = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < n; row += stride) {
+    float x[RP];
+    load_row<T, RP>(Mtx, row, r, x);
+    const float dd = to_f<T>(d[row]);
+    if (mode == 0) {
+      const float y = to_f<T>(from_f<T>(dd * to_f<T>(g[row])));
+#pragma unroll
+      for (int c = 0; c < RP; ++c) acc[c] = fmaf(x[c], y, acc[c]);
+    } else if (mode == 1) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < RP; ++c) dot = fmaf(x[c], ps[c], dot);
+      const float y = to_f<T>(from_f<T>(dd * to_f<T>(g[row]))) + dot;
+      g2[row] = y;
+#pragma unroll
+      for (int c = 0; c < RP; ++c) acc[c] = fmaf(x[c], y, acc[c]);
+    } else {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < RP; ++c) dot = fmaf(x[c], ps[c], dot);
+      T o = from_f<T>(dd * (g2[row] + dot));
+      out[row] = o;
+      float f = to_f<T>(o);
+      ssq = fmaf(f, f, ssq);
+    }
+  }
+  if (mode < 2) {
+    // block reduce the RP accumulators: warp shuffle then smem across the 4 warps
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < RP; ++c) {
+      float s = warp_sum(acc[c]);
+      if (lane == 0) accs[w][c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < RP && threadIdx.x < r) atomicAdd(&pout[threadIdx.x], accs[0][threadIdx.x] + accs[1][threadIdx.x] + accs[2][threadIdx.x] + accs[3][threadIdx.x]);
+  } else if (sumsq) {
+    float s = warp_sum(ssq);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sumsq, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct LraWs {
+  float* acc; float* par; float* p1; float* p2; float* dd; void* hbuf; char* zero_begin; size_t zero_bytes; size_t total; int RP;
+};
+static int pad_rank(int r) { int p = 4; while (p < r) p <<= 1; return p; }
+
+static void layout_lra(const psgd_lra_t* l, void* base, LraWs& w) {
+  char* b = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return b ? (void*)(b + o) : (void*)(o + 256); };
+  const int RP = pad_rank(l->r);
+  w.RP = RP;
+  w.zero_begin = (char*)take(0);
+  size_t z0 = off;
+  w.acc = (float*)take(lra_acc_floats(RP) * 4);
+  w.par = (float*)take(lra_par_floats(RP) * 4);
+  w.p1 = (float*)take(64 * 4);
+  w.p2 = (float*)take(64 * 4);
+  w.zero_bytes = off - z0;
+  w.dd = (float*)take((size_t)l->n * 4);
+  w.hbuf = take((size_t)l->n * dtype_size(l->dtype));
+  w.total = off;
+}
+
+#define LRA_DISPATCH(dt, RP, ...)                                                          \
+  do {                                                                                     \
+    if ((dt) == PSGD_BF16) { typedef bf16 T;                                               \
+      switch (RP) { case 4: { constexpr int R_ = 4; __VA_ARGS__; } break; case 8: { constexpr int R_ = 8; __VA_ARGS__; } break; \
+        case 16: { constexpr int R_ = 16; __VA_ARGS__; } break; case 32: { constexpr int R_ = 32; __VA_ARGS__; } break;         \
+        default: { constexpr int R_ = 64; __VA_ARGS__; } break; }                          \
+    } else { typedef float T;                                                              \
+      switch (RP) { case 4: { constexpr int R_ = 4; __VA_ARGS__; } break; case 8: { constexpr int R_ = 8; __VA_ARGS__; } break; \
+        case 16: { constexpr int R_ = 16; __VA_ARGS__; } break; case 32: { constexpr int R_ = 32; __VA_ARGS__; } break;         \
+        default: { constexpr int R_ = 64; __VA_ARGS__; } break; }                          \
+    }                                                                                      \
+  } while (0)
+
+static int validate_lra(const psgd_lra_t* l) {
+  if (!l || l->n < 1 || l->r < 1 || l->r > 64 || !l->U || !l->V || !l->d) return PSGD_ERR_INVALID_ARG;
+  if (l->dtype != PSGD_BF16 && l->dtype != PSGD_F32) return PSGD_ERR_INVALID_ARG;
+  return PSGD_OK;
+}
+
+static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const void* hv, float lr, float betaL, int update_U, LraWs& w,
+                           cudaStream_t st) {
+  const int dt = l->dtype, RP = w.RP, r = l->r;
+  const long long n = l->n;
+  int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+  long long tiles = (n + 63) / 64;
+  int grid1 = (int)(tiles < (long long)ctx->num_sms * 2 ? tiles : (long long)ctx->num_sms * 2);
+  LRA_DISPATCH(dt, RP, (k_lra_sweep1<T, R_><<<grid1, 256, 0, st>>>((const T*)l->U, (const T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.acc)));
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep1"); if (rc) return rc;
+  size_t smem_small = ((size_t)8 * RP * RP + 24 * RP) * 4;
+  static bool small_attr = false;
+  if (!small_attr) { cudaFuncSetAttribute(k_lra_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); small_attr = true; }
+  k_lra_small<<<1, 256, smem_small, st>>>(w.acc, w.par, r, RP, lr, betaL, update_U, l->Lu, l->Lv, dt);
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_small"); if (rc) return rc;
+  long long rows_blocks = (n + 127) / 128;
+  int grid2 = (int)(rows_blocks < (long long)ctx->num_sms * 8 ? rows_blocks : (long long)ctx->num_sms * 8);
+  size_t smem2 = ((size_t)2 * RP * RP + LV_NVEC * RP) * 4;
+  float* scal = w.par + (size_t)2 * RP * RP + (size_t)LV_NVEC * RP;
+  LRA_DISPATCH(dt, RP, {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_lra_sweep2<T, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    k_lra_sweep2<T, R_><<<grid2, 128, smem2, st>>>((T*)l->U, (T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.par, update_U, w.dd, scal);
+  });
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep2"); if (rc) return rc;
+  k_lra_Ld<<<1, 32, 0, st>>>(scal, lr, betaL, l->Ld, dt);
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_Ld"); if (rc) return rc;
+  int gridd = (int)(((n + 255) / 256) < (long long)ctx->num_sms * 8 ? ((n + 255) / 256) : (long long)ctx->num_sms * 8);
+  if (dt == PSGD_BF16) k_lra_d_update<bf16><<<gridd, 256, 0, st>>>((bf16*)l->d, w.dd, n, scal);
+  else k_lra_d_update<float><<<gridd, 256, 0, st>>>((float*)l->d, w.dd, n, scal);
+  ctx->launches++; return check_cuda(ctx, cudaGetLastError(), "k_lra_d_update");
+}
+
+}  // namespace psgd
+
+using namespace psgd;
+
+extern "C" {
+
+size_t psgd_lra_workspace_bytes(psgd_handle_t, const psgd_lra_t* l) {
+  if (validate_lra(l)) return 0;
+  LraWs w;
+  layout_lra(l, nullptr, w);
+  return w.total;
+}
+
+int psgd_lra_update(psgd_handle_t h, const psgd_lra_t* l, const void* v, const void* hvec, float lr, float betaL, int update_U,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !v || !hvec) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_lra(l); if (rc) return rc;
+  if (!l->Lu || !l->Lv || !l->Ld) return PSGD_ERR_INVALID_ARG;
+  LraWs w;
+  layout_lra(l, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  return lra_update_impl(ctx, l, v, hvec, lr, betaL, update_U, w, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int psgd_lra_whiten_update(psgd_handle_t h, const psgd_lra_t* l, const void* g, const void* v, float lr, float betaL, float damping,
+                           int update_U, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !v || !g) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_lra(l); if (rc) return rc;
+  if (!l->Lu || !l->Lv || !l->Ld) return PSGD_ERR_INVALID_ARG;
+  LraWs w;
+  layout_lra(l, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = l->n;
+  int grid = (int)(((n + 255) / 256) < (long long)ctx->num_sms * 8 ? ((n + 255) / 256) : (long long)ctx->num_sms * 8);
+  if (l->dtype == PSGD_BF16) k_lra_damp<bf16><<<grid, 256, 0, st>>>((const bf16*)g, (const bf16*)v, (bf16*)w.hbuf, n, damping, dtype_eps(PSGD_BF16));
+  else k_lra_damp<float><<<grid, 256, 0, st>>>((const float*)g, (const float*)v, (float*)w.hbuf, n, damping, dtype_eps(PSGD_F32));
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_damp"); if (rc) return rc;
+  return lra_update_impl(ctx, l, v, w.hbuf, lr, betaL, update_U, w, st);
+}
+
+int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, void* out, float* sumsq_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !g || !out) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_lra(l); if (rc) return rc;
+  LraWs w;
+  layout_lra(l, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int dt = l->dtype, RP = w.RP, r = l->r;
+  const long long n = l->n;
+  rc = check_cuda(ctx, cudaMemsetAsync(w.p1, 0, 64 * 4, st), "memset"); if (rc) return rc;
+  rc = check_cuda(ctx, cudaMemsetAsync(w.p2, 0, 64 * 4, st), "memset"); if (rc) return rc;
+  if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4, st), "memset"); if (rc) return rc; }
+  long long rb = (n + 127) / 128;
+  int grid = (int)(rb < (long long)ctx->num_sms * 8 ? rb : (long long)ctx->num_sms * 8);
+  LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->V, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 0, nullptr, w.p1, nullptr)));
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply0"); if (rc) return rc;
+  LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->U, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 1, w.p1, w.p2, nullptr)));
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply1"); if (rc) return rc;
+  LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->V, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 2, w.p2, nullptr, sumsq_out)));
+  ctx->launches++; return check_cuda(ctx, cudaGetLastError(), "k_lra_apply2");
+}
+
+}  // extern "C"
