@@ -155,26 +155,51 @@ static int run_bound(Ctx* ctx, int dt, const void* A, int s, const void* V0, con
   LAUNCH_CHECK(ctx, "k_bound_prep");
   DISPATCH_T(dt, (k_probe_init<T><<<32, 256, 0, st>>>((const T*)A, s, (const T*)V0, w.scal, (T*)Va)));
   LAUNCH_CHECK(ctx, "k_probe_init");
-  // W1 = V1 A / nf  (+ row norms)
-  GemmDesc g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
-  g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn1;
-  int rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  k_rowscale<<<1, 32, 0, st>>>(w.rn1, w.scal, tiny, w.sc1, 32);
-  LAUNCH_CHECK(ctx, "k_rowscale");
-  // W2 = (W1 / |W1|) A / nf
-  g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
-  g.epi.row_scale = w.sc1;
-  rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  // W3 = W2 A / nf (+ row norms)
-  g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
-  g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn3;
-  rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  k_rowscale<<<1, 32, 0, st>>>(w.rn3, w.scal, tiny, w.sc3, 32);
-  LAUNCH_CHECK(ctx, "k_rowscale");
-  // W4 = (W3 / |W3|) A / nf (+ row norms)
-  g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
-  g.epi.row_scale = w.sc3; g.epi.row_sumsq = w.rn4;
-  rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  int rc;
+  GemmDesc g;
+  const bool tc_form = ctx->gemm_path != 1 && dt == PSGD_BF16 && s >= 128 && (s % 8) == 0;
+  if (tc_form) {
+    // tensor-core formulation: keep the probes transposed, X = W^T (s x 32), X_new = A^T X: the s-long dimension is the
+    // UMMA M dimension, the 32 probes ride in N; A is read through MN-major descriptors, no transposed copy is made.
+    // probe norms are column sums of squares, the normalisation a column scale.
+    g = gemm_desc(dt, A, s, 1, Va, s, 1, s, 32, s, Vb, 32);                      // X1 = A^T V1^T / nf
+    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.col_sumsq = w.rn1;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    k_rowscale<<<1, 32, 0, st>>>(w.rn1, w.scal, tiny, w.sc1, 32);
+    LAUNCH_CHECK(ctx, "k_rowscale");
+    g = gemm_desc(dt, A, s, 1, Vb, 32, 0, s, 32, s, Va, 32);                     // X2 = A^T (X1 / |x1|) / nf
+    g.epi.col_scale = w.sc1;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    g = gemm_desc(dt, A, s, 1, Va, 32, 0, s, 32, s, Vb, 32);                     // X3 = A^T X2 / nf
+    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.col_sumsq = w.rn3;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    k_rowscale<<<1, 32, 0, st>>>(w.rn3, w.scal, tiny, w.sc3, 32);
+    LAUNCH_CHECK(ctx, "k_rowscale");
+    g = gemm_desc(dt, A, s, 1, Vb, 32, 0, s, 32, s, Va, 32);                     // X4 = A^T (X3 / |x3|) / nf
+    g.epi.col_scale = w.sc3; g.epi.col_sumsq = w.rn4;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  } else {
+    // W1 = V1 A / nf  (+ row norms)
+    g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
+    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn1;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    k_rowscale<<<1, 32, 0, st>>>(w.rn1, w.scal, tiny, w.sc1, 32);
+    LAUNCH_CHECK(ctx, "k_rowscale");
+    // W2 = (W1 / |W1|) A / nf
+    g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
+    g.epi.row_scale = w.sc1;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    // W3 = W2 A / nf (+ row norms)
+    g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
+    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn3;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    k_rowscale<<<1, 32, 0, st>>>(w.rn3, w.scal, tiny, w.sc3, 32);
+    LAUNCH_CHECK(ctx, "k_rowscale");
+    // W4 = (W3 / |W3|) A / nf (+ row norms)
+    g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
+    g.epi.row_scale = w.sc3; g.epi.row_sumsq = w.rn4;
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  }
   k_bound_final<<<1, 32, 0, st>>>(w.rn4, 32, w.scal, dt);
   LAUNCH_CHECK(ctx, "k_bound_final");
   return PSGD_OK;

@@ -158,7 +158,9 @@ __global__ void k_probe_init(const T* __restrict__ A, int s, const T* __restrict
 // sc[p] = inv_nf / (sqrt(rn[p]) + tiny): normalisation of psgd.py:66 folded with the /nf of the next product
 __global__ void k_rowscale(const float* __restrict__ rn, const float* __restrict__ scal, float tiny, float* sc, int k) {
   int p = threadIdx.x;
-  if (p < k) sc[p] = scal[SC_INV_NF] / (sqrtf(rn[p]) + tiny);
+  // rn == 0 means the whole probe row is exactly zero (e.g. R = Q^T - Q = 0 while Q is still symmetric): the reference
+  // computes 0/(0+tiny) = 0 there; keep the folded factor finite so that 0 * factor stays 0 instead of 0 * inf = NaN
+  if (p < k) sc[p] = fminf(scal[SC_INV_NF] / (sqrtf(rn[p]) + tiny), 3.0e38f);
 }
 
 // bound = nf * max_p sqrt(rn[p])   psgd.py:68.  mode 0: just store.  One warp.
