@@ -57,12 +57,14 @@ SYMBOLS = {
     "psgd_norm_lower_bound_skh": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "psgd_procrustes_step2": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _sz, _vp]),
     "psgd_kwns4_head": (_i, [_vp, _i64, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp, _i, _f, _vp]),
-    "psgd_kwns4_tail": (_i, [_vp, _i64, _vp, _i, _vp, _i, _vp, _f, _f, _f, _vp]),
+    "psgd_kwns4_tail": (_i, [_vp, _i64, _i64, _vp, _i, _vp, _i, _vp, _f, _f, _f, _vp]),
     "psgd_lra_workspace_bytes": (_sz, [_vp, C.POINTER(LraT)]),
     "psgd_lra_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _i, _vp, _sz, _vp]),
     "psgd_lra_whiten_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _f, _i, _vp, _sz, _vp]),
     "psgd_lra_precond_grad": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _vp, _vp, _sz, _vp]),
     "psgd_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _f, _vp, _i, _f, _vp]),
+    "psgd_timing_enable": (_i, [_vp, _i]),
+    "psgd_timing_read": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "psgd_debug_set_mn_desc": (_i, [_vp, _i, _i]),
 }
 

@@ -382,6 +382,35 @@ int psgd_set_gemm_path(psgd_handle_t h, int p) {
 
 int64_t psgd_launch_count(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->launches : 0; }
 
+int psgd_timing_enable(psgd_handle_t h, int on) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx) return PSGD_ERR_INVALID_ARG;
+  if (on && !ctx->ev_begin) {
+    ctx->ev_capacity = 8192;
+    ctx->ev_begin = new (std::nothrow) cudaEvent_t[ctx->ev_capacity];
+    ctx->ev_end = new (std::nothrow) cudaEvent_t[ctx->ev_capacity];
+    if (!ctx->ev_begin || !ctx->ev_end) return PSGD_ERR_CUDA;
+    for (int i = 0; i < ctx->ev_capacity; ++i) { cudaEventCreate(&ctx->ev_begin[i]); cudaEventCreate(&ctx->ev_end[i]); }
+  }
+  ctx->timing_on = on ? 1 : 0;
+  ctx->timing_count = 0;
+  ctx->timing_flops = 0.0;
+  return PSGD_OK;
+}
+
+int psgd_timing_read(psgd_handle_t h, int* launches, double* total_ms, double* flops) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !launches || !total_ms || !flops) return PSGD_ERR_INVALID_ARG;
+  double ms = 0.0;
+  for (int i = 0; i < ctx->timing_count; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->ev_begin[i], ctx->ev_end[i]) != cudaSuccess) return PSGD_ERR_CUDA;
+    ms += t;
+  }
+  *launches = ctx->timing_count; *total_ms = ms; *flops = ctx->timing_flops;
+  return PSGD_OK;
+}
+
 int psgd_debug_set_mn_desc(psgd_handle_t h, int lbo, int sbo) {
   if (!h) return PSGD_ERR_INVALID_ARG;
   reinterpret_cast<Ctx*>(h)->mn_lbo = lbo;
@@ -610,17 +639,17 @@ int psgd_kwns4_head(psgd_handle_t h, int64_t numel, void* p, int p_dtype, const 
   return head_dispatch_q<float, float>(ctx, numel, p, grad, weight_decay, lr_params, decoupled, ema, g_out, pre_dtype, beta, st);
 }
 
-int psgd_kwns4_tail(psgd_handle_t h, int64_t numel, void* p, int p_dtype, void* hbuf, int h_dtype, const float* sumsq,
+int psgd_kwns4_tail(psgd_handle_t h, int64_t numel, int64_t amp_numel, void* p, int p_dtype, void* hbuf, int h_dtype, const float* sumsq,
                     float max_avg_amp, float max_elem_amp, float lr_params, void* stream) {
   Ctx* ctx = reinterpret_cast<Ctx*>(h);
   if (!ctx || numel < 0 || !p || !hbuf || !sumsq) return PSGD_ERR_INVALID_ARG;
   if (numel == 0) return PSGD_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int blocks = ew_blocks(ctx, (size_t)numel);
-  if (p_dtype == PSGD_BF16 && h_dtype == PSGD_BF16) k_kwns4_tail<bf16, bf16><<<blocks, 256, 0, st>>>((bf16*)p, (bf16*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
-  else if (p_dtype == PSGD_BF16) k_kwns4_tail<bf16, float><<<blocks, 256, 0, st>>>((bf16*)p, (float*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
-  else if (h_dtype == PSGD_BF16) k_kwns4_tail<float, bf16><<<blocks, 256, 0, st>>>((float*)p, (bf16*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
-  else k_kwns4_tail<float, float><<<blocks, 256, 0, st>>>((float*)p, (float*)hbuf, (size_t)numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  if (p_dtype == PSGD_BF16 && h_dtype == PSGD_BF16) k_kwns4_tail<bf16, bf16><<<blocks, 256, 0, st>>>((bf16*)p, (bf16*)hbuf, (size_t)numel, (float)amp_numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  else if (p_dtype == PSGD_BF16) k_kwns4_tail<bf16, float><<<blocks, 256, 0, st>>>((bf16*)p, (float*)hbuf, (size_t)numel, (float)amp_numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  else if (h_dtype == PSGD_BF16) k_kwns4_tail<float, bf16><<<blocks, 256, 0, st>>>((float*)p, (bf16*)hbuf, (size_t)numel, (float)amp_numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
+  else k_kwns4_tail<float, float><<<blocks, 256, 0, st>>>((float*)p, (float*)hbuf, (size_t)numel, (float)amp_numel, sumsq, max_avg_amp, max_elem_amp, lr_params, h_dtype);
   LAUNCH_CHECK(ctx, "k_kwns4_tail");
   return PSGD_OK;
 }

@@ -135,6 +135,13 @@ struct Ctx {
   int64_t launches;
   char last_error[256];
   void* encode_tiled;  // cuTensorMapEncodeTiled entry point
+  // optional per-launch timing of the tcgen05 GEMM kernel (bench.py roofline): CUDA events on the launching stream
+  int timing_on;
+  int timing_count;      // event pairs recorded since the last reset
+  double timing_flops;   // algorithmic FLOPs (2*M*N*K, true sizes) of the recorded launches
+  cudaEvent_t* ev_begin;
+  cudaEvent_t* ev_end;
+  int ev_capacity;
 };
 
 // one GEMM problem: C = epi(op(A) op(B)), op(A) M x K, op(B) K x N

@@ -509,7 +509,14 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     attr_set[ai] = true;
   }
   int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  const bool timed = ctx->timing_on && BN == 256 && ctx->timing_count < ctx->ev_capacity;
+  if (timed) cudaEventRecord(ctx->ev_begin[ctx->timing_count], st);
   gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
+  if (timed) {
+    cudaEventRecord(ctx->ev_end[ctx->timing_count], st);
+    ctx->timing_count++;
+    for (int i = 0; i < n; ++i) ctx->timing_flops += 2.0 * gs[i].M * (double)gs[i].N * gs[i].K;
+  }
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "gemm_tc");
 }

@@ -274,9 +274,9 @@ __global__ void k_kwns4_head(TP* __restrict__ p, const TG* __restrict__ grad, si
 
 // clip + clamp + parameter update (ddp.py:153-157)
 template <typename TP, typename TQ>
-__global__ void k_kwns4_tail(TP* __restrict__ p, TQ* __restrict__ h, size_t numel, const float* __restrict__ sumsq,
+__global__ void k_kwns4_tail(TP* __restrict__ p, TQ* __restrict__ h, size_t numel, float amp_numel, const float* __restrict__ sumsq,
                              float max_avg_amp, float max_elem_amp, float lr_params, int h_dtype) {
-  float avg_amp = round_to(h_dtype, sqrtf(round_to(h_dtype, *sumsq / (float)numel)));
+  float avg_amp = round_to(h_dtype, sqrtf(round_to(h_dtype, *sumsq / amp_numel)));
   float scale = (avg_amp > max_avg_amp) ? round_to(h_dtype, max_avg_amp / avg_amp) : 1.f;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;

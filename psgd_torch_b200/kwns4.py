@@ -1,0 +1,248 @@
+"""KWNS4 -- drop-in for the reference's torch.optim wrappers, re-pointed at the B200 engine.
+
+    KWNS4         mirrors /root/reference/wrapped_as_torch_optimizer_for_ddp.py:4-176      (single GPU and DDP)
+    KWNS4DTensor  mirrors /root/reference/wrapped_as_torch_optimizer_for_dtensor.py:4-185  (FSDP2 / DTensor shards)
+
+Same constructor arguments, defaults, asserts, param_groups keys and per-parameter state keys ("QL", "exprs", "step",
+"ema") with the same tensor layouts, so a reference checkpoint's tensors load.  Same RNG discipline: private CPU+CUDA
+generator states are swapped in around step() (ddp.py:100-104,172-176) and all draws happen in the reference's order, so
+DDP replicas draw identical numbers and stay consistent.
+
+What changes is where the arithmetic runs: the per-parameter loop body (ddp.py:117-157) is
+    psgd_kwns4_head  (weight decay + cast + momentum EMA, one pass)
+    psgd_kron_whiten_q0p5eq1p5_update
+    psgd_kron_precond_grad (sum of squares for the clipping rule fused into the last product)
+    psgd_kwns4_tail  (clip + clamp + parameter update, one pass, no host synchronisation -- the reference's
+                      `if avg_amp > max_avg_amp` at ddp.py:154 stalls the host once per parameter)
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from . import psgd
+
+
+class KWNS4(torch.optim.Optimizer):
+    """Kronecker-product whitening preconditioner fitted with online Newton-Schulz iteration (dQ = Q^0.5 E Q^1.5).
+    See the reference docstring (ddp.py:5-23) for the meaning of every hyper-parameter; they are kept verbatim."""
+
+    def __init__(
+            self,
+            params,
+            whiten_grad=False,
+            preconditioner_max_size=float("inf"),
+            preconditioner_max_skew=1.0,
+            preconditioner_init_scale=1.0,
+            lr_params=2e-4,
+            lr_preconditioner=0.5,
+            betaL=0.9,
+            damping=1e-9,
+            momentum=0.9,
+            weight_decay=0.05,
+            decoupled_weight_decay=True,
+            grad_clip_max_amps=(2.0, 10.0),
+            preconditioner_update_probability=1.0,
+            preconditioner_dtype: torch.dtype | None = torch.bfloat16,
+            update_preconditioner_first=True,
+            resync_every=1000_000,
+    ):
+        # ddp.py:45-62, verbatim
+        assert whiten_grad in (False, True)
+        assert preconditioner_max_size >= 0.0
+        assert preconditioner_max_skew >= 0.0
+        assert preconditioner_init_scale > 0.0
+        assert lr_params > 0.0
+        assert 0.0 < lr_preconditioner < 1.0
+        assert 0.0 <= betaL <= 1.0
+        assert damping >= 0.0
+        assert 0.0 <= momentum < 1.0
+        assert weight_decay >= 0.0
+        assert decoupled_weight_decay in (False, True)
+        assert grad_clip_max_amps[1] >= grad_clip_max_amps[0] >= 1.0
+        assert 0.0 < preconditioner_update_probability <= 1.0
+        assert preconditioner_dtype in (None, torch.bfloat16, torch.float32)
+        assert update_preconditioner_first in (False, True)
+        assert resync_every > 0
+        if not whiten_grad:
+            assert momentum > 0.0, "Cannot whiten momentum if momentum setting is zero."
+
+        defaults = {
+            "whiten_grad": whiten_grad,
+            "preconditioner_max_size": preconditioner_max_size,
+            "preconditioner_max_skew": preconditioner_max_skew,
+            "preconditioner_init_scale": preconditioner_init_scale,
+            "lr_params": lr_params,
+            "lr_preconditioner": lr_preconditioner,
+            "betaL": betaL,
+            "damping": damping,
+            "momentum": momentum,
+            "weight_decay": weight_decay,
+            "decoupled_weight_decay": decoupled_weight_decay,
+            "grad_clip_max_amps": grad_clip_max_amps,
+            "preconditioner_update_probability": preconditioner_update_probability,
+            "preconditioner_dtype": preconditioner_dtype,
+            "update_preconditioner_first": update_preconditioner_first,
+            "resync_every": resync_every,
+        }
+        super().__init__(params, defaults)
+
+        self.dQ = "Q0.5EQ1.5"  # ddp.py:84-86
+        self.update_precond = psgd.update_precond_kron_whiten_q0p5eq1p5
+        self.precond_grad = psgd.precond_grad_kron
+        self._sumsq = {}
+        self._init_rng_sync()
+
+    # ---- RNG discipline (ddp.py:88-96) ----
+    def _needs_rng_sync(self):
+        return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+    def _init_rng_sync(self):
+        self.is_distributed = self._needs_rng_sync()
+        if self.is_distributed:
+            on_gpu = torch.distributed.get_backend() != "gloo"  # the reference assumes nccl; gloo keeps CPU tensors (tests)
+            state = torch.get_rng_state()
+            state = state.cuda() if on_gpu else state
+            torch.distributed.broadcast(state, src=0)
+            self.cpu_rng_state = state.cpu()
+            if torch.cuda.is_available():
+                state = torch.cuda.get_rng_state()
+                state = state.cuda() if on_gpu else state
+                torch.distributed.broadcast(state, src=0)
+                self.cuda_rng_state = state.cpu()
+            else:
+                self.cuda_rng_state = None
+
+    # ---- hooks overridden by the DTensor variant ----
+    def _local(self, t):
+        return t
+
+    def _resync(self, p, state, group, momentum):
+        # ddp.py:163-170
+        if self.is_distributed and (state["step"] % group["resync_every"] == 0):
+            torch.distributed.broadcast(p, src=0)
+            if momentum > 0.0:
+                torch.distributed.broadcast(state["ema"], src=0)
+            for q, ell in zip(*state["QL"]):
+                torch.distributed.broadcast(q, src=0)
+                torch.distributed.broadcast(ell, src=0)
+
+    def _sumsq_buf(self, device):
+        b = self._sumsq.get(device)
+        if b is None:
+            b = torch.zeros(1, dtype=torch.float32, device=device)
+            self._sumsq[device] = b
+        return b
+
+    @torch.no_grad()
+    def step(self):
+        if self.is_distributed:  # ddp.py:100-104
+            external_cpu_rng_state = torch.get_rng_state()
+            torch.set_rng_state(self.cpu_rng_state)
+            if self.cuda_rng_state is not None:
+                external_cuda_rng_state = torch.cuda.get_rng_state()
+                torch.cuda.set_rng_state(self.cuda_rng_state)
+
+        lib = _lib.load_library()
+        for group in self.param_groups:
+            momentum = group["momentum"]
+            max_avg_amp, max_element_amp = group["grad_clip_max_amps"]
+            updateP_first, updateP_last = ((group["update_preconditioner_first"], not group["update_preconditioner_first"])
+                                           if torch.rand([]) < group["preconditioner_update_probability"] else (False, False))
+            wd, lr_params = group["weight_decay"], group["lr_params"]
+            for p in group["params"]:
+                grad = p.grad
+                if grad is None:
+                    continue
+                grad = self._local(grad)
+                if grad.numel() == 0:  # dtensor.py:124-125
+                    continue
+                local_p = self._local(p)
+                if not local_p.is_contiguous():
+                    raise _lib.EngineError("KWNS4 (B200 engine) needs contiguous parameters")
+                grad = grad.contiguous()
+                pre_dtype = group["preconditioner_dtype"] or grad.dtype
+                sq_shape = grad.squeeze().shape  # ddp.py:124
+                dev = grad.device
+                h = _lib.handle_for(dev)
+
+                state = self.state[p]
+                if len(state) == 0:  # ddp.py:130-137
+                    QL, exprs = psgd.init_kron(torch.empty(sq_shape, dtype=pre_dtype, device=dev),
+                                               Scale=group["preconditioner_init_scale"],
+                                               max_size=group["preconditioner_max_size"],
+                                               max_skew=group["preconditioner_max_skew"], dQ=self.dQ)
+                    state["QL"], state["exprs"] = QL, exprs
+                    state["step"] = 0
+                    state["ema"] = None if momentum == 0.0 else torch.zeros(sq_shape, dtype=pre_dtype, device=dev)
+
+                t = state["step"]
+                beta = min(t / (t + 1), momentum) if momentum > 0.0 else 0.0  # ddp.py:141
+                need_g = group["whiten_grad"] or momentum == 0.0
+                coupled = wd > 0.0 and not group["decoupled_weight_decay"]
+                if need_g and (grad.dtype != pre_dtype or coupled):
+                    g_cast = torch.empty(sq_shape, dtype=pre_dtype, device=dev)
+                else:
+                    g_cast = None
+                # head: weight decay (ddp.py:117-122) + cast (125-127) + EMA (139-143), one pass
+                rc = lib.psgd_kwns4_head(h, grad.numel(), _lib.ptr(local_p), _lib.dtype_code(local_p), _lib.ptr(grad),
+                                         _lib.dtype_code(grad), float(wd), float(lr_params), int(group["decoupled_weight_decay"]),
+                                         _lib.ptr(state["ema"]), _lib.ptr(g_cast), _lib._DTYPES[pre_dtype], float(beta),
+                                         _lib.stream_ptr(dev))
+                _lib.check(h, rc, "psgd_kwns4_head")
+                state["step"] += 1
+                g_pre = g_cast if g_cast is not None else grad.view(sq_shape)
+
+                to_be_whitened = g_pre if group["whiten_grad"] else state["ema"]
+                if updateP_first:  # ddp.py:146-148
+                    self.update_precond(state["QL"], state["exprs"], to_be_whitened,
+                                        lr=group["lr_preconditioner"], betaL=group["betaL"], damping=group["damping"])
+
+                to_be_preconded = g_pre if momentum == 0.0 else state["ema"]
+                sumsq = self._sumsq_buf(dev)
+                hh = self.precond_grad(state["QL"], state["exprs"], to_be_preconded, sumsq_out=sumsq)  # ddp.py:150-151
+
+                # tail: clip (ddp.py:153-156) + p -= lr*h (157), one pass, device-side branch
+                rc = lib.psgd_kwns4_tail(h, hh.numel(), hh.numel(), _lib.ptr(local_p), _lib.dtype_code(local_p), _lib.ptr(hh),
+                                         _lib.dtype_code(hh), _lib.ptr(sumsq), float(max_avg_amp), float(max_element_amp),
+                                         float(lr_params), _lib.stream_ptr(dev))
+                _lib.check(h, rc, "psgd_kwns4_tail")
+
+                if updateP_last:  # ddp.py:159-161
+                    self.update_precond(state["QL"], state["exprs"], to_be_whitened,
+                                        lr=group["lr_preconditioner"], betaL=group["betaL"], damping=group["damping"])
+
+                self._resync(p, state, group, momentum)
+
+        if self.is_distributed:  # ddp.py:172-176
+            self.cpu_rng_state = torch.get_rng_state()
+            torch.set_rng_state(external_cpu_rng_state)
+            if self.cuda_rng_state is not None:
+                self.cuda_rng_state = torch.cuda.get_rng_state()
+                torch.cuda.set_rng_state(external_cuda_rng_state)
+
+
+class KWNS4DTensor(KWNS4):
+    """dtensor.py:4-185: every rank preconditions its LOCAL shard of each DTensor parameter independently."""
+
+    def _needs_rng_sync(self):
+        return True  # dtensor.py:89-96 syncs unconditionally
+
+    def _local(self, t):
+        return t.to_local() if hasattr(t, "to_local") else t
+
+    def _resync(self, p, state, group, momentum):
+        # dtensor.py:167-179: resync along replicated mesh dims only (sharded dims: "NOT implemented" in the reference)
+        if state["step"] % group["resync_every"] != 0 or not hasattr(p, "placements"):
+            return
+        from torch.distributed.tensor.placement_types import Replicate
+        for mesh_dim, placement in enumerate(p.placements):
+            if isinstance(placement, Replicate):
+                pg = p.device_mesh.get_group(mesh_dim)
+                src = torch.distributed.get_process_group_ranks(pg)[0]
+                torch.distributed.broadcast(p.to_local(), src=src, group=pg)
+                if momentum > 0.0:
+                    torch.distributed.broadcast(state["ema"], src=src, group=pg)
+                for q, ell in zip(*state["QL"]):
+                    torch.distributed.broadcast(q, src=src, group=pg)
+                    torch.distributed.broadcast(ell, src=src, group=pg)
