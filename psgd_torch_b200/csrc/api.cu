@@ -102,8 +102,8 @@ struct KronWs {
   // buffers
   float* qsq[2];    // fp32 squares of diagonal factors
   void* B0; void* B1; void* B2;   // m x n
-  void* S[5];       // smax x smax: T, Qn, R, RQ, RRQ   (R / RQ slots double as P_L / P_R before the Grams)
-  void* Va; void* Vb;             // 32 x smax
+  void* S[2][4];    // per dense factor, s x s each: T (Gram, later R), Qn, RQ, RRQ   (the Qn slots double as P_L / P_R in the chain)
+  void* Va[2]; void* Vb[2];       // per dense factor: 32 x s probe buffers
   size_t total;
 };
 
@@ -119,8 +119,6 @@ static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
   const size_t m = k->m, n = k->has_r ? k->n : 1;
   const int sdim[2] = {k->m, k->has_r ? k->n : 0};
   const int dense[2] = {k->kind_l == PSGD_DENSE, k->has_r && k->kind_r == PSGD_DENSE};
-  size_t smax = 0;
-  for (int i = 0; i < 2; ++i) if (dense[i] && (size_t)sdim[i] > smax) smax = sdim[i];
   w.zero_begin = (char*)b.take(0);
   size_t z0 = b.off;
   for (int i = 0; i < 2; ++i) {
@@ -140,92 +138,150 @@ static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
   w.qsq[0] = (float*)b.take(m * 4);
   w.qsq[1] = (float*)b.take(n * 4);
   w.B0 = b.take(m * n * es); w.B1 = b.take(m * n * es); w.B2 = b.take(m * n * es);
-  for (int i = 0; i < 5; ++i) w.S[i] = b.take(smax * smax * es);
-  w.Va = b.take(32 * smax * es); w.Vb = b.take(32 * smax * es);
+  for (int i = 0; i < 2; ++i) {
+    const size_t sd = dense[i] ? (size_t)sdim[i] : 0;
+    for (int j = 0; j < 4; ++j) w.S[i][j] = b.take(sd * sd * es);
+    w.Va[i] = b.take(32 * sd * es); w.Vb[i] = b.take(32 * sd * es);
+  }
   w.total = b.off;
 }
 
-// ---------------------------------------------------------------------------------------------
-// norm_lower_bound_{spd,skh}  (psgd.py:46-93): A s x s, row_sumsq / nf_src already reduced
-// ---------------------------------------------------------------------------------------------
-static int run_bound(Ctx* ctx, int dt, const void* A, int s, const void* V0, const float* row_sumsq, const float* nf_src,
-                     BoundWs& w, void* Va, void* Vb, cudaStream_t st) {
-  const float tiny = dtype_tiny(dt);
-  k_bound_prep<<<1, 1024, 0, st>>>(row_sumsq, s, nf_src, tiny, w.scal);
-  LAUNCH_CHECK(ctx, "k_bound_prep");
-  DISPATCH_T(dt, (k_probe_init<T><<<32, 256, 0, st>>>((const T*)A, s, (const T*)V0, w.scal, (T*)Va)));
-  LAUNCH_CHECK(ctx, "k_probe_init");
-  int rc;
-  GemmDesc g;
-  const bool tc_form = ctx->gemm_path != 1 && dt == PSGD_BF16 && s >= 128 && (s % 8) == 0;
-  if (tc_form) {
-    // tensor-core formulation: keep the probes transposed, X = W^T (s x 32), X_new = A^T X: the s-long dimension is the
-    // UMMA M dimension, the 32 probes ride in N; A is read through MN-major descriptors, no transposed copy is made.
-    // probe norms are column sums of squares, the normalisation a column scale.
-    g = gemm_desc(dt, A, s, 1, Va, s, 1, s, 32, s, Vb, 32);                      // X1 = A^T V1^T / nf
-    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.col_sumsq = w.rn1;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    k_rowscale<<<1, 32, 0, st>>>(w.rn1, w.scal, tiny, w.sc1, 32);
-    LAUNCH_CHECK(ctx, "k_rowscale");
-    g = gemm_desc(dt, A, s, 1, Vb, 32, 0, s, 32, s, Va, 32);                     // X2 = A^T (X1 / |x1|) / nf
-    g.epi.col_scale = w.sc1;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    g = gemm_desc(dt, A, s, 1, Va, 32, 0, s, 32, s, Vb, 32);                     // X3 = A^T X2 / nf
-    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.col_sumsq = w.rn3;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    k_rowscale<<<1, 32, 0, st>>>(w.rn3, w.scal, tiny, w.sc3, 32);
-    LAUNCH_CHECK(ctx, "k_rowscale");
-    g = gemm_desc(dt, A, s, 1, Vb, 32, 0, s, 32, s, Va, 32);                     // X4 = A^T (X3 / |x3|) / nf
-    g.epi.col_scale = w.sc3; g.epi.col_sumsq = w.rn4;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  } else {
-    // W1 = V1 A / nf  (+ row norms)
-    g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
-    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn1;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    k_rowscale<<<1, 32, 0, st>>>(w.rn1, w.scal, tiny, w.sc1, 32);
-    LAUNCH_CHECK(ctx, "k_rowscale");
-    // W2 = (W1 / |W1|) A / nf
-    g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
-    g.epi.row_scale = w.sc1;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    // W3 = W2 A / nf (+ row norms)
-    g = gemm_desc(dt, Va, s, 0, A, s, 0, 32, s, s, Vb, s);
-    g.epi.alpha_ptr = w.scal + SC_INV_NF; g.epi.row_sumsq = w.rn3;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    k_rowscale<<<1, 32, 0, st>>>(w.rn3, w.scal, tiny, w.sc3, 32);
-    LAUNCH_CHECK(ctx, "k_rowscale");
-    // W4 = (W3 / |W3|) A / nf (+ row norms)
-    g = gemm_desc(dt, Vb, s, 0, A, s, 0, 32, s, s, Va, s);
-    g.epi.row_scale = w.sc3; g.epi.row_sumsq = w.rn4;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  }
-  k_bound_final<<<1, 32, 0, st>>>(w.rn4, 32, w.scal, dt);
-  LAUNCH_CHECK(ctx, "k_bound_final");
+// up to TC_MAX independent GEMMs: one grouped tcgen05 launch when all qualify, else one launch each
+static int launch_gemm_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
+  if (n <= 0) return PSGD_OK;
+  bool all_tc = ctx->gemm_path != 1 && n <= 4;
+  for (int i = 0; i < n && all_tc; ++i) all_tc = tc_eligible(gs[i]) && gs[i].M > 0 && gs[i].N > 0;
+  if (all_tc) return launch_gemm_tc_group(ctx, gs, n, st);
+  for (int i = 0; i < n; ++i) { int rc = launch_gemm(ctx, gs[i], st); if (rc) return rc; }
   return PSGD_OK;
 }
 
-// procrustes_step2 (psgd.py:101-124) on Qn -> writes Q.  S buffers: R, RQ, RRQ
-static int run_procrustes(Ctx* ctx, int dt, const void* Qn, void* Q, int s, const void* V0, float max_step, FactorWs& f,
-                          void* R, void* RQ, void* RRQ, void* Va, void* Vb, cudaStream_t st) {
-  dim3 grid((s + 31) / 32, (s + 31) / 32), block(32, 8);
-  DISPATCH_T(dt, (k_skew<T><<<grid, block, 0, st>>>((const T*)Qn, (T*)R, s, f.r_abs_max, f.r_row_sumsq)));
-  LAUNCH_CHECK(ctx, "k_skew");
-  int rc = run_bound(ctx, dt, R, s, V0, f.r_row_sumsq, f.r_abs_max, f.b_skh, Va, Vb, st);
-  if (rc) return rc;
-  k_procrustes_scal<<<1, 32, 0, st>>>(f.b_skh.scal, dtype_tiny(dt), f.fs);
-  LAUNCH_CHECK(ctx, "k_procrustes_scal");
-  GemmDesc g = gemm_desc(dt, R, s, 0, Qn, s, 0, s, s, s, RQ, s);
-  g.epi.alpha_ptr = f.fs + FS_INV_SR; g.epi.trace = f.fs + FS_TR1;
-  rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  g = gemm_desc(dt, R, s, 0, RQ, s, 0, s, s, s, RRQ, s);
-  g.epi.alpha_ptr = f.fs + FS_INV_SR; g.epi.trace = f.fs + FS_TR2;
-  rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  size_t numel = (size_t)s * s;
-  DISPATCH_T(dt, (k_procrustes_finish<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)Qn, (const T*)RQ, (const T*)RRQ,
-                                                                                 (T*)Q, numel, f.fs, max_step)));
-  LAUNCH_CHECK(ctx, "k_procrustes_finish");
+// ---------------------------------------------------------------------------------------------
+// norm_lower_bound_{spd,skh}  (psgd.py:46-93) for up to two matrices at once (the left and right factor of one update
+// advance together so that their 32-probe products share one grouped launch).  row_sumsq / nf_src already reduced.
+// ---------------------------------------------------------------------------------------------
+struct BoundJob {
+  const void* A; int s; const void* V0; const float* row_sumsq; const float* nf_src; BoundWs* w; void* Va; void* Vb;
+};
+
+static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, cudaStream_t st) {
+  const float tiny = dtype_tiny(dt);
+  bool tc_form[2];
+  for (int j = 0; j < n; ++j) {
+    tc_form[j] = ctx->gemm_path != 1 && dt == PSGD_BF16 && jb[j].s >= 128 && (jb[j].s % 8) == 0;
+    k_bound_prep<<<1, 1024, 0, st>>>(jb[j].row_sumsq, jb[j].s, jb[j].nf_src, tiny, jb[j].w->scal);
+    LAUNCH_CHECK(ctx, "k_bound_prep");
+    DISPATCH_T(dt, (k_probe_init<T><<<32, 256, 0, st>>>((const T*)jb[j].A, jb[j].s, (const T*)jb[j].V0, jb[j].w->scal, (T*)jb[j].Va)));
+    LAUNCH_CHECK(ctx, "k_probe_init");
+  }
+  GemmDesc g[2];
+  // four products W <- W A / nf with a row normalisation after the 1st and 3rd (psgd.py:64-67).
+  // tensor-core formulation: the probes stay transposed, X = W^T (s x 32), X_new = A^T X: the s-long dimension is the UMMA M
+  // dimension, the 32 probes ride in N, A is read through MN-major descriptors (no transposed copy); probe norms are column
+  // sums of squares and the normalisation a column scale.  SIMT formulation (small / fp32): W (32 x s) row-major as written.
+  for (int step = 0; step < 4; ++step) {
+    for (int j = 0; j < n; ++j) {
+      const BoundJob& J = jb[j];
+      BoundWs& w = *J.w;
+      void* src = (step & 1) ? J.Vb : J.Va;
+      void* dst = (step & 1) ? J.Va : J.Vb;
+      const int s = J.s;
+      if (tc_form[j]) {
+        if (step == 0) g[j] = gemm_desc(dt, J.A, s, 1, src, s, 1, s, 32, s, dst, 32);   // V1 is stored 32 x s
+        else g[j] = gemm_desc(dt, J.A, s, 1, src, 32, 0, s, 32, s, dst, 32);
+        if (step == 0 || step == 2) g[j].epi.alpha_ptr = w.scal + SC_INV_NF; else g[j].epi.col_scale = (step == 1) ? w.sc1 : w.sc3;
+        if (step == 0) g[j].epi.col_sumsq = w.rn1;
+        if (step == 2) g[j].epi.col_sumsq = w.rn3;
+        if (step == 3) g[j].epi.col_sumsq = w.rn4;
+      } else {
+        g[j] = gemm_desc(dt, src, s, 0, J.A, s, 0, 32, s, s, dst, s);
+        if (step == 0 || step == 2) g[j].epi.alpha_ptr = w.scal + SC_INV_NF; else g[j].epi.row_scale = (step == 1) ? w.sc1 : w.sc3;
+        if (step == 0) g[j].epi.row_sumsq = w.rn1;
+        if (step == 2) g[j].epi.row_sumsq = w.rn3;
+        if (step == 3) g[j].epi.row_sumsq = w.rn4;
+      }
+    }
+    int rc = launch_gemm_group(ctx, g, n, st); if (rc) return rc;
+    if (step == 0 || step == 2) {
+      for (int j = 0; j < n; ++j) {
+        k_rowscale<<<1, 32, 0, st>>>(step == 0 ? jb[j].w->rn1 : jb[j].w->rn3, jb[j].w->scal, tiny, step == 0 ? jb[j].w->sc1 : jb[j].w->sc3, 32);
+        LAUNCH_CHECK(ctx, "k_rowscale");
+      }
+    }
+  }
+  for (int j = 0; j < n; ++j) {
+    k_bound_final<<<1, 32, 0, st>>>(jb[j].w->rn4, 32, jb[j].w->scal, dt);
+    LAUNCH_CHECK(ctx, "k_bound_final");
+  }
   return PSGD_OK;
+}
+
+// one dense factor travelling through the update
+struct DenseItem {
+  int s; void* q; float* L; float t2;
+  void* T;     // Gram term1 on entry; reused for R = Qn^T - Qn
+  void* Qn; void* RQ; void* RRQ; void* Va; void* Vb;
+  const void* v_spd; const void* v_skh;
+  FactorWs* f;
+};
+
+// procrustes_step2 (psgd.py:101-124) on it[i].Qn -> writes it[i].q
+static int run_procrustes(Ctx* ctx, int dt, DenseItem* it, int n, float max_step, cudaStream_t st) {
+  BoundJob jb[2];
+  GemmDesc g[2];
+  for (int i = 0; i < n; ++i) {
+    const int s = it[i].s;
+    dim3 grid((s + 63) / 64, (s + 63) / 64);
+    DISPATCH_T(dt, (k_skew<T><<<grid, 256, 0, st>>>((const T*)it[i].Qn, (T*)it[i].T, s, it[i].f->r_abs_max, it[i].f->r_row_sumsq)));
+    LAUNCH_CHECK(ctx, "k_skew");
+    jb[i] = BoundJob{it[i].T, s, it[i].v_skh, it[i].f->r_row_sumsq, it[i].f->r_abs_max, &it[i].f->b_skh, it[i].Va, it[i].Vb};
+  }
+  int rc = run_bounds(ctx, dt, jb, n, st); if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    k_procrustes_scal<<<1, 32, 0, st>>>(it[i].f->b_skh.scal, dtype_tiny(dt), it[i].f->fs);
+    LAUNCH_CHECK(ctx, "k_procrustes_scal");
+    g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].Qn, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].RQ, it[i].s);     // RQ = R Qn / |R|
+    g[i].epi.alpha_ptr = it[i].f->fs + FS_INV_SR; g[i].epi.trace = it[i].f->fs + FS_TR1;
+  }
+  rc = launch_gemm_group(ctx, g, n, st); if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].RQ, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].RRQ, it[i].s);    // RRQ = R RQ / |R|
+    g[i].epi.alpha_ptr = it[i].f->fs + FS_INV_SR; g[i].epi.trace = it[i].f->fs + FS_TR2;
+  }
+  rc = launch_gemm_group(ctx, g, n, st); if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    const size_t numel = (size_t)it[i].s * it[i].s;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (dt == PSGD_BF16 && numel % 8 == 0 && al16(it[i].Qn) && al16(it[i].RQ) && al16(it[i].RRQ) && al16(it[i].q)) {
+      k_procrustes_finish_bf16x8<<<ew_blocks(ctx, numel / 8), 256, 0, st>>>((const bf16*)it[i].Qn, (const bf16*)it[i].RQ, (const bf16*)it[i].RRQ,
+                                                                            (bf16*)it[i].q, numel / 8, it[i].f->fs, max_step);
+    } else {
+      DISPATCH_T(dt, (k_procrustes_finish<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)it[i].Qn, (const T*)it[i].RQ, (const T*)it[i].RRQ,
+                                                                                     (T*)it[i].q, numel, it[i].f->fs, max_step)));
+    }
+    LAUNCH_CHECK(ctx, "k_procrustes_finish");
+  }
+  return PSGD_OK;
+}
+
+// psgd.py:412-416 for up to two dense factors: bound of term1, L update, Newton-Schulz step, procrustes
+static int run_dense_factors(Ctx* ctx, int dt, DenseItem* it, int n, float lr, float betaL, cudaStream_t st) {
+  if (n <= 0) return PSGD_OK;
+  BoundJob jb[2];
+  GemmDesc g[2];
+  for (int i = 0; i < n; ++i)
+    jb[i] = BoundJob{it[i].T, it[i].s, it[i].v_spd, it[i].f->row_sumsq, it[i].f->diag_max, &it[i].f->b_spd, it[i].Va, it[i].Vb};
+  int rc = run_bounds(ctx, dt, jb, n, st); if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    k_dense_L_update<<<1, 32, 0, st>>>(it[i].f->b_spd.scal, it[i].t2, lr, betaL, it[i].L, it[i].f->fs, dt);
+    LAUNCH_CHECK(ctx, "k_dense_L_update");
+    // Qn = Q - lr/L (term1 Q - t2 Q)    psgd.py:415   (out of place: Q is an operand of the product)
+    g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].q, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].Qn, it[i].s);
+    g[i].epi.alpha_ptr = it[i].f->fs + FS_ALPHA; g[i].epi.D = it[i].q; g[i].epi.ldd = it[i].s; g[i].epi.d_dtype = dt; g[i].epi.beta = 1.f;
+    g[i].epi.beta_ptr = it[i].f->fs + FS_BETA;
+  }
+  rc = launch_gemm_group(ctx, g, n, st); if (rc) return rc;
+  return run_procrustes(ctx, dt, it, n, 0.125f, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,8 +305,8 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
     LAUNCH_CHECK(ctx, "k_scale2d");
     return PSGD_OK;
   }
-  void* PL = w.S[2];
-  void* PR = w.S[3];
+  void* PL = w.S[0][1];
+  void* PR = w.S[1][1];
   // ---- left side ----
   // scratch: B0 and B2 (out is B1 or caller memory, X is B0 or caller memory).  X is dead once the first product
   // of the chain form has consumed it, so B0 may be overwritten afterwards; the P-first form reads X last.
@@ -444,8 +500,13 @@ int psgd_kron_whiten_q0p5eq1p5_update(psgd_handle_t h, const psgd_kron_t* k, con
   rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
 
   // G' = G + (damping + eps|G|) N      psgd.py:402-403
-  DISPATCH_T(dt, (k_add_noise<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)G, (const T*)noise->N, (T*)w.B0, numel, damping,
-                                                                        dtype_eps(dt))));
+  if (dt == PSGD_BF16 && numel % 8 == 0 && (reinterpret_cast<uintptr_t>(G) & 15u) == 0 && (reinterpret_cast<uintptr_t>(noise->N) & 15u) == 0) {
+    k_add_noise_bf16x8<<<ew_blocks(ctx, numel / 8), 256, 0, st>>>((const bf16*)G, (const bf16*)noise->N, (bf16*)w.B0, numel / 8, damping,
+                                                                  dtype_eps(dt));
+  } else {
+    DISPATCH_T(dt, (k_add_noise<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)G, (const T*)noise->N, (T*)w.B0, numel, damping,
+                                                                          dtype_eps(dt))));
+  }
   LAUNCH_CHECK(ctx, "k_add_noise");
   // Pg = P G'  with the sums of squares the diagonal factors need fused into the last product
   void* Pg = w.B1;
@@ -453,22 +514,20 @@ int psgd_kron_whiten_q0p5eq1p5_update(psgd_handle_t h, const psgd_kron_t* k, con
   if (rc) return rc;
 
   // Grams of the dense factors (psgd.py:405) -- one grouped launch when both exist
-  void* TL = w.S[0];
-  void* TR = w.S[1];
-  GemmDesc gl, gr;
+  GemmDesc gg[2];
+  int ng = 0;
   if (dense[0]) {
-    gl = gemm_desc(dt, Pg, n, 0, Pg, n, 1, m, m, n, TL, m);
-    gl.epi.row_sumsq = w.f[0].row_sumsq; gl.epi.diag_max = w.f[0].diag_max;
+    gg[ng] = gemm_desc(dt, Pg, n, 0, Pg, n, 1, m, m, n, w.S[0][0], m);
+    gg[ng].epi.row_sumsq = w.f[0].row_sumsq; gg[ng].epi.diag_max = w.f[0].diag_max; ++ng;
   }
   if (dense[1]) {
-    gr = gemm_desc(dt, Pg, n, 1, Pg, n, 0, n, n, m, TR, n);
-    gr.epi.row_sumsq = w.f[1].row_sumsq; gr.epi.diag_max = w.f[1].diag_max;
+    gg[ng] = gemm_desc(dt, Pg, n, 1, Pg, n, 0, n, n, m, w.S[1][0], n);
+    gg[ng].epi.row_sumsq = w.f[1].row_sumsq; gg[ng].epi.diag_max = w.f[1].diag_max; ++ng;
   }
-  if (dense[0] && dense[1]) rc = launch_gemm_pair(ctx, gl, gr, st);
-  else if (dense[0]) rc = launch_gemm(ctx, gl, st);
-  else if (dense[1]) rc = launch_gemm(ctx, gr, st);
-  if (rc) return rc;
+  rc = launch_gemm_group(ctx, gg, ng, st); if (rc) return rc;
 
+  DenseItem items[2];
+  int nd = 0;
   for (int i = 0; i < 2; ++i) {
     if (i == 1 && !k->has_r) break;
     const int s = i == 0 ? m : n;
@@ -481,21 +540,14 @@ int psgd_kron_whiten_q0p5eq1p5_update(psgd_handle_t h, const psgd_kron_t* k, con
       LAUNCH_CHECK(ctx, "k_diag_update");
       continue;
     }
-    void* Tm = i == 0 ? TL : TR;
-    const void* v_spd = i == 0 ? noise->V0_spd_l : noise->V0_spd_r;
-    const void* v_skh = i == 0 ? noise->V0_skh_l : noise->V0_skh_r;
-    // ell = norm_lower_bound_spd(term1) + t2 ; L update ; step size     psgd.py:413-414
-    rc = run_bound(ctx, dt, Tm, s, v_spd, f.row_sumsq, f.diag_max, f.b_spd, w.Va, w.Vb, st); if (rc) return rc;
-    k_dense_L_update<<<1, 32, 0, st>>>(f.b_spd.scal, t2, lr, betaL, L, f.fs, dt);
-    LAUNCH_CHECK(ctx, "k_dense_L_update");
-    // Qn = Q - lr/L (term1 Q - t2 Q)    psgd.py:415   (out of place: Q is an operand of the product)
-    void* Qn = w.S[2];
-    GemmDesc g = gemm_desc(dt, Tm, s, 0, q, s, 0, s, s, s, Qn, s);
-    g.epi.alpha_ptr = f.fs + FS_ALPHA; g.epi.D = q; g.epi.ldd = s; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.beta_ptr = f.fs + FS_BETA;
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    // procrustes_step2(Q)    psgd.py:416 ; the Gram buffer of this factor is dead now and is reused for R
-    rc = run_procrustes(ctx, dt, Qn, q, s, v_skh, 0.125f, f, Tm, w.S[3], w.S[4], w.Va, w.Vb, st); if (rc) return rc;
+    DenseItem& d = items[nd++];
+    d.s = s; d.q = q; d.L = L; d.t2 = t2;
+    d.T = w.S[i][0]; d.Qn = w.S[i][1]; d.RQ = w.S[i][2]; d.RRQ = w.S[i][3]; d.Va = w.Va[i]; d.Vb = w.Vb[i];
+    d.v_spd = i == 0 ? noise->V0_spd_l : noise->V0_spd_r;
+    d.v_skh = i == 0 ? noise->V0_skh_l : noise->V0_skh_r;
+    d.f = &f;
   }
+  rc = run_dense_factors(ctx, dt, items, nd, lr, betaL, st); if (rc) return rc;
   if (do_balance) { rc = run_balance(ctx, k, w, st); if (rc) return rc; }
   return PSGD_OK;
 }
@@ -585,7 +637,8 @@ static int bound_entry(psgd_handle_t h, int dt, const void* A, int s, const void
   int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
   DISPATCH_T(dt, (k_rowstats<T><<<s, 256, 0, st>>>((const T*)A, s, w.row_sumsq, spd ? w.nf : nullptr, spd ? nullptr : w.nf)));
   LAUNCH_CHECK(ctx, "k_rowstats");
-  rc = run_bound(ctx, dt, A, s, V0, w.row_sumsq, w.nf, w.f.b_spd, w.Va, w.Vb, st); if (rc) return rc;
+  BoundJob jb{A, s, V0, w.row_sumsq, w.nf, &w.f.b_spd, w.Va, w.Vb};
+  rc = run_bounds(ctx, dt, &jb, 1, st); if (rc) return rc;
   k_copy_scalar<<<1, 32, 0, st>>>(w.f.b_spd.scal + SC_BOUND, out);
   LAUNCH_CHECK(ctx, "k_copy_scalar");
   return PSGD_OK;
@@ -609,7 +662,10 @@ int psgd_procrustes_step2(psgd_handle_t h, int dt, void* Q, int s, const void* V
   if (!workspace || wsb < w.total) return PSGD_ERR_WORKSPACE;
   int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
   rc = check_cuda(ctx, cudaMemcpyAsync(w.Qn, Q, (size_t)s * s * dtype_size(dt), cudaMemcpyDeviceToDevice, st), "memcpy"); if (rc) return rc;
-  return run_procrustes(ctx, dt, w.Qn, Q, s, V0, max_step_size, w.f, w.R, w.RQ, w.RRQ, w.Va, w.Vb, st);
+  DenseItem it;
+  it.s = s; it.q = Q; it.L = nullptr; it.t2 = 0.f; it.T = w.R; it.Qn = w.Qn; it.RQ = w.RQ; it.RRQ = w.RRQ; it.Va = w.Va; it.Vb = w.Vb;
+  it.v_spd = nullptr; it.v_skh = V0; it.f = &w.f;
+  return run_procrustes(ctx, dt, &it, 1, max_step_size, st);
 }
 
 }  // extern "C"

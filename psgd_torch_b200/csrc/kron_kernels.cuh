@@ -11,6 +11,22 @@ enum { SC_INV_NF = 0, SC_NF = 1, SC_J = 2, SC_BOUND = 3, SC_COUNT = 8 };
 // slots of the per-factor update scalars
 enum { FS_ALPHA = 0, FS_BETA = 1, FS_INV_SR = 2, FS_TR1 = 3, FS_TR2 = 4, FS_COUNT = 8 };
 
+// 8 bf16 <-> 8 floats through one 16-byte access
+__device__ __forceinline__ void ld8(const bf16* p, float* x) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { float2 f = __bfloat1622float2(h[t]); x[2 * t] = f.x; x[2 * t + 1] = f.y; }
+}
+__device__ __forceinline__ void st8(bf16* p, const float* x) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(x[2 * t], x[2 * t + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
 // G' = G + (damping + eps*|G|) * N     psgd.py:402-403
 template <typename T>
 __global__ void k_add_noise(const T* __restrict__ G, const T* __restrict__ Nz, T* __restrict__ out, size_t numel,
@@ -23,6 +39,19 @@ __global__ void k_add_noise(const T* __restrict__ G, const T* __restrict__ Nz, T
     float d = to_f<T>(from_f<T>(damping + to_f<T>(from_f<T>(eps * fabsf(g)))));
     float dn = to_f<T>(from_f<T>(d * to_f<T>(Nz[i])));
     out[i] = from_f<T>(g + dn);
+  }
+}
+// bf16, numel % 8 == 0, 16-byte aligned pointers
+__global__ void k_add_noise_bf16x8(const bf16* __restrict__ G, const bf16* __restrict__ Nz, bf16* __restrict__ out, size_t nvec,
+                                   float damping, float eps) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < nvec; i += stride) {
+    float g[8], z[8], o[8];
+    ld8(G + i * 8, g); ld8(Nz + i * 8, z);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { float d = rbf(damping + rbf(eps * fabsf(g[t]))); o[t] = g[t] + rbf(d * z[t]); }
+    st8(out + i * 8, o);
   }
 }
 
@@ -55,40 +84,60 @@ __global__ void k_scale2d(const T* __restrict__ X, T* __restrict__ out, int m, i
 }
 
 // R = Q^T - Q  (psgd.py:117) with max|R| (psgd.py:84) and row sums of squares (psgd.py:86) fused.
-// 32x32 tiles, block (32, 8).
+// grid (T, T), T = ceil(s/64), block 256; block (bi <= bj) loads the tile pair Q[bi,bj], Q[bj,bi] once and writes both
+// R[bi,bj] and its mirror R[bj,bi] = -R[bi,bj]^T (exactly skew by construction); blocks with bi > bj exit.
 template <typename T>
-__global__ void k_skew(const T* __restrict__ Q, T* __restrict__ R, int s, float* abs_max, float* row_sumsq) {
-  __shared__ float tA[32][33];
-  __shared__ float tB[32][33];
+__global__ void __launch_bounds__(256) k_skew(const T* __restrict__ Q, T* __restrict__ R, int s, float* abs_max, float* row_sumsq) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi > bj) return;
+  __shared__ float tA[64][65];  // Q[i0 + y][j0 + x]
+  __shared__ float tB[64][65];  // Q[j0 + y][i0 + x]
   __shared__ float red[32];
-  int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  int tx = threadIdx.x, ty = threadIdx.y;
-  for (int y = ty; y < 32; y += 8) {
-    int i = i0 + y, j = j0 + tx;
-    tA[y][tx] = (i < s && j < s) ? to_f<T>(Q[(size_t)i * s + j]) : 0.f;
-    int i2 = j0 + y, j2 = i0 + tx;
-    tB[y][tx] = (i2 < s && j2 < s) ? to_f<T>(Q[(size_t)i2 * s + j2]) : 0.f;
+  const int i0 = bi * 64, j0 = bj * 64, tid = threadIdx.x;
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int y = e >> 6, x = e & 63;
+    int i = i0 + y, j = j0 + x;
+    tA[y][x] = (i < s && j < s) ? to_f<T>(Q[(size_t)i * s + j]) : 0.f;
+    i = j0 + y; j = i0 + x;
+    tB[y][x] = (i < s && j < s) ? to_f<T>(Q[(size_t)i * s + j]) : 0.f;
   }
   __syncthreads();
+  const int w = tid >> 5, lane = tid & 31;
   float am = 0.f;
-  for (int y = ty; y < 32; y += 8) {
-    int i = i0 + y, j = j0 + tx;
-    float r = tB[tx][y] - tA[y][tx];
-    T o = from_f<T>(r);
-    float f = to_f<T>(o);
-    if (i < s && j < s) R[(size_t)i * s + j] = o; else f = 0.f;
-    am = fmaxf(am, fabsf(f));
-    float rsq = warp_sum(f * f);
-    if (tx == 0 && i < s && row_sumsq) atomicAdd(&row_sumsq[i], rsq);
+  for (int y = w; y < 64; y += 8) {   // tile (bi, bj): R[i0+y][j0+x] = Q[j0+x][i0+y] - Q[i0+y][j0+x]
+    float rs = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int x = lane + 32 * hh;
+      const int i = i0 + y, j = j0 + x;
+      T o = from_f<T>(tB[x][y] - tA[y][x]);
+      float f = to_f<T>(o);
+      if (i < s && j < s) R[(size_t)i * s + j] = o; else f = 0.f;
+      rs = fmaf(f, f, rs);
+      am = fmaxf(am, fabsf(f));
+    }
+    rs = warp_sum(rs);
+    if (lane == 0 && i0 + y < s && row_sumsq) atomicAdd(&row_sumsq[i0 + y], rs);
   }
-  am = warp_max(am);
-  if (tx == 0) red[ty] = am;
-  __syncthreads();
-  if (ty == 0) {
-    float v = tx < 8 ? red[tx] : 0.f;
-    v = warp_max(v);
-    if (tx == 0 && abs_max) atomic_max_nonneg(abs_max, v);
+  if (bi != bj) {
+    for (int y = w; y < 64; y += 8) {  // mirror tile (bj, bi): R[j0+y][i0+x] = Q[i0+x][j0+y] - Q[j0+y][i0+x]
+      float rs = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int x = lane + 32 * hh;
+        const int i = j0 + y, j = i0 + x;
+        T o = from_f<T>(tA[x][y] - tB[y][x]);
+        float f = to_f<T>(o);
+        if (i < s && j < s) R[(size_t)i * s + j] = o; else f = 0.f;
+        rs = fmaf(f, f, rs);
+        am = fmaxf(am, fabsf(f));
+      }
+      rs = warp_sum(rs);
+      if (lane == 0 && j0 + y < s && row_sumsq) atomicAdd(&row_sumsq[j0 + y], rs);
+    }
   }
+  am = block_max(am, red);
+  if (tid == 0 && abs_max) atomic_max_nonneg(abs_max, am);
 }
 
 // j = argmax_i rowsumsq[i]; nf = *nf_src + tiny   (psgd.py:58-61 / 83-86). One block.
@@ -200,6 +249,21 @@ __global__ void k_procrustes_finish(const T* __restrict__ Qn, const T* __restric
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < numel; i += stride)
     Q[i] = from_f<T>(to_f<T>(Qn[i]) + a * (to_f<T>(RQ[i]) + 0.5f * a * to_f<T>(RRQ[i])));
+}
+
+__global__ void k_procrustes_finish_bf16x8(const bf16* __restrict__ Qn, const bf16* __restrict__ RQ, const bf16* __restrict__ RRQ,
+                                           bf16* __restrict__ Q, size_t nvec, const float* __restrict__ fs, float max_step) {
+  const float tr1 = fs[FS_TR1], tr2 = fs[FS_TR2];
+  const float a = (tr2 < 0.f) ? fminf(-tr1 / tr2, max_step) : max_step;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < nvec; i += stride) {
+    float q[8], r1[8], r2[8], o[8];
+    ld8(Qn + i * 8, q); ld8(RQ + i * 8, r1); ld8(RRQ + i * 8, r2);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) o[t] = q[t] + a * (r1[t] + 0.5f * a * r2[t]);
+    st8(Q + i * 8, o);
+  }
 }
 
 // diagonal factor (psgd.py:406-410): ell = max(term1) + t2; L = max(betaL*L+(1-betaL)*ell, ell);

@@ -169,3 +169,56 @@ def test_lra_engine_matches_reference_golden(fname):
         for l, lr_ in zip(Luvd, st["L"]):
             assert relerr(l, lr_) < tol, fname
         assert relerr(psgd.precond_grad_lra(UVd, st["g"].to(dev)), st["Pg"]) < tol, fname
+
+
+KWNS4_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "kwns4_*.pt")))
+
+
+@pytest.mark.parametrize("fname", KWNS4_CASES)
+def test_kwns4_wrapper_matches_reference_golden(fname, monkeypatch):
+    """The KWNS4 drop-in, driven step by step with the gradients and the random numbers the reference KWNS4 (ddp.py) consumed."""
+    from psgd_torch_b200 import KWNS4, psgd
+    dev = _dev()
+    case = load_golden(fname)
+    pdtype = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}[case["pdtype"]]
+    p = torch.nn.Parameter(case["p0"].clone().to(dev))
+    opt = KWNS4([p], preconditioner_dtype=pdtype, **case["kw"])
+    queue = []
+    monkeypatch.setattr(psgd, "draw_kron_noise", lambda G, Q: queue.pop(0))
+    for st in case["steps"]:
+        p.grad = st["grad"].clone().to(dev)
+        if st["do_update"]:
+            queue.append(_noise_to(st["noise"], dev))
+        opt.step()
+        tol_p = 1e-6 if pdtype == torch.float32 else 2e-3
+        assert relerr(p, st["p"]) < tol_p, fname
+        state = opt.state[p]
+        tol = 1e-5 if pdtype == torch.float32 else 2e-2
+        for q, qr in zip(state["QL"][0], st["Q"]):
+            assert q.dtype == qr.dtype and q.shape == qr.shape      # state layout identical to the reference's
+            assert relerr(q, qr) < tol, fname
+        if st["ema"] is not None:
+            assert relerr(state["ema"], st["ema"]) < tol, fname
+    assert not queue
+
+
+def test_lra_optimizer_reduces_a_quadratic():
+    """The LRA torch.optim wrapper (authored here; the reference has none) on a small ill-conditioned quadratic."""
+    from psgd_torch_b200 import LRAWhitenOptimizer
+    dev = _dev()
+    torch.manual_seed(0)
+    A = torch.diag(torch.logspace(0, 3, 60)).to(dev)
+    w1 = torch.nn.Parameter(torch.randn(30, device=dev))
+    w2 = torch.nn.Parameter(torch.randn(5, 6, device=dev))
+    opt = LRAWhitenOptimizer([w1, w2], rank_of_approximation=8, preconditioner_init_scale=None, lr_params=0.05, lr_preconditioner=0.1,
+                             momentum=0.9)
+    def loss_fn():
+        x = torch.cat([w1.reshape(-1), w2.reshape(-1)])
+        return 0.5 * x @ A @ x
+    l0 = float(loss_fn())
+    for _ in range(300):
+        opt.zero_grad()
+        loss = loss_fn()
+        loss.backward()
+        opt.step()
+    assert float(loss_fn()) < 1e-2 * l0

@@ -1,0 +1,104 @@
+"""CPU tests of the host-side logic: owner-computes partition and the world_size-2 (gloo) RNG discipline of the wrappers."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _llama_costs():
+    sys.path.insert(0, ROOT)
+    import bench
+    from psgd_torch_b200 import partition
+    costs = []
+    for name, shape, kind in bench.unit_list():
+        if kind == "lra":
+            costs.append(partition.lra_unit_cost(shape[0], bench.LRA_RANK))
+        elif len(shape) == 1:
+            costs.append(partition.kron_unit_cost(shape[0], 1, False, False))
+        else:
+            dl, dr = bench.dense_flags(shape)
+            costs.append(partition.kron_unit_cost(shape[0], shape[1], dl, dr))
+    return costs
+
+
+def test_unit_set_matches_survey():
+    import bench
+    units = bench.unit_list()
+    assert len(units) == 291  # 64+64+64+32+2+65
+    assert bench.dense_flags((4096, 4096)) == [True, True]
+    assert bench.dense_flags((1024, 4096)) == [True, False]
+    assert bench.dense_flags((14336, 4096)) == [False, True]
+    assert bench.dense_flags((4096, 14336)) == [True, False]
+    assert bench.dense_flags((128256, 4096)) == [False, True]
+    assert bench.dense_flags((4096,)) == [False]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_lpt_partition_covers_every_unit_once_and_balances(world):
+    from psgd_torch_b200 import partition
+    costs = _llama_costs()
+    parts = partition.lpt_partition(costs, world)
+    flat = sorted(i for p in parts for i in p)
+    assert flat == list(range(len(costs)))
+    imb, _ = partition.imbalance(costs, parts)
+    assert imb < (1.02 if world <= 4 else 1.35)   # at 8 ranks the single LRA unit is the critical path
+    assert partition.lpt_partition(costs, world) == parts  # deterministic: every rank computes the same assignment
+    own = partition.owner_of(costs, world)
+    assert all(i in parts[own[i]] for i in range(len(costs)))
+
+
+def test_kron_unit_flops_match_survey_figures():
+    from oracle.psgd_oracle import kron_unit_flops
+    up, ap = kron_unit_flops(4096, 4096, True, True)
+    assert abs(up - 1.6493e12) / 1.6493e12 < 1e-3 and abs(ap - 5.4976e11) / 5.4976e11 < 1e-3
+    up, ap = kron_unit_flops(4096, 14336, True, False)
+    assert abs(up - 1.5118e12) / 1.5118e12 < 1e-3 and abs(ap - 6.1848e11) / 6.1848e11 < 1e-3
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from psgd_torch_b200 import KWNS4
+    torch.manual_seed(100 + rank)  # ranks start with DIFFERENT generator states
+    p = torch.nn.Parameter(torch.zeros(4, 6))
+    opt = KWNS4([p])
+    assert opt.is_distributed
+    st = opt.cpu_rng_state.clone()
+    gathered = [torch.zeros_like(st) for _ in range(world)]
+    dist.all_gather(gathered, st)
+    same_state = all(torch.equal(g, gathered[0]) for g in gathered)
+    ext_before = torch.get_rng_state()
+    opt.step()  # p.grad is None -> no engine call; still swaps the private RNG state in and out (ddp.py:100-104,172-176)
+    ext_after = torch.get_rng_state()
+    drew = not torch.equal(opt.cpu_rng_state, st)   # the group coin flip (ddp.py:110) advanced the PRIVATE state
+    # owner-computes partition is identical on every rank
+    from psgd_torch_b200 import partition
+    parts = partition.lpt_partition([5.0, 1.0, 3.0, 3.0, 2.0, 8.0], world)
+    t = torch.tensor([sum((r + 1) * (i + 1) * 7919 for r, pp in enumerate(parts) for i in pp)], dtype=torch.int64)
+    lst = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(lst, t)
+    q.put((rank, same_state, torch.equal(ext_before, ext_after), drew, all(int(x) == int(lst[0]) for x in lst)))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_rng_sync_and_partition():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same_state, ext_restored, drew, same_parts in res:
+        assert same_state, "private RNG states must be identical across ranks after construction (ddp.py:88-96)"
+        assert ext_restored, "step() must restore the caller's RNG state (ddp.py:172-176)"
+        assert drew and same_parts
