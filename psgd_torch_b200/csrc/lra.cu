@@ -12,17 +12,11 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "lra_mma.cuh"
 
 namespace psgd {
 
-// ---- parameter block produced by the small kernel, consumed by sweep 2 (floats) ----
-// layout for padded rank RP:  [Au RP*RP][Av RP*RP][vec 0..11 each RP][scalars 16]
-enum { LV_AUC1 = 0, LV_AVC2, LV_AVS1, LV_AUS2, LV_AVATU, LV_AVBTU, LV_WA, LV_WB, LV_ATU, LV_BTU, LV_P1, LV_P2, LV_NVEC };
-enum { LS_STEP = 0, LS_STEP_D = 1, LS_MAX_PHH = 2, LS_MAX_VINV = 3, LS_NSCAL = 16 };
-// accumulator block of sweep 1 (floats): [UtU RP*RP][VtV RP*RP][VtU RP*RP][Utx1 RP][Vtx1 RP][Utx2 RP][Vtx2 RP][x1sq][x2sq]
-
-__host__ __device__ inline size_t lra_acc_floats(int RP) { return (size_t)3 * RP * RP + 4 * RP + 2; }
-__host__ __device__ inline size_t lra_par_floats(int RP) { return (size_t)2 * RP * RP + (size_t)LV_NVEC * RP + LS_NSCAL; }
+// parameter / accumulator block layouts: see lra_mma.cuh
 
 template <typename T, int RP>
 __device__ __forceinline__ void load_row(const T* __restrict__ base, long long row, int r, float* x) {
@@ -243,6 +237,18 @@ __global__ void k_lra_small(const float* __restrict__ acc, float* __restrict__ p
     Au[i * RP + j] = (idn - e1 + e2) / rho;   // U' = (U/rho)(I - E + E2)
     Av[i * RP + j] = (idn + e1 + e2) * rho;   // V' = (V rho)(I + E + E2)
   }
+  {  // tensor-core sweep 2 applies the identity part exactly and only the small corrections through bf16 (transposed: N x K)
+    bf16* EuT = reinterpret_cast<bf16*>(par + lra_par_et_off(RP));
+    bf16* EvT = EuT + RP * RP;
+    for (int e = tid; e < RP * RP; e += blockDim.x) {
+      int nn = e / RP, kk = e - nn * RP;
+      bool in = nn < r && kk < r;
+      float e1 = in ? E[kk * RP + nn] : 0.f, e2 = in ? 0.5f * T1[kk * RP + nn] : 0.f;
+      EuT[e] = __float2bfloat16_rn(e1 - e2);
+      EvT[e] = __float2bfloat16_rn(e1 + e2);
+    }
+    if (tid == 0) { float* ps = par + lra_par_scal_off(RP); ps[LS_INV_RHO] = 1.f / rho; ps[LS_RHO] = rho; }
+  }
   __syncthreads();
   // balanced Grams: G'uu = Au^T Guu Au etc. (reuse E as scratch)
   mm_small(Guu, Au, T1, r, RP, false, false); mm_small(Au, T1, E, r, RP, true, false);
@@ -318,8 +324,8 @@ __global__ void k_lra_small(const float* __restrict__ acc, float* __restrict__ p
   const float nb2 = x2sq - 2.f * dot_small(s1, vpx2, r) + dot_small(s1, tmp, r);
   __syncthreads();
   const float na = sqrtf(fmaxf(na2, 0.f)), nb = sqrtf(fmaxf(nb2, 0.f));
-  float* pvec = par + 2 * MM;
-  float* pscal = pvec + (size_t)LV_NVEC * RP;
+  float* pvec = par + lra_par_vec_off(RP);
+  float* pscal = par + lra_par_scal_off(RP);
   if (update_U) {  // psgd.py:1036-1043
     mv_small(Mx, c1, atX, r, RP, false);                 // atV = V'^T a = (I + V'^T U') c1
     for (int i = tid; i < r; i += blockDim.x) btX[i] = t[i];   // btV = V'^T b
@@ -357,6 +363,11 @@ __global__ void k_lra_small(const float* __restrict__ acc, float* __restrict__ p
     __syncthreads();
     if (tid == 0) { *Lv = Ln; pscal[LS_STEP] = lr / Ln; }
   }
+  for (int i = tid; i < RP; i += blockDim.x) {
+    pvec[LV_C1 * RP + i] = i < r ? c1[i] : 0.f; pvec[LV_C2 * RP + i] = i < r ? c2[i] : 0.f;
+    pvec[LV_S1 * RP + i] = i < r ? s1[i] : 0.f; pvec[LV_S2 * RP + i] = i < r ? s2[i] : 0.f;
+  }
+  __syncthreads();
   // row-dot vectors against the UNtransformed rows: U'_i . c = U_i . (Au c)
   mv_small(Au, c1, tmp, r, RP, false);
   for (int i = tid; i < RP; i += blockDim.x) pvec[LV_AUC1 * RP + i] = i < r ? tmp[i] : 0.f;
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(128) k_lra_sweep2(T* __restrict__ U, T* __rest
   __shared__ float red[32];
   for (int e = threadIdx.x; e < 2 * RP * RP + LV_NVEC * RP; e += blockDim.x) smp[e] = par[e];
   __syncthreads();
-  const float step = par[(size_t)2 * RP * RP + (size_t)LV_NVEC * RP + LS_STEP];
+  const float step = par[lra_par_scal_off(RP) + LS_STEP];
   float mx1 = 0.f, mx2 = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < n; row += stride) {
@@ -604,10 +615,30 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   const int dt = l->dtype, RP = w.RP, r = l->r;
   const long long n = l->n;
   int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
-  long long tiles = (n + 63) / 64;
-  int grid1 = (int)(tiles < (long long)ctx->num_sms * 2 ? tiles : (long long)ctx->num_sms * 2);
-  LRA_DISPATCH(dt, RP, (k_lra_sweep1<T, R_><<<grid1, 256, 0, st>>>((const T*)l->U, (const T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.acc)));
-  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep1"); if (rc) return rc;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  // tensor-core sweeps: bf16, rank exactly 16 or 32 (rows are whole 16-byte pieces); everything else takes the CUDA-core sweeps
+  const bool mma_path = dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && ctx->gemm_path != 1;
+  const int smem_mma = 8 * 4 * (r == 32 ? LraTile<32>::BYTES : LraTile<16>::BYTES);
+  if (mma_path) {
+    long long chunks = (n + 15) / 16;
+    int grid1 = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
+    static bool attr_g = false;
+    if (!attr_g) {
+      cudaFuncSetAttribute(k_lra_gram_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<32>::BYTES);
+      cudaFuncSetAttribute(k_lra_gram_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<16>::BYTES);
+      cudaFuncSetAttribute(k_lra_rotate_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<32>::BYTES);
+      cudaFuncSetAttribute(k_lra_rotate_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<16>::BYTES);
+      attr_g = true;
+    }
+    if (r == 32) k_lra_gram_mma<32><<<grid1, 256, smem_mma, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.acc);
+    else k_lra_gram_mma<16><<<grid1, 256, smem_mma, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.acc);
+    ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_gram_mma"); if (rc) return rc;
+  } else {
+    long long tiles = (n + 63) / 64;
+    int grid1 = (int)(tiles < (long long)ctx->num_sms * 2 ? tiles : (long long)ctx->num_sms * 2);
+    LRA_DISPATCH(dt, RP, (k_lra_sweep1<T, R_><<<grid1, 256, 0, st>>>((const T*)l->U, (const T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.acc)));
+    ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep1"); if (rc) return rc;
+  }
   size_t smem_small = ((size_t)8 * RP * RP + 24 * RP) * 4;
   static bool small_attr = false;
   if (!small_attr) { cudaFuncSetAttribute(k_lra_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); small_attr = true; }
@@ -616,8 +647,13 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   long long rows_blocks = (n + 127) / 128;
   int grid2 = (int)(rows_blocks < (long long)ctx->num_sms * 8 ? rows_blocks : (long long)ctx->num_sms * 8);
   size_t smem2 = ((size_t)2 * RP * RP + LV_NVEC * RP) * 4;
-  float* scal = w.par + (size_t)2 * RP * RP + (size_t)LV_NVEC * RP;
-  LRA_DISPATCH(dt, RP, {
+  float* scal = w.par + lra_par_scal_off(RP);
+  if (mma_path) {
+    long long chunks = (n + 15) / 16;
+    int gridr = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
+    if (r == 32) k_lra_rotate_mma<32><<<gridr, 256, smem_mma, st>>>((bf16*)l->U, (bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.par, update_U, w.dd, scal);
+    else k_lra_rotate_mma<16><<<gridr, 256, smem_mma, st>>>((bf16*)l->U, (bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.par, update_U, w.dd, scal);
+  } else LRA_DISPATCH(dt, RP, {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lra_sweep2<T, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
     k_lra_sweep2<T, R_><<<grid2, 128, smem2, st>>>((T*)l->U, (T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.par, update_U, w.dd, scal);

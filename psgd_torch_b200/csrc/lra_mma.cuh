@@ -1,0 +1,398 @@
+// lra_mma.cuh -- tensor-core streaming kernels for the two sweeps of the LRA update (bf16, rank 16 or 32).
+//
+// Both sweeps are HBM-bound (6*n*r*2 bytes per update); on CUDA cores the r x r Grams (sweep 1) and the
+// balancing rotations (sweep 2) make them compute-bound by 5-7x.  Here every warp streams its own 16-row chunks
+//   global --cp.async 16 B--> warp-private smem ring (XOR-swizzled rows [U | V]) --ldmatrix--> mma.sync.m16n8k16 (bf16, fp32 acc)
+// so the arithmetic rides on the tensor cores and the kernel runs at memory speed.  Warp-level mma.sync is the right tool
+// here: the operands are 16 x 64 slivers with a 2-4 K-step reduction, far below a tcgen05 tile, and the roofline is HBM.
+#pragma once
+#include "common.cuh"
+
+namespace psgd {
+
+// parameter block (floats) written by k_lra_small:  [Au RP^2][Av RP^2][LV_NVEC vectors of RP][LS_NSCAL scalars][EuT bf16 RP^2][EvT bf16 RP^2]
+enum { LV_AUC1 = 0, LV_AVC2, LV_AVS1, LV_AUS2, LV_AVATU, LV_AVBTU, LV_WA, LV_WB, LV_ATU, LV_BTU, LV_P1, LV_P2,
+       LV_C1, LV_C2, LV_S1, LV_S2, LV_NVEC };
+enum { LS_STEP = 0, LS_STEP_D = 1, LS_MAX_PHH = 2, LS_MAX_VINV = 3, LS_INV_RHO = 4, LS_RHO = 5, LS_NSCAL = 16 };
+
+__host__ __device__ inline size_t lra_acc_floats(int RP) { return (size_t)3 * RP * RP + 4 * RP + 2; }
+__host__ __device__ inline size_t lra_par_vec_off(int RP) { return (size_t)2 * RP * RP; }
+__host__ __device__ inline size_t lra_par_scal_off(int RP) { return (size_t)2 * RP * RP + (size_t)LV_NVEC * RP; }
+__host__ __device__ inline size_t lra_par_et_off(int RP) { return lra_par_scal_off(RP) + LS_NSCAL; }   // bf16 EuT then EvT
+__host__ __device__ inline size_t lra_par_floats(int RP) { return lra_par_et_off(RP) + (size_t)RP * RP; }
+
+__device__ __forceinline__ uint32_t smem_u32_generic(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
+
+// warp-private smem tile of one 16-row chunk: row = [U (RP bf16) | V (RP bf16)] = CPR 16-byte chunks; chunk c of row r sits at
+// physical chunk c ^ swz(r) so that the 8 rows of an ldmatrix 8x8 block hit 8 different bank groups.
+template <int RP> struct LraTile {
+  static constexpr int CPR = RP / 4;            // 16-byte chunks per row (8 for RP=32, 4 for RP=16)
+  static constexpr int ROW_BYTES = CPR * 16;
+  static constexpr int BYTES = 16 * ROW_BYTES;  // 2 KB (RP=32)
+  __device__ static __forceinline__ int swz(int row) { return CPR == 8 ? (row & 7) : ((row >> 1) & 3); }
+  __device__ static __forceinline__ uint32_t off(int row, int chunk) { return row * ROW_BYTES + ((chunk ^ swz(row)) << 4); }
+};
+
+// issue the cp.async loads of chunk `ck` (rows ck*16 ..) into the tile at smem address `tile`; rows >= n are zero-filled
+template <int RP>
+__device__ __forceinline__ void lra_issue_chunk(const bf16* __restrict__ U, const bf16* __restrict__ V, long long n, long long ck, uint32_t tile,
+                                                int lane) {
+  using Tl = LraTile<RP>;
+  constexpr int PIECES = 16 * Tl::CPR;  // 128 (RP=32) / 64 (RP=16)
+#pragma unroll
+  for (int i = 0; i < PIECES / 32; ++i) {
+    const int p = lane + 32 * i;
+    const int row = p / Tl::CPR, lc = p % Tl::CPR;
+    const long long grow = ck * 16 + row;
+    const bool isV = lc >= Tl::CPR / 2;
+    const bf16* src = (isV ? V : U) + grow * RP + (isV ? lc - Tl::CPR / 2 : lc) * 8;
+    const bool ok = grow < n;
+    cp_async16(tile + Tl::off(row, lc), ok ? (const void*)src : (const void*)U, ok ? 16 : 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep 1: U^T U, V^T V, V^T U (RP x RP each) and the projections U^T x, V^T x for x1 = d.h, x2 = v/d, plus |x1|^2, |x2|^2
+// (psgd.py:1006 and the r-sized right-hand sides of 1017-1052).  block = 8 warps, each warp streams its own chunks.
+// accumulators per warp: tiles of the 2RP x 2RP Gram of W = [U V] that are needed (upper blocks of UtU / VtV, all of VtU) + 2RP x 8
+// for the x columns.  Only RP = 32 and RP = 16 are instantiated.
+// ------------------------------------------------------------------------------------------------
+template <int RP>
+__global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict__ U, const bf16* __restrict__ V, const bf16* __restrict__ d,
+                                                         const bf16* __restrict__ hvec, const bf16* __restrict__ vvec, long long n,
+                                                         float* __restrict__ acc_out) {
+  using Tl = LraTile<RP>;
+  constexpr int STAGES = 4;
+  constexpr int MT = RP / 8;        // 16-row m-tiles of W^T: 2RP / 16
+  constexpr int NT = RP / 4;        // 8-col n-tiles of W: 2RP / 8
+  constexpr int HM = MT / 2, HN = NT / 2;   // tiles belonging to U
+  extern __shared__ __align__(128) uint8_t smem_lra[];
+  __shared__ float blk_acc[3 * RP * RP + 4 * RP + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int e = threadIdx.x; e < 3 * RP * RP + 4 * RP + 2; e += blockDim.x) blk_acc[e] = 0.f;
+  __syncthreads();
+  const uint32_t ring = smem_u32_generic(smem_lra) + warp * STAGES * Tl::BYTES;
+
+  // accumulators: UtU tiles (mt < HM, nt in [2*mt, HN)), VtV tiles (mt >= HM, nt in [HN + 2*(mt-HM), NT)), VtU (mt >= HM, nt < HN), x (all mt)
+  float aUU[HM][HN][4], aVV[HM][HN][4], aVU[HM][HN][4], aX[MT][4];
+#pragma unroll
+  for (int i = 0; i < HM; ++i)
+#pragma unroll
+    for (int j = 0; j < HN; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { aUU[i][j][e] = 0.f; aVV[i][j][e] = 0.f; aVU[i][j][e] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) aX[i][e] = 0.f;
+  float sq = 0.f;
+
+  const long long nchunks = (n + 15) / 16;
+  const long long gw = (long long)blockIdx.x * 8 + warp, tw = (long long)gridDim.x * 8;
+  // prologue: STAGES-1 chunks in flight
+  long long ck_issue = gw;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s * Tl::BYTES, lane);
+    cp_async_commit();
+    ck_issue += tw;
+  }
+  int stage = 0;
+  for (long long ck = gw; ck < nchunks; ck += tw) {
+    {  // keep the ring full
+      const int s_issue = (stage + STAGES - 1) % STAGES;
+      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
+      cp_async_commit();
+      ck_issue += tw;
+    }
+    // x columns: lanes with g == 0 carry x1 = d*h, g == 1 carry x2 = v/d (rows 2t, 2t+1, 2t+8, 2t+9 of the chunk), others zero
+    uint32_t xb0 = 0u, xb1 = 0u;
+    if (g < 2) {
+      float xv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long row = ck * 16 + 2 * t + (q & 1) + 8 * (q >> 1);
+        float x = 0.f;
+        if (row < n) {
+          const float dd = __bfloat162float(d[row]);
+          x = (g == 0) ? __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(hvec[row])))
+                       : __bfloat162float(__float2bfloat16_rn(__bfloat162float(vvec[row]) / dd));
+        }
+        xv[q] = x;
+        sq = fmaf(x, x, sq);
+      }
+      xb0 = pack_bf16(xv[0], xv[1]);
+      xb1 = pack_bf16(xv[2], xv[3]);
+    }
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const uint32_t tile = ring + stage * Tl::BYTES;
+    // F[c] = transposed 8x8 blocks (k rows 0-7 | 8-15) x (column chunks 2c, 2c+1): A fragment of m-tile c and B fragments of n-tiles 2c, 2c+1
+    uint32_t F[MT][4];
+#pragma unroll
+    for (int c = 0; c < MT; ++c) {
+      const int mi = lane >> 3, rr = lane & 7;            // matrix index 0..3, row within it
+      const int krow = (mi >> 1) * 8 + rr;                // matrices 0,1: k rows 0-7; 2,3: k rows 8-15
+      const int chunk = 2 * c + (mi & 1);
+      ldsm_x4_trans(tile + Tl::off(krow, chunk), F[c]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t b0 = F[nt >> 1][nt & 1], b1 = F[nt >> 1][2 + (nt & 1)];
+        if (mt < HM && nt < HN) { if (nt >= 2 * mt) mma16816(aUU[mt][nt], F[mt], b0, b1); }
+        else if (mt >= HM && nt >= HN) { if (nt - HN >= 2 * (mt - HM)) mma16816(aVV[mt - HM][nt - HN], F[mt], b0, b1); }
+        else if (mt >= HM && nt < HN) mma16816(aVU[mt - HM][nt], F[mt], b0, b1);
+      }
+      mma16816(aX[mt], F[mt], xb0, xb1);
+    }
+    stage = (stage + 1) % STAGES;
+  }
+  cp_async_wait<0>();
+  // ---- flush: warp -> block (smem atomics) -> global atomics ----
+  float* bUU = blk_acc; float* bVV = blk_acc + RP * RP; float* bVU = blk_acc + 2 * RP * RP; float* bP = blk_acc + 3 * RP * RP;
+#pragma unroll
+  for (int mt = 0; mt < HM; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < HN; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = 16 * mt + g + 8 * (e >> 1), col = 8 * nt + 2 * t + (e & 1);
+        if (nt >= 2 * mt) {
+          atomicAdd(&bUU[row * RP + col], aUU[mt][nt][e]);
+          atomicAdd(&bVV[row * RP + col], aVV[mt][nt][e]);
+          if (nt >= 2 * mt + 2) {   // strictly-upper block: mirror into the block that was skipped
+            atomicAdd(&bUU[col * RP + row], aUU[mt][nt][e]);
+            atomicAdd(&bVV[col * RP + row], aVV[mt][nt][e]);
+          }
+        }
+        atomicAdd(&bVU[row * RP + col], aVU[mt][nt][e]);
+      }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = 16 * mt + g + 8 * (e >> 1), col = 2 * t + (e & 1);   // col 0: x1, col 1: x2
+      if (col < 2) {
+        const int isV = row >= RP;
+        // layout: [Utx1][Vtx1][Utx2][Vtx2]
+        atomicAdd(&bP[(col * 2 + isV) * RP + (row - isV * RP)], aX[mt][e]);
+      }
+    }
+  if (g < 2) atomicAdd(&bP[4 * RP + g], sq);
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * RP * RP + 4 * RP + 2; e += blockDim.x) atomicAdd(&acc_out[e], blk_acc[e]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep 2: balancing rotation U' = (U - U Eu)/rho, V' = (V + V Ev) rho on tensor cores (Eu = E - E^2/2, Ev = E + E^2/2: the identity part
+// is applied exactly in fp32, only the small correction goes through bf16 -- same rounding structure as psgd.py:1012-1015), per-row
+// terms of the d update (psgd.py:1017-1029) and the rank-2 update of U or V (psgd.py:1036-1052), written back in place.
+// ------------------------------------------------------------------------------------------------
+template <int RP>
+__global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U, bf16* __restrict__ V, const bf16* __restrict__ d,
+                                                           const bf16* __restrict__ hvec, const bf16* __restrict__ vvec, long long n,
+                                                           const float* __restrict__ par, int update_U, float* __restrict__ dd_out,
+                                                           float* __restrict__ scal_out) {
+  using Tl = LraTile<RP>;
+  constexpr int STAGES = 4;
+  constexpr int KS = RP / 16;   // k-steps of the rotation products
+  constexpr int NT = RP / 8;    // 8-col n-tiles of one factor
+  constexpr int HC = Tl::CPR / 2;
+  extern __shared__ __align__(128) uint8_t smem_lra[];
+  __shared__ float vecs[8][RP];   // c1, c2, s1, s2, wa|atU, wb|btU
+  __shared__ float red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float* pvec = par + lra_par_vec_off(RP);
+  const float* pscal = par + lra_par_scal_off(RP);
+  const bf16* EuT = reinterpret_cast<const bf16*>(par + lra_par_et_off(RP));
+  const bf16* EvT = EuT + RP * RP;
+  for (int e = threadIdx.x; e < RP; e += blockDim.x) {
+    vecs[0][e] = pvec[LV_C1 * RP + e]; vecs[1][e] = pvec[LV_C2 * RP + e]; vecs[2][e] = pvec[LV_S1 * RP + e]; vecs[3][e] = pvec[LV_S2 * RP + e];
+    vecs[4][e] = update_U ? pvec[LV_WA * RP + e] : pvec[LV_ATU * RP + e];
+    vecs[5][e] = update_U ? pvec[LV_WB * RP + e] : pvec[LV_BTU * RP + e];
+  }
+  __syncthreads();
+  const float step = pscal[LS_STEP], inv_rho = pscal[LS_INV_RHO], rho = pscal[LS_RHO];
+  // B fragments of Eu, Ev (K x N "col"): b0 = (k = 16ks + 2t, +1 ; n = 8nt + g), b1 = k + 8.  E*T is stored N x K so the pair is one word.
+  uint32_t bu[NT][KS][2], bv[NT][KS][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int nn = 8 * nt + g, kk = 16 * ks + 2 * t;
+      bu[nt][ks][0] = *reinterpret_cast<const uint32_t*>(EuT + nn * RP + kk);
+      bu[nt][ks][1] = *reinterpret_cast<const uint32_t*>(EuT + nn * RP + kk + 8);
+      bv[nt][ks][0] = *reinterpret_cast<const uint32_t*>(EvT + nn * RP + kk);
+      bv[nt][ks][1] = *reinterpret_cast<const uint32_t*>(EvT + nn * RP + kk + 8);
+    }
+  const uint32_t ring = smem_u32_generic(smem_lra) + warp * STAGES * Tl::BYTES;
+  uint8_t* ring_gen = smem_lra + warp * STAGES * Tl::BYTES;
+  float mx1 = 0.f, mx2 = 0.f;
+  const long long nchunks = (n + 15) / 16;
+  const long long gw = (long long)blockIdx.x * 8 + warp, tw = (long long)gridDim.x * 8;
+  long long ck_issue = gw;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s * Tl::BYTES, lane);
+    cp_async_commit();
+    ck_issue += tw;
+  }
+  int stage = 0;
+  for (long long ck = gw; ck < nchunks; ck += tw) {
+    // the slot refilled now is the one whose coalesced stores were issued last iteration (they read smem synchronously) -> safe
+    {
+      const int s_issue = (stage + STAGES - 1) % STAGES;
+      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
+      cp_async_commit();
+      ck_issue += tw;
+    }
+    // per-row inputs of rows g and g+8
+    float dd[2], hh[2], vv[2];
+    bool rok[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const long long row = ck * 16 + g + 8 * q;
+      rok[q] = row < n;
+      dd[q] = rok[q] ? __bfloat162float(d[row]) : 1.f;
+      hh[q] = rok[q] ? __bfloat162float(hvec[row]) : 0.f;
+      vv[q] = rok[q] ? __bfloat162float(vvec[row]) : 0.f;
+    }
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const uint32_t tile = ring + stage * Tl::BYTES;
+    uint8_t* tile_gen = ring_gen + stage * Tl::BYTES;
+    // A fragments (row-major 16 x 16 per k-step): matrices (rows 0-7, chunk 2ks), (rows 8-15, chunk 2ks), (rows 0-7, chunk 2ks+1), (rows 8-15, 2ks+1)
+    uint32_t au[KS][4], av[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int mi = lane >> 3, rr = lane & 7;
+      const int row = (mi & 1) * 8 + rr;
+      const int chunk = 2 * ks + (mi >> 1);
+      ldsm_x4(tile + Tl::off(row, chunk), au[ks]);
+      ldsm_x4(tile + Tl::off(row, HC + chunk), av[ks]);
+    }
+    float cu[NT][4], cv[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { cu[nt][e] = 0.f; cv[nt][e] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) { mma16816(cu[nt], au[ks], bu[nt][ks][0], bu[nt][ks][1]); mma16816(cv[nt], av[ks], bv[nt][ks][0], bv[nt][ks][1]); }
+    }
+    // rotated rows in registers: element e of tile nt = (row g + 8*(e>>1), col 8nt + 2t + (e&1)); the unrotated value sits in the A fragment
+    float duc1[2] = {0.f, 0.f}, dus2[2] = {0.f, 0.f}, dvc2[2] = {0.f, 0.f}, dvs1[2] = {0.f, 0.f}, dva[2] = {0.f, 0.f}, dvb[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int ks = nt >> 1, hi = nt & 1;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float2 u0 = unpack_bf16(au[ks][2 * hi + q]);
+        const float2 v0 = unpack_bf16(av[ks][2 * hi + q]);
+        const float un[2] = {(u0.x - cu[nt][2 * q]) * inv_rho, (u0.y - cu[nt][2 * q + 1]) * inv_rho};
+        const float vn[2] = {(v0.x + cv[nt][2 * q]) * rho, (v0.y + cv[nt][2 * q + 1]) * rho};
+        cu[nt][2 * q] = un[0]; cu[nt][2 * q + 1] = un[1];
+        cv[nt][2 * q] = vn[0]; cv[nt][2 * q + 1] = vn[1];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * nt + 2 * t + e;
+          duc1[q] = fmaf(un[e], vecs[0][col], duc1[q]);
+          dus2[q] = fmaf(un[e], vecs[3][col], dus2[q]);
+          dvc2[q] = fmaf(vn[e], vecs[1][col], dvc2[q]);
+          dvs1[q] = fmaf(vn[e], vecs[2][col], dvs1[q]);
+          if (!update_U) { dva[q] = fmaf(vn[e], vecs[4][col], dva[q]); dvb[q] = fmaf(vn[e], vecs[5][col], dvb[q]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        duc1[q] += __shfl_xor_sync(0xffffffffu, duc1[q], o); dus2[q] += __shfl_xor_sync(0xffffffffu, dus2[q], o);
+        dvc2[q] += __shfl_xor_sync(0xffffffffu, dvc2[q], o); dvs1[q] += __shfl_xor_sync(0xffffffffu, dvs1[q], o);
+        dva[q] += __shfl_xor_sync(0xffffffffu, dva[q], o); dvb[q] += __shfl_xor_sync(0xffffffffu, dvb[q], o);
+      }
+    }
+    float ca[2], cb[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float x1 = __bfloat162float(__float2bfloat16_rn(dd[q] * hh[q]));
+      const float x2 = __bfloat162float(__float2bfloat16_rn(vv[q] / dd[q]));
+      const float a = x1 + duc1[q];                 // Qh_i          psgd.py:1017
+      const float Ph = dd[q] * (a + dvc2[q]);       // Ph_i          psgd.py:1018
+      const float b = x2 - dvs1[q];                 // invQtv_i      psgd.py:1024
+      const float invPv = (b - dus2[q]) / dd[q];    // invPv_i       psgd.py:1025-1026
+      const float Phh = Ph * hh[q], vinv = vv[q] * invPv;
+      if (rok[q]) {
+        mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
+        if (t == 0) dd_out[ck * 16 + g + 8 * q] = Phh - vinv;
+      }
+      ca[q] = update_U ? step * a : step * (a + dva[q]);
+      cb[q] = update_U ? step * b : step * (b + dvb[q]);
+    }
+    __syncwarp();   // all lanes have consumed their ldmatrix data before the tile is overwritten
+    // rank-2 update + write the new rows back into the tile (same swizzled positions the fragments came from)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int row = g + 8 * q, col = 8 * nt + 2 * t;
+        float u0 = cu[nt][2 * q], u1 = cu[nt][2 * q + 1], v0 = cv[nt][2 * q], v1 = cv[nt][2 * q + 1];
+        const float w0 = ca[q] * vecs[4][col] - cb[q] * vecs[5][col], w1 = ca[q] * vecs[4][col + 1] - cb[q] * vecs[5][col + 1];
+        if (update_U) { u0 -= w0; u1 -= w1; } else { v0 -= w0; v1 -= w1; }
+        // chunk index within the row: col / 8 = nt (U) or HC + nt (V); byte offset within chunk: (col % 8) * 2 = 4t
+        *reinterpret_cast<uint32_t*>(tile_gen + Tl::off(row, nt) + 4 * t) = pack_bf16(u0, u1);
+        *reinterpret_cast<uint32_t*>(tile_gen + Tl::off(row, HC + nt) + 4 * t) = pack_bf16(v0, v1);
+      }
+    }
+    __syncwarp();
+    // coalesced 16-byte stores, mirror image of lra_issue_chunk
+    constexpr int PIECES = 16 * Tl::CPR;
+#pragma unroll
+    for (int i = 0; i < PIECES / 32; ++i) {
+      const int p = lane + 32 * i;
+      const int row = p / Tl::CPR, lc = p % Tl::CPR;
+      const long long grow = ck * 16 + row;
+      if (grow < n) {
+        const uint4 val = *reinterpret_cast<const uint4*>(tile_gen + Tl::off(row, lc));
+        const bool isV = lc >= HC;
+        bf16* dst = (isV ? V : U) + grow * RP + (isV ? lc - HC : lc) * 8;
+        *reinterpret_cast<uint4*>(dst) = val;
+      }
+    }
+    __syncwarp();
+    stage = (stage + 1) % STAGES;
+  }
+  cp_async_wait<0>();
+  mx1 = block_max(mx1, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(&scal_out[LS_MAX_PHH], mx1);
+  mx2 = block_max(mx2, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(&scal_out[LS_MAX_VINV], mx2);
+}
+
+}  // namespace psgd

@@ -222,3 +222,38 @@ def test_lra_optimizer_reduces_a_quadratic():
         loss.backward()
         opt.step()
     assert float(loss_fn()) < 1e-2 * l0
+
+
+@pytest.mark.parametrize("n,r", [(1003, 32), (4096, 16), (70000, 32)])
+def test_lra_tensor_core_sweeps_match_oracle(n, r):
+    """bf16, rank 16/32 takes the mma.sync sweeps (lra_mma.cuh); compare with the bf16 oracle and with an fp64 evaluation."""
+    from psgd_torch_b200 import psgd
+    from oracle import psgd_oracle as orc
+    dev = _dev()
+    g0 = torch.Generator().manual_seed(n + r)
+    bf = torch.bfloat16
+    U = (torch.randn(n, r, generator=g0) * (0.1 / (n * r)) ** 0.5 * 3).to(bf)
+    V = (torch.randn(n, r, generator=g0) * (0.1 / (n * r)) ** 0.5 * 3).to(bf)
+    d = (1.0 + 0.2 * torch.rand(n, 1, generator=g0)).to(bf)
+    UVe = [U.clone().to(dev), V.clone().to(dev), d.clone().to(dev)]
+    Le = [torch.zeros([], dtype=torch.float32, device=dev) for _ in range(3)]
+    for step in range(4):
+        g = (0.1 * torch.randn(n, 1, generator=g0) * (1 + torch.arange(n).reshape(n, 1) % 5)).to(bf)
+        noise = {"v": torch.randn(n, 1, generator=g0).to(bf), "update_U": step % 2 == 0}
+        # one step from the ENGINE's current state, evaluated by the bf16 oracle and in fp64
+        UVo = [x.detach().cpu().clone() for x in UVe]
+        Lo = [l.detach().cpu().clone() for l in Le]
+        UV64 = [x.detach().cpu().double() for x in UVe]
+        L64 = [l.detach().cpu().double() for l in Le]
+        orc.update_precond_lra_whiten(UVo, Lo, g, noise, lr=0.1, betaL=0.9, damping=1e-9)
+        orc.update_precond_lra_whiten(UV64, L64, g.double(), {"v": noise["v"].double(), "update_U": noise["update_U"]}, lr=0.1, betaL=0.9, damping=1e-9)
+        psgd.update_precond_lra_whiten(UVe, Le, g.to(dev), lr=0.1, betaL=0.9, damping=1e-9,
+                                       noise={"v": noise["v"].to(dev), "update_U": noise["update_U"]})
+        for xe, xo, x64 in zip(UVe, UVo, UV64):
+            assert relerr(xe, xo) < 3e-2
+            assert relerr(xe, x64) <= 1.5 * relerr(xo, x64) + 2e-3
+        for le, l64 in zip(Le, L64):
+            assert relerr(le, l64) < 3e-2
+        Pe = psgd.precond_grad_lra(UVe, g.to(dev))
+        P64 = orc.precond_grad_lra([x.detach().cpu().double() for x in UVe], g.double())
+        assert relerr(Pe, P64) < 1e-2
