@@ -467,6 +467,12 @@ int psgd_timing_read(psgd_handle_t h, int* launches, double* total_ms, double* f
   return PSGD_OK;
 }
 
+int psgd_debug_set_tile_n(psgd_handle_t h, int bn) {
+  if (!h || (bn != 0 && bn != 128 && bn != 256)) return PSGD_ERR_INVALID_ARG;
+  reinterpret_cast<Ctx*>(h)->force_bn = bn;
+  return PSGD_OK;
+}
+
 int psgd_debug_set_mn_desc(psgd_handle_t h, int lbo, int sbo) {
   if (!h) return PSGD_ERR_INVALID_ARG;
   reinterpret_cast<Ctx*>(h)->mn_lbo = lbo;

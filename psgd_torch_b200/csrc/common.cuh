@@ -132,6 +132,7 @@ struct Ctx {
   int num_sms;
   int gemm_path;       // 0 auto, 1 simt, 2 tc
   int mn_lbo, mn_sbo;  // MN-major UMMA descriptor byte offsets
+  int force_bn;        // debug: 0 = automatic tile width, else 128 / 256
   int64_t launches;
   char last_error[256];
   void* encode_tiled;  // cuTensorMapEncodeTiled entry point

@@ -530,6 +530,8 @@ int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
   }
   TcGroup grp;
   memset(&grp, 0, sizeof(grp));
+  if (ctx->force_bn == 128) return launch_tc<128>(ctx, grp, gs, n, st);
+  if (ctx->force_bn == 256) return launch_tc<256>(ctx, grp, gs, n, st);
   if (max_n > 128) return launch_tc<256>(ctx, grp, gs, n, st);
   return launch_tc<128>(ctx, grp, gs, n, st);
 }

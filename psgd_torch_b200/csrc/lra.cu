@@ -617,17 +617,17 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   // tensor-core sweeps: bf16, rank exactly 16 or 32 (rows are whole 16-byte pieces); everything else takes the CUDA-core sweeps
-  const bool mma_path = dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && ctx->gemm_path != 1;
-  const int smem_mma = 8 * 4 * (r == 32 ? LraTile<32>::BYTES : LraTile<16>::BYTES);
+  const bool mma_path = dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && al16(l->d) && al16(hv) && al16(v) && ctx->gemm_path != 1;
+  const int smem_mma = 8 * LRA_STAGES * (r == 32 ? LraTile<32>::BYTES : LraTile<16>::BYTES);
   if (mma_path) {
     long long chunks = (n + 15) / 16;
     int grid1 = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
     static bool attr_g = false;
     if (!attr_g) {
-      cudaFuncSetAttribute(k_lra_gram_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<32>::BYTES);
-      cudaFuncSetAttribute(k_lra_gram_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<16>::BYTES);
-      cudaFuncSetAttribute(k_lra_rotate_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<32>::BYTES);
-      cudaFuncSetAttribute(k_lra_rotate_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * LraTile<16>::BYTES);
+      cudaFuncSetAttribute(k_lra_gram_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
+      cudaFuncSetAttribute(k_lra_gram_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
+      cudaFuncSetAttribute(k_lra_rotate_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
+      cudaFuncSetAttribute(k_lra_rotate_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
       attr_g = true;
     }
     if (r == 32) k_lra_gram_mma<32><<<grid1, 256, smem_mma, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.acc);
@@ -724,6 +724,22 @@ int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
   rc = check_cuda(ctx, cudaMemsetAsync(w.p1, 0, 64 * 4, st), "memset"); if (rc) return rc;
   rc = check_cuda(ctx, cudaMemsetAsync(w.p2, 0, 64 * 4, st), "memset"); if (rc) return rc;
   if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4, st), "memset"); if (rc) return rc; }
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && ctx->gemm_path != 1) {
+    const int rpi = r == 32 ? 8 : 16;   // rows per warp instruction
+    long long need = ((n + rpi - 1) / rpi + 4 * 8 - 1) / (4 * 8);   // blocks of 8 warps x 4 groups
+    int gridc = (int)(need < (long long)ctx->num_sms * 8 ? need : (long long)ctx->num_sms * 8);
+    if (gridc < 1) gridc = 1;
+    for (int mode = 0; mode < 3; ++mode) {
+      const bf16* Mx = (const bf16*)(mode == 1 ? l->U : l->V);
+      const float* pin = mode == 0 ? nullptr : (mode == 1 ? w.p1 : w.p2);
+      float* pout = mode == 0 ? w.p1 : (mode == 1 ? w.p2 : nullptr);
+      if (r == 32) k_lra_apply_bf16<32><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
+      else k_lra_apply_bf16<16><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
+      ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply_bf16"); if (rc) return rc;
+    }
+    return PSGD_OK;
+  }
   long long rb = (n + 127) / 128;
   int grid = (int)(rb < (long long)ctx->num_sms * 8 ? rb : (long long)ctx->num_sms * 8);
   LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->V, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 0, nullptr, w.p1, nullptr)));

@@ -46,18 +46,21 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) { return __bfloat1622f
 
 // warp-private smem tile of one 16-row chunk: row = [U (RP bf16) | V (RP bf16)] = CPR 16-byte chunks; chunk c of row r sits at
 // physical chunk c ^ swz(r) so that the 8 rows of an ldmatrix 8x8 block hit 8 different bank groups.
+constexpr int LRA_STAGES = 8;
 template <int RP> struct LraTile {
   static constexpr int CPR = RP / 4;            // 16-byte chunks per row (8 for RP=32, 4 for RP=16)
   static constexpr int ROW_BYTES = CPR * 16;
-  static constexpr int BYTES = 16 * ROW_BYTES;  // 2 KB (RP=32)
+  static constexpr int VEC_OFF = 16 * ROW_BYTES;   // then one 128-byte line: d[16] | h[16] | v[16] (bf16) | pad
+  static constexpr int BYTES = VEC_OFF + 128;
   __device__ static __forceinline__ int swz(int row) { return CPR == 8 ? (row & 7) : ((row >> 1) & 3); }
   __device__ static __forceinline__ uint32_t off(int row, int chunk) { return row * ROW_BYTES + ((chunk ^ swz(row)) << 4); }
 };
 
 // issue the cp.async loads of chunk `ck` (rows ck*16 ..) into the tile at smem address `tile`; rows >= n are zero-filled
 template <int RP>
-__device__ __forceinline__ void lra_issue_chunk(const bf16* __restrict__ U, const bf16* __restrict__ V, long long n, long long ck, uint32_t tile,
-                                                int lane) {
+__device__ __forceinline__ void lra_issue_chunk(const bf16* __restrict__ U, const bf16* __restrict__ V, const bf16* __restrict__ d,
+                                                const bf16* __restrict__ hvec, const bf16* __restrict__ vvec, long long n, long long ck,
+                                                uint32_t tile, int lane) {
   using Tl = LraTile<RP>;
   constexpr int PIECES = 16 * Tl::CPR;  // 128 (RP=32) / 64 (RP=16)
 #pragma unroll
@@ -69,6 +72,14 @@ __device__ __forceinline__ void lra_issue_chunk(const bf16* __restrict__ U, cons
     const bf16* src = (isV ? V : U) + grow * RP + (isV ? lc - Tl::CPR / 2 : lc) * 8;
     const bool ok = grow < n;
     cp_async16(tile + Tl::off(row, lc), ok ? (const void*)src : (const void*)U, ok ? 16 : 0);
+  }
+  if (lane < 6) {  // the per-row vectors ride in the same pipeline: d, h, v, two 16-byte pieces (8 rows) each
+    const int which = lane >> 1, piece = lane & 1;
+    const bf16* vec = which == 0 ? d : (which == 1 ? hvec : vvec);
+    const long long r0 = ck * 16 + piece * 8;
+    long long valid = (n - r0) * 2;
+    valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
+    cp_async16(tile + Tl::VEC_OFF + which * 32 + piece * 16, valid > 0 ? (const void*)(vec + r0) : (const void*)U, (int)valid);
   }
 }
 
@@ -83,7 +94,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
                                                          const bf16* __restrict__ hvec, const bf16* __restrict__ vvec, long long n,
                                                          float* __restrict__ acc_out) {
   using Tl = LraTile<RP>;
-  constexpr int STAGES = 4;
+  constexpr int STAGES = LRA_STAGES;
   constexpr int MT = RP / 8;        // 16-row m-tiles of W^T: 2RP / 16
   constexpr int NT = RP / 4;        // 8-col n-tiles of W: 2RP / 8
   constexpr int HM = MT / 2, HN = NT / 2;   // tiles belonging to U
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
   long long ck_issue = gw;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s * Tl::BYTES, lane);
+    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s * Tl::BYTES, lane);
     cp_async_commit();
     ck_issue += tw;
   }
@@ -123,22 +134,26 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
   for (long long ck = gw; ck < nchunks; ck += tw) {
     {  // keep the ring full
       const int s_issue = (stage + STAGES - 1) % STAGES;
-      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
+      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
       cp_async_commit();
       ck_issue += tw;
     }
     // x columns: lanes with g == 0 carry x1 = d*h, g == 1 carry x2 = v/d (rows 2t, 2t+1, 2t+8, 2t+9 of the chunk), others zero
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const uint32_t tile = ring + stage * Tl::BYTES;
     uint32_t xb0 = 0u, xb1 = 0u;
     if (g < 2) {
+      const bf16* vl = reinterpret_cast<const bf16*>(smem_lra + warp * STAGES * Tl::BYTES + stage * Tl::BYTES + Tl::VEC_OFF);
       float xv[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const long long row = ck * 16 + 2 * t + (q & 1) + 8 * (q >> 1);
+        const int lr = 2 * t + (q & 1) + 8 * (q >> 1);
         float x = 0.f;
-        if (row < n) {
-          const float dd = __bfloat162float(d[row]);
-          x = (g == 0) ? __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(hvec[row])))
-                       : __bfloat162float(__float2bfloat16_rn(__bfloat162float(vvec[row]) / dd));
+        if (ck * 16 + lr < n) {
+          const float dd = __bfloat162float(vl[lr]);
+          x = (g == 0) ? __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(vl[16 + lr])))
+                       : __bfloat162float(__float2bfloat16_rn(__bfloat162float(vl[32 + lr]) / dd));
         }
         xv[q] = x;
         sq = fmaf(x, x, sq);
@@ -146,9 +161,6 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
       xb0 = pack_bf16(xv[0], xv[1]);
       xb1 = pack_bf16(xv[2], xv[3]);
     }
-    cp_async_wait<STAGES - 1>();
-    __syncwarp();
-    const uint32_t tile = ring + stage * Tl::BYTES;
     // F[c] = transposed 8x8 blocks (k rows 0-7 | 8-15) x (column chunks 2c, 2c+1): A fragment of m-tile c and B fragments of n-tiles 2c, 2c+1
     uint32_t F[MT][4];
 #pragma unroll
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
                                                            const float* __restrict__ par, int update_U, float* __restrict__ dd_out,
                                                            float* __restrict__ scal_out) {
   using Tl = LraTile<RP>;
-  constexpr int STAGES = 4;
+  constexpr int STAGES = LRA_STAGES;
   constexpr int KS = RP / 16;   // k-steps of the rotation products
   constexpr int NT = RP / 8;    // 8-col n-tiles of one factor
   constexpr int HC = Tl::CPR / 2;
@@ -259,7 +271,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
   long long ck_issue = gw;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s * Tl::BYTES, lane);
+    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s * Tl::BYTES, lane);
     cp_async_commit();
     ck_issue += tw;
   }
@@ -268,25 +280,28 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
     // the slot refilled now is the one whose coalesced stores were issued last iteration (they read smem synchronously) -> safe
     {
       const int s_issue = (stage + STAGES - 1) % STAGES;
-      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
+      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
       cp_async_commit();
       ck_issue += tw;
-    }
-    // per-row inputs of rows g and g+8
-    float dd[2], hh[2], vv[2];
-    bool rok[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const long long row = ck * 16 + g + 8 * q;
-      rok[q] = row < n;
-      dd[q] = rok[q] ? __bfloat162float(d[row]) : 1.f;
-      hh[q] = rok[q] ? __bfloat162float(hvec[row]) : 0.f;
-      vv[q] = rok[q] ? __bfloat162float(vvec[row]) : 0.f;
     }
     cp_async_wait<STAGES - 1>();
     __syncwarp();
     const uint32_t tile = ring + stage * Tl::BYTES;
     uint8_t* tile_gen = ring_gen + stage * Tl::BYTES;
+    // per-row inputs of rows g and g+8 (streamed with the tile)
+    float dd[2], hh[2], vv[2];
+    bool rok[2];
+    {
+      const bf16* vl = reinterpret_cast<const bf16*>(tile_gen + Tl::VEC_OFF);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int lr = g + 8 * q;
+        rok[q] = ck * 16 + lr < n;
+        dd[q] = rok[q] ? __bfloat162float(vl[lr]) : 1.f;
+        hh[q] = rok[q] ? __bfloat162float(vl[16 + lr]) : 0.f;
+        vv[q] = rok[q] ? __bfloat162float(vl[32 + lr]) : 0.f;
+      }
+    }
     // A fragments (row-major 16 x 16 per k-step): matrices (rows 0-7, chunk 2ks), (rows 8-15, chunk 2ks), (rows 0-7, chunk 2ks+1), (rows 8-15, 2ks+1)
     uint32_t au[KS][4], av[KS][4];
 #pragma unroll
@@ -393,6 +408,93 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
   if (threadIdx.x == 0) atomic_max_nonneg(&scal_out[LS_MAX_PHH], mx1);
   mx2 = block_max(mx2, red);
   if (threadIdx.x == 0) atomic_max_nonneg(&scal_out[LS_MAX_VINV], mx2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply sweeps (psgd.py:1055-1063), bf16, rank 16/32: fully coalesced mapping -- lane = (row within a group of 32/PPR rows, 16-byte
+// piece of that row); row dot products are reduced across the PPR lanes of a row with shuffles, the r-vector accumulators are split by
+// piece so every lane carries only 8 of them.
+//   mode 0: p1 += V_i * (d_i g_i)      mode 1: g2_i = d_i g_i + U_i . p1 (fp32, stored) ; p2 += U_i * g2_i      mode 2: out_i = d_i (g2_i + V_i . p2)
+// ------------------------------------------------------------------------------------------------
+template <int RP>
+__global__ void __launch_bounds__(256) k_lra_apply_bf16(const bf16* __restrict__ Mtx, const bf16* __restrict__ d, const bf16* __restrict__ g,
+                                                        float* __restrict__ g2, bf16* __restrict__ out, long long n, int mode,
+                                                        const float* __restrict__ pin, float* __restrict__ pout, float* sumsq) {
+  constexpr int PPR = RP / 8;          // 16-byte pieces per row
+  constexpr int RPI = 32 / PPR;        // rows per warp instruction
+  constexpr int UNR = 4;
+  __shared__ float pacc[RP];
+  const int lane = threadIdx.x & 31;
+  const int piece = lane % PPR, rsub = lane / PPR;
+  if (threadIdx.x < RP) pacc[threadIdx.x] = 0.f;
+  float pv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) pv[c] = (mode > 0) ? pin[piece * 8 + c] : 0.f;
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  float ssq = 0.f;
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long ngroups = (n + RPI - 1) / RPI;
+  for (long long grp0 = gwarp * UNR; grp0 < ngroups; grp0 += nwarps * UNR) {
+    uint4 raw[UNR];
+    float dd[UNR], gg[UNR], g2v[UNR];
+    bool ok[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long row = (grp0 + u) * RPI + rsub;
+      ok[u] = row < n;
+      raw[u] = ok[u] ? *reinterpret_cast<const uint4*>(Mtx + row * RP + piece * 8) : make_uint4(0u, 0u, 0u, 0u);
+      dd[u] = ok[u] ? __bfloat162float(d[row]) : 0.f;
+      gg[u] = (ok[u] && mode < 2) ? __bfloat162float(g[row]) : 0.f;
+      g2v[u] = (ok[u] && mode == 2) ? g2[row] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long row = (grp0 + u) * RPI + rsub;
+      float x[8];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { float2 f = __bfloat1622float2(h2[c]); x[2 * c] = f.x; x[2 * c + 1] = f.y; }
+      if (mode == 0) {
+        const float y = __bfloat162float(__float2bfloat16_rn(dd[u] * gg[u]));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(x[c], y, acc[c]);
+      } else {
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dot = fmaf(x[c], pv[c], dot);
+#pragma unroll
+        for (int o = 1; o < PPR; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (mode == 1) {
+          const float y = __bfloat162float(__float2bfloat16_rn(dd[u] * gg[u])) + dot;
+          if (ok[u] && piece == 0) g2[row] = y;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = fmaf(x[c], ok[u] ? y : 0.f, acc[c]);
+        } else {
+          const bf16 o = __float2bfloat16_rn(dd[u] * (g2v[u] + dot));
+          if (ok[u] && piece == 0) { out[row] = o; const float f = __bfloat162float(o); ssq = fmaf(f, f, ssq); }
+        }
+      }
+    }
+  }
+  if (mode < 2) {
+    // reduce over the lanes that share a piece (lane bits above log2(PPR)), then block (smem), then global
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v = acc[c];
+#pragma unroll
+      for (int o = PPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (rsub == 0) atomicAdd(&pacc[piece * 8 + c], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < RP) atomicAdd(&pout[threadIdx.x], pacc[threadIdx.x]);
+  } else if (sumsq) {
+    float v = warp_sum(ssq);
+    if (lane == 0) atomicAdd(sumsq, v);
+  }
 }
 
 }  // namespace psgd
