@@ -153,6 +153,7 @@ struct GemmDesc {
   int ta, tb;  // ta: A stored K x M; tb: B stored N x K
   int M, N, K;
   int in_dtype;
+  int sym;  // output is symmetric (C = X X^T or X^T X, M == N): the tcgen05 path computes the upper 128-blocks only and mirrors them
   Epi epi;
 };
 

@@ -34,6 +34,7 @@ struct alignas(64) TcProblem {
   Epi epi;
   int M, N, K;
   int a_mn, b_mn;  // operand is MN-major in memory
+  int sym;         // symmetric output: only tiles that reach the upper triangle are enumerated
   int tiles_m, tiles_n;
   int tile_start;  // first flat tile index of this problem
 };
@@ -144,13 +145,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // flat tile -> (problem, tile_m, tile_n); m-grouped rasterisation (8 row-tiles per group) for L2 reuse
-__device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int& pi, int& tm, int& tn) {
+__device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int bn, int& pi, int& tm, int& tn) {
   pi = 0;
 #pragma unroll
   for (int i = 1; i < TC_MAX_PROBLEMS; ++i)
     if (i < g.num_problems && t >= g.p[i].tile_start) pi = i;
   const TcProblem& p = g.p[pi];
   int lt = t - p.tile_start;
+  if (p.sym) {
+    // row tm owns the tiles tn >= tn_min(tm) = floor(tm * 128 / BN): those whose last column reaches the diagonal block of row tm
+    tm = 0;
+    while (true) {
+      const int cnt = p.tiles_n - (tm * TC_BM) / bn;
+      if (lt < cnt) break;
+      lt -= cnt;
+      ++tm;
+    }
+    tn = (tm * TC_BM) / bn + lt;
+    return;
+  }
   const int GROUP = 8;
   int per_group = GROUP * p.tiles_n;
   int gidx = lt / per_group;
@@ -168,8 +181,10 @@ struct RowAcc {
   float row_sumsq, tot, amax, tr, dmax;
 };
 
+// mirror: 0 = plain block, 1 = strictly-upper block of a symmetric output (also writes C[col][row] and credits the column sums to
+// row_sumsq[col], i.e. the row norms of the mirrored block)
 __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int row, int col0, uint32_t* raw, float alpha,
-                                               float beta, int lane, RowAcc& ra) {
+                                               float beta, int lane, RowAcc& ra, int mirror) {
   float v[32];
   const bool row_ok = row < M;
   const float rs = (e.row_scale && row_ok) ? e.row_scale[row] : 1.f;
@@ -230,6 +245,19 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
         *reinterpret_cast<float4*>(cp + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
     }
   }
+  if (mirror) {  // C[col0 + j][row] = v[j]: for a fixed j the 32 lanes (consecutive rows) write 64 contiguous bytes
+    if (e.out_dtype == PSGD_BF16) {
+      bf16* cp = reinterpret_cast<bf16*>(e.C) + (size_t)col0 * e.ldc + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (row_ok && col0 + j < N) cp[(size_t)j * e.ldc] = __float2bfloat16_rn(v[j]);
+    } else {
+      float* cp = reinterpret_cast<float*>(e.C) + (size_t)col0 * e.ldc + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (row_ok && col0 + j < N) cp[(size_t)j * e.ldc] = v[j];
+    }
+  }
   // reductions over the rounded values; out-of-range elements contribute 0
   const bool need_red = e.row_sumsq || e.col_sumsq || e.total_sumsq || e.abs_max || e.trace || e.diag_max;
   if (!need_red) return;
@@ -240,7 +268,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
 #pragma unroll
   for (int j = 0; j < 32; ++j) { s = fmaf(v[j], v[j], s); am = fmaxf(am, fabsf(v[j])); }
   ra.row_sumsq += s;
-  ra.tot += s;
+  ra.tot += mirror ? 2.f * s : s;
   ra.amax = fmaxf(ra.amax, am);
   if ((e.trace || e.diag_max) && row >= col0 && row < col0 + 32) {
     float dv = 0.f;
@@ -250,7 +278,8 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
     ra.tr += dv;
     ra.dmax = fmaxf(ra.dmax, dv);
   }
-  if (e.col_sumsq) {
+  float* csq = mirror ? e.row_sumsq : e.col_sumsq;
+  if (csq) {
     // transpose-reduce: after the 5 halving steps lane l holds sum over the warp's 32 rows of column col0 + l
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
@@ -266,7 +295,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
     }
     PSGD_TR_STEP(16) PSGD_TR_STEP(8) PSGD_TR_STEP(4) PSGD_TR_STEP(2) PSGD_TR_STEP(1)
 #undef PSGD_TR_STEP
-    if (col0 + lane < N) atomicAdd(&e.col_sumsq[col0 + lane], v[0]);
+    if (col0 + lane < N) atomicAdd(&csq[col0 + lane], v[0]);
   }
 }
 
@@ -321,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
         int pi, tm, tn;
-        locate_tile(g, t, pi, tm, tn);
+        locate_tile(g, t, BN, pi, tm, tn);
         const TcProblem& p = g.p[pi];
         const int num_kb = (p.K + TC_BK - 1) / TC_BK;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -356,7 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
         int pi, tm, tn;
-        locate_tile(g, t, pi, tm, tn);
+        locate_tile(g, t, BN, pi, tm, tn);
         const TcProblem& p = g.p[pi];
         const int num_kb = (p.K + TC_BK - 1) / TC_BK;
         // instruction descriptor: D=f32 (bit4), A=bf16 (bit7), B=bf16 (bit10), a_major bit15, b_major bit16,
@@ -395,7 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       int pi, tm, tn;
-      locate_tile(g, t, pi, tm, tn);
+      locate_tile(g, t, BN, pi, tm, tn);
       const TcProblem& p = g.p[pi];
       const Epi& e = p.epi;
       const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
@@ -407,11 +436,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = tn * BN + c * 32;
+        int mirror = 0;
+        if (p.sym) {  // 128-block classification: below the diagonal block -> produced by the mirror of its transpose, skip
+          const int cb = col0 >> 7;
+          if (cb < tm) continue;
+          mirror = cb > tm;
+        }
         uint32_t raw[32];
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
         tmem_ld_32x32(taddr, raw);
         tmem_ld_wait();
-        if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra);
+        if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
       }
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
@@ -494,7 +529,12 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     p.tiles_m = (g.M + TC_BM - 1) / TC_BM;
     p.tiles_n = (g.N + BN - 1) / BN;
     p.tile_start = tiles;
-    tiles += p.tiles_m * p.tiles_n;
+    p.sym = (g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
+    if (p.sym) {
+      for (int tm = 0; tm < p.tiles_m; ++tm) tiles += p.tiles_n - (tm * TC_BM) / BN;
+    } else {
+      tiles += p.tiles_m * p.tiles_n;
+    }
   }
   grp.num_problems = n;
   grp.total_tiles = tiles;

@@ -56,32 +56,60 @@ template <int RP> struct LraTile {
   __device__ static __forceinline__ uint32_t off(int row, int chunk) { return row * ROW_BYTES + ((chunk ^ swz(row)) << 4); }
 };
 
-// issue the cp.async loads of chunk `ck` (rows ck*16 ..) into the tile at smem address `tile`; rows >= n are zero-filled
-template <int RP>
-__device__ __forceinline__ void lra_issue_chunk(const bf16* __restrict__ U, const bf16* __restrict__ V, const bf16* __restrict__ d,
-                                                const bf16* __restrict__ hvec, const bf16* __restrict__ vvec, long long n, long long ck,
-                                                uint32_t tile, int lane) {
+// per-lane constants of the chunk loader: piece i of this lane copies 16 bytes from (U or V) + chunk_base + src_off[i] to tile + dst_off[i]
+template <int RP> struct LraLoader {
   using Tl = LraTile<RP>;
-  constexpr int PIECES = 16 * Tl::CPR;  // 128 (RP=32) / 64 (RP=16)
+  static constexpr int NP = 16 * Tl::CPR / 32;   // pieces per lane: 4 (RP=32) / 2 (RP=16)
+  int src_off[NP];      // element offset inside the chunk
+  uint32_t dst_off[NP];
+  uint32_t is_v;        // bit i: piece i comes from V
+  int row[NP];
+  uint32_t vdst;        // vector piece (lanes 0..5): smem offset, source selector, element offset
+  int vwhich, vpiece;
+  __device__ __forceinline__ void init(int lane) {
+    is_v = 0;
 #pragma unroll
-  for (int i = 0; i < PIECES / 32; ++i) {
-    const int p = lane + 32 * i;
-    const int row = p / Tl::CPR, lc = p % Tl::CPR;
-    const long long grow = ck * 16 + row;
-    const bool isV = lc >= Tl::CPR / 2;
-    const bf16* src = (isV ? V : U) + grow * RP + (isV ? lc - Tl::CPR / 2 : lc) * 8;
-    const bool ok = grow < n;
-    cp_async16(tile + Tl::off(row, lc), ok ? (const void*)src : (const void*)U, ok ? 16 : 0);
+    for (int i = 0; i < NP; ++i) {
+      const int p = lane + 32 * i;
+      const int r = p / Tl::CPR, lc = p % Tl::CPR;
+      const bool v = lc >= Tl::CPR / 2;
+      row[i] = r;
+      src_off[i] = r * RP + (v ? lc - Tl::CPR / 2 : lc) * 8;
+      dst_off[i] = Tl::off(r, lc);
+      is_v |= (v ? 1u : 0u) << i;
+    }
+    vwhich = lane >> 1; vpiece = lane & 1;
+    vdst = Tl::VEC_OFF + vwhich * 32 + vpiece * 16;
   }
-  if (lane < 6) {  // the per-row vectors ride in the same pipeline: d, h, v, two 16-byte pieces (8 rows) each
-    const int which = lane >> 1, piece = lane & 1;
-    const bf16* vec = which == 0 ? d : (which == 1 ? hvec : vvec);
-    const long long r0 = ck * 16 + piece * 8;
-    long long valid = (n - r0) * 2;
-    valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
-    cp_async16(tile + Tl::VEC_OFF + which * 32 + piece * 16, valid > 0 ? (const void*)(vec + r0) : (const void*)U, (int)valid);
+  // rows >= n are zero-filled; the full-chunk fast path carries no per-piece predicate
+  __device__ __forceinline__ void issue(const bf16* __restrict__ U, const bf16* __restrict__ V, const bf16* __restrict__ d,
+                                        const bf16* __restrict__ hvec, const bf16* __restrict__ vvec, long long n, long long ck, uint32_t tile,
+                                        int lane) const {
+    const long long r0 = ck * 16;
+    const bf16* ub = U + r0 * RP;
+    const bf16* vb = V + r0 * RP;
+    if (r0 + 16 <= n) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) cp_async16(tile + dst_off[i], (((is_v >> i) & 1u) ? vb : ub) + src_off[i], 16);
+      if (lane < 6) {
+        const bf16* vec = vwhich == 0 ? d : (vwhich == 1 ? hvec : vvec);
+        cp_async16(tile + vdst, vec + r0 + vpiece * 8, 16);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const bool ok = r0 + row[i] < n;
+        cp_async16(tile + dst_off[i], ok ? (const void*)((((is_v >> i) & 1u) ? vb : ub) + src_off[i]) : (const void*)U, ok ? 16 : 0);
+      }
+      if (lane < 6) {
+        const bf16* vec = vwhich == 0 ? d : (vwhich == 1 ? hvec : vvec);
+        long long valid = (n - (r0 + vpiece * 8)) * 2;
+        valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
+        cp_async16(tile + vdst, valid > 0 ? (const void*)(vec + r0 + vpiece * 8) : (const void*)U, (int)valid);
+      }
+    }
   }
-}
+};
 
 // ------------------------------------------------------------------------------------------------
 // sweep 1: U^T U, V^T V, V^T U (RP x RP each) and the projections U^T x, V^T x for x1 = d.h, x2 = v/d, plus |x1|^2, |x2|^2
@@ -105,7 +133,15 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
   for (int e = threadIdx.x; e < 3 * RP * RP + 4 * RP + 2; e += blockDim.x) blk_acc[e] = 0.f;
   __syncthreads();
   const uint32_t ring = smem_u32_generic(smem_lra) + warp * STAGES * Tl::BYTES;
+  LraLoader<RP> loader;
+  loader.init(lane);
 
+  uint32_t ldoff[MT];   // ldmatrix.x4.trans row addresses of this lane: matrices 0,1 = k rows 0-7, 2,3 = k rows 8-15; chunk 2c + (mi & 1)
+#pragma unroll
+  for (int c = 0; c < MT; ++c) {
+    const int mi = lane >> 3, rr = lane & 7;
+    ldoff[c] = Tl::off((mi >> 1) * 8 + rr, 2 * c + (mi & 1));
+  }
   // accumulators: UtU tiles (mt < HM, nt in [2*mt, HN)), VtV tiles (mt >= HM, nt in [HN + 2*(mt-HM), NT)), VtU (mt >= HM, nt < HN), x (all mt)
   float aUU[HM][HN][4], aVV[HM][HN][4], aVU[HM][HN][4], aX[MT][4];
 #pragma unroll
@@ -126,7 +162,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
   long long ck_issue = gw;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s * Tl::BYTES, lane);
+    if (ck_issue < nchunks) loader.issue(U, V, d, hvec, vvec, n, ck_issue, ring + s * Tl::BYTES, lane);
     cp_async_commit();
     ck_issue += tw;
   }
@@ -134,7 +170,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
   for (long long ck = gw; ck < nchunks; ck += tw) {
     {  // keep the ring full
       const int s_issue = (stage + STAGES - 1) % STAGES;
-      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
+      if (ck_issue < nchunks) loader.issue(U, V, d, hvec, vvec, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
       cp_async_commit();
       ck_issue += tw;
     }
@@ -142,34 +178,30 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
     cp_async_wait<STAGES - 1>();
     __syncwarp();
     const uint32_t tile = ring + stage * Tl::BYTES;
-    uint32_t xb0 = 0u, xb1 = 0u;
-    if (g < 2) {
+    // x columns: lanes 0-15 form x1 = d*h of row `lane`, lanes 16-31 x2 = v/d of row `lane-16`; the B fragment of the x tile
+    // (column g: 0 -> x1, 1 -> x2, rest 0; rows 2t, 2t+1, 2t+8, 2t+9) is gathered with 4 shuffles
+    uint32_t xb0, xb1;
+    {
       const bf16* vl = reinterpret_cast<const bf16*>(smem_lra + warp * STAGES * Tl::BYTES + stage * Tl::BYTES + Tl::VEC_OFF);
-      float xv[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int lr = 2 * t + (q & 1) + 8 * (q >> 1);
-        float x = 0.f;
-        if (ck * 16 + lr < n) {
-          const float dd = __bfloat162float(vl[lr]);
-          x = (g == 0) ? __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(vl[16 + lr])))
-                       : __bfloat162float(__float2bfloat16_rn(__bfloat162float(vl[32 + lr]) / dd));
-        }
-        xv[q] = x;
-        sq = fmaf(x, x, sq);
+      const int xr = lane & 15;
+      float x = 0.f;
+      if (ck * 16 + xr < n) {
+        const float dd = __bfloat162float(vl[xr]);
+        x = (lane < 16) ? __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(vl[16 + xr])))
+                        : __bfloat162float(__float2bfloat16_rn(__bfloat162float(vl[32 + xr]) / dd));
       }
-      xb0 = pack_bf16(xv[0], xv[1]);
-      xb1 = pack_bf16(xv[2], xv[3]);
+      sq = fmaf(x, x, sq);
+      const int srcb = (g & 1) * 16 + 2 * t;
+      float x0 = __shfl_sync(0xffffffffu, x, srcb), x1 = __shfl_sync(0xffffffffu, x, srcb + 1);
+      float x2 = __shfl_sync(0xffffffffu, x, srcb + 8), x3 = __shfl_sync(0xffffffffu, x, srcb + 9);
+      if (g >= 2) { x0 = 0.f; x1 = 0.f; x2 = 0.f; x3 = 0.f; }
+      xb0 = pack_bf16(x0, x1);
+      xb1 = pack_bf16(x2, x3);
     }
     // F[c] = transposed 8x8 blocks (k rows 0-7 | 8-15) x (column chunks 2c, 2c+1): A fragment of m-tile c and B fragments of n-tiles 2c, 2c+1
     uint32_t F[MT][4];
 #pragma unroll
-    for (int c = 0; c < MT; ++c) {
-      const int mi = lane >> 3, rr = lane & 7;            // matrix index 0..3, row within it
-      const int krow = (mi >> 1) * 8 + rr;                // matrices 0,1: k rows 0-7; 2,3: k rows 8-15
-      const int chunk = 2 * c + (mi & 1);
-      ldsm_x4_trans(tile + Tl::off(krow, chunk), F[c]);
-    }
+    for (int c = 0; c < MT; ++c) ldsm_x4_trans(tile + ldoff[c], F[c]);
     __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -215,7 +247,12 @@ __global__ void __launch_bounds__(256, 1) k_lra_gram_mma(const bf16* __restrict_
         atomicAdd(&bP[(col * 2 + isV) * RP + (row - isV * RP)], aX[mt][e]);
       }
     }
-  if (g < 2) atomicAdd(&bP[4 * RP + g], sq);
+  {
+    float v = sq;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 15) == 0) atomicAdd(&bP[4 * RP + (lane >> 4)], v);
+  }
   __syncthreads();
   for (int e = threadIdx.x; e < 3 * RP * RP + 4 * RP + 2; e += blockDim.x) atomicAdd(&acc_out[e], blk_acc[e]);
 }
@@ -236,7 +273,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
   constexpr int NT = RP / 8;    // 8-col n-tiles of one factor
   constexpr int HC = Tl::CPR / 2;
   extern __shared__ __align__(128) uint8_t smem_lra[];
-  __shared__ float vecs[8][RP];   // c1, c2, s1, s2, wa|atU, wb|btU
+  __shared__ float wvec[2][RP];   // rank-2 update directions: (w_a, w_b) for U, (atU, btU) for V
   __shared__ float red[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -245,9 +282,8 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
   const bf16* EuT = reinterpret_cast<const bf16*>(par + lra_par_et_off(RP));
   const bf16* EvT = EuT + RP * RP;
   for (int e = threadIdx.x; e < RP; e += blockDim.x) {
-    vecs[0][e] = pvec[LV_C1 * RP + e]; vecs[1][e] = pvec[LV_C2 * RP + e]; vecs[2][e] = pvec[LV_S1 * RP + e]; vecs[3][e] = pvec[LV_S2 * RP + e];
-    vecs[4][e] = update_U ? pvec[LV_WA * RP + e] : pvec[LV_ATU * RP + e];
-    vecs[5][e] = update_U ? pvec[LV_WB * RP + e] : pvec[LV_BTU * RP + e];
+    wvec[0][e] = update_U ? pvec[LV_WA * RP + e] : pvec[LV_ATU * RP + e];
+    wvec[1][e] = update_U ? pvec[LV_WB * RP + e] : pvec[LV_BTU * RP + e];
   }
   __syncthreads();
   const float step = pscal[LS_STEP], inv_rho = pscal[LS_INV_RHO], rho = pscal[LS_RHO];
@@ -263,15 +299,55 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
       bv[nt][ks][0] = *reinterpret_cast<const uint32_t*>(EvT + nn * RP + kk);
       bv[nt][ks][1] = *reinterpret_cast<const uint32_t*>(EvT + nn * RP + kk + 8);
     }
+  // the per-row dot products ride on the tensor cores too: one extra 8-column tile per factor whose columns are the (hi, lo) bf16
+  // split of the rotated vectors -- U'_i . c = U_i . (Au c) --  U tile: [Au c1 | Au s2 | 0 0];  V tile: [Av c2 | Av s1 | Av atU | Av btU]
+  uint32_t du[KS][2], dv[KS][2];
+  {
+    const int vi = g >> 1, lo = g & 1;
+    const int uvec = vi == 0 ? LV_AUC1 : LV_AUS2;
+    const int vvecid = vi == 0 ? LV_AVC2 : (vi == 1 ? LV_AVS1 : (vi == 2 ? LV_AVATU : LV_AVBTU));
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int kk = 16 * ks + 2 * t + 8 * hf;
+        float f[2], w[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float xu = (vi < 2) ? pvec[uvec * RP + kk + e] : 0.f;
+          const float xv = (update_U && vi >= 2) ? 0.f : pvec[vvecid * RP + kk + e];
+          const float hu = __bfloat162float(__float2bfloat16_rn(xu)), hv = __bfloat162float(__float2bfloat16_rn(xv));
+          f[e] = lo ? xu - hu : hu;
+          w[e] = lo ? xv - hv : hv;
+        }
+        du[ks][hf] = pack_bf16(f[0], f[1]);
+        dv[ks][hf] = pack_bf16(w[0], w[1]);
+      }
+  }
   const uint32_t ring = smem_u32_generic(smem_lra) + warp * STAGES * Tl::BYTES;
+  LraLoader<RP> loader;
+  loader.init(lane);
   uint8_t* ring_gen = smem_lra + warp * STAGES * Tl::BYTES;
+  uint32_t ldoff_u[KS], ldoff_v[KS];   // ldmatrix.x4 (row-major A): matrices (rows 0-7, chunk 2ks), (rows 8-15, 2ks), (rows 0-7, 2ks+1), (rows 8-15, 2ks+1)
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int mi = lane >> 3, rr = lane & 7;
+    const int row = (mi & 1) * 8 + rr, chunk = 2 * ks + (mi >> 1);
+    ldoff_u[ks] = Tl::off(row, chunk);
+    ldoff_v[ks] = Tl::off(row, HC + chunk);
+  }
+  uint32_t stoff[NT][2];   // where element pair (row g + 8q, cols 8nt + 2t, +1) of U lives in the tile (V: chunk + HC)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) stoff[nt][q] = Tl::off(g + 8 * q, nt) + 4 * t;
   float mx1 = 0.f, mx2 = 0.f;
   const long long nchunks = (n + 15) / 16;
   const long long gw = (long long)blockIdx.x * 8 + warp, tw = (long long)gridDim.x * 8;
   long long ck_issue = gw;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s * Tl::BYTES, lane);
+    if (ck_issue < nchunks) loader.issue(U, V, d, hvec, vvec, n, ck_issue, ring + s * Tl::BYTES, lane);
     cp_async_commit();
     ck_issue += tw;
   }
@@ -280,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
     // the slot refilled now is the one whose coalesced stores were issued last iteration (they read smem synchronously) -> safe
     {
       const int s_issue = (stage + STAGES - 1) % STAGES;
-      if (ck_issue < nchunks) lra_issue_chunk<RP>(U, V, d, hvec, vvec, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
+      if (ck_issue < nchunks) loader.issue(U, V, d, hvec, vvec, n, ck_issue, ring + s_issue * Tl::BYTES, lane);
       cp_async_commit();
       ck_issue += tw;
     }
@@ -302,17 +378,12 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
         vv[q] = rok[q] ? __bfloat162float(vl[32 + lr]) : 0.f;
       }
     }
-    // A fragments (row-major 16 x 16 per k-step): matrices (rows 0-7, chunk 2ks), (rows 8-15, chunk 2ks), (rows 0-7, chunk 2ks+1), (rows 8-15, 2ks+1)
     uint32_t au[KS][4], av[KS][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const int mi = lane >> 3, rr = lane & 7;
-      const int row = (mi & 1) * 8 + rr;
-      const int chunk = 2 * ks + (mi >> 1);
-      ldsm_x4(tile + Tl::off(row, chunk), au[ks]);
-      ldsm_x4(tile + Tl::off(row, HC + chunk), av[ks]);
-    }
-    float cu[NT][4], cv[NT][4];
+    for (int ks = 0; ks < KS; ++ks) { ldsm_x4(tile + ldoff_u[ks], au[ks]); ldsm_x4(tile + ldoff_v[ks], av[ks]); }
+    float cu[NT][4], cv[NT][4], dotu[4] = {0.f, 0.f, 0.f, 0.f}, dotv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) { mma16816(dotu, au[ks], du[ks][0], du[ks][1]); mma16816(dotv, av[ks], dv[ks][0], dv[ks][1]); }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
@@ -320,84 +391,66 @@ __global__ void __launch_bounds__(256, 1) k_lra_rotate_mma(bf16* __restrict__ U,
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) { mma16816(cu[nt], au[ks], bu[nt][ks][0], bu[nt][ks][1]); mma16816(cv[nt], av[ks], bv[nt][ks][0], bv[nt][ks][1]); }
     }
-    // rotated rows in registers: element e of tile nt = (row g + 8*(e>>1), col 8nt + 2t + (e&1)); the unrotated value sits in the A fragment
-    float duc1[2] = {0.f, 0.f}, dus2[2] = {0.f, 0.f}, dvc2[2] = {0.f, 0.f}, dvs1[2] = {0.f, 0.f}, dva[2] = {0.f, 0.f}, dvb[2] = {0.f, 0.f};
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const int ks = nt >> 1, hi = nt & 1;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float2 u0 = unpack_bf16(au[ks][2 * hi + q]);
-        const float2 v0 = unpack_bf16(av[ks][2 * hi + q]);
-        const float un[2] = {(u0.x - cu[nt][2 * q]) * inv_rho, (u0.y - cu[nt][2 * q + 1]) * inv_rho};
-        const float vn[2] = {(v0.x + cv[nt][2 * q]) * rho, (v0.y + cv[nt][2 * q + 1]) * rho};
-        cu[nt][2 * q] = un[0]; cu[nt][2 * q + 1] = un[1];
-        cv[nt][2 * q] = vn[0]; cv[nt][2 * q + 1] = vn[1];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = 8 * nt + 2 * t + e;
-          duc1[q] = fmaf(un[e], vecs[0][col], duc1[q]);
-          dus2[q] = fmaf(un[e], vecs[3][col], dus2[q]);
-          dvc2[q] = fmaf(vn[e], vecs[1][col], dvc2[q]);
-          dvs1[q] = fmaf(vn[e], vecs[2][col], dvs1[q]);
-          if (!update_U) { dva[q] = fmaf(vn[e], vecs[4][col], dva[q]); dvb[q] = fmaf(vn[e], vecs[5][col], dvb[q]); }
-        }
-      }
-    }
+    // dot tile: lane t holds vector t's (hi, lo) columns for rows g (c0, c1) and g+8 (c2, c3); broadcast inside the quad
+    float a_[2], b_[2], ca[2], cb[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-#pragma unroll
-      for (int o = 1; o <= 2; o <<= 1) {
-        duc1[q] += __shfl_xor_sync(0xffffffffu, duc1[q], o); dus2[q] += __shfl_xor_sync(0xffffffffu, dus2[q], o);
-        dvc2[q] += __shfl_xor_sync(0xffffffffu, dvc2[q], o); dvs1[q] += __shfl_xor_sync(0xffffffffu, dvs1[q], o);
-        dva[q] += __shfl_xor_sync(0xffffffffu, dva[q], o); dvb[q] += __shfl_xor_sync(0xffffffffu, dvb[q], o);
-      }
-    }
-    float ca[2], cb[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
+      const float su = dotu[2 * q] + dotu[2 * q + 1], sv = dotv[2 * q] + dotv[2 * q + 1];
+      const int qb = lane & ~3;
+      const float duc1 = __shfl_sync(0xffffffffu, su, qb), dus2 = __shfl_sync(0xffffffffu, su, qb + 1);
+      const float dvc2 = __shfl_sync(0xffffffffu, sv, qb), dvs1 = __shfl_sync(0xffffffffu, sv, qb + 1);
+      const float dva = __shfl_sync(0xffffffffu, sv, qb + 2), dvb = __shfl_sync(0xffffffffu, sv, qb + 3);
       const float x1 = __bfloat162float(__float2bfloat16_rn(dd[q] * hh[q]));
       const float x2 = __bfloat162float(__float2bfloat16_rn(vv[q] / dd[q]));
-      const float a = x1 + duc1[q];                 // Qh_i          psgd.py:1017
-      const float Ph = dd[q] * (a + dvc2[q]);       // Ph_i          psgd.py:1018
-      const float b = x2 - dvs1[q];                 // invQtv_i      psgd.py:1024
-      const float invPv = (b - dus2[q]) / dd[q];    // invPv_i       psgd.py:1025-1026
+      const float a = x1 + duc1;                    // Qh_i          psgd.py:1017
+      const float Ph = dd[q] * (a + dvc2);          // Ph_i          psgd.py:1018
+      const float b = x2 - dvs1;                    // invQtv_i      psgd.py:1024
+      const float invPv = (b - dus2) / dd[q];       // invPv_i       psgd.py:1025-1026
       const float Phh = Ph * hh[q], vinv = vv[q] * invPv;
       if (rok[q]) {
         mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
         if (t == 0) dd_out[ck * 16 + g + 8 * q] = Phh - vinv;
       }
-      ca[q] = update_U ? step * a : step * (a + dva[q]);
-      cb[q] = update_U ? step * b : step * (b + dvb[q]);
+      a_[q] = a; b_[q] = b;
+      ca[q] = update_U ? step * a : step * (a + dva);
+      cb[q] = update_U ? step * b : step * (b + dvb);
     }
     __syncwarp();   // all lanes have consumed their ldmatrix data before the tile is overwritten
-    // rank-2 update + write the new rows back into the tile (same swizzled positions the fragments came from)
+    // rotation (identity part exact, correction from the MMA), rank-2 update, write back into the tile at the fragment positions
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
+      const int ks = nt >> 1, hi = nt & 1;
+      const float wa0 = wvec[0][8 * nt + 2 * t], wa1 = wvec[0][8 * nt + 2 * t + 1];
+      const float wb0 = wvec[1][8 * nt + 2 * t], wb1 = wvec[1][8 * nt + 2 * t + 1];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int row = g + 8 * q, col = 8 * nt + 2 * t;
-        float u0 = cu[nt][2 * q], u1 = cu[nt][2 * q + 1], v0 = cv[nt][2 * q], v1 = cv[nt][2 * q + 1];
-        const float w0 = ca[q] * vecs[4][col] - cb[q] * vecs[5][col], w1 = ca[q] * vecs[4][col + 1] - cb[q] * vecs[5][col + 1];
-        if (update_U) { u0 -= w0; u1 -= w1; } else { v0 -= w0; v1 -= w1; }
-        // chunk index within the row: col / 8 = nt (U) or HC + nt (V); byte offset within chunk: (col % 8) * 2 = 4t
-        *reinterpret_cast<uint32_t*>(tile_gen + Tl::off(row, nt) + 4 * t) = pack_bf16(u0, u1);
-        *reinterpret_cast<uint32_t*>(tile_gen + Tl::off(row, HC + nt) + 4 * t) = pack_bf16(v0, v1);
+        const float2 u0 = unpack_bf16(au[ks][2 * hi + q]);
+        const float2 v0 = unpack_bf16(av[ks][2 * hi + q]);
+        float un0 = (u0.x - cu[nt][2 * q]) * inv_rho, un1 = (u0.y - cu[nt][2 * q + 1]) * inv_rho;
+        float vn0 = (v0.x + cv[nt][2 * q]) * rho, vn1 = (v0.y + cv[nt][2 * q + 1]) * rho;
+        const float w0 = ca[q] * wa0 - cb[q] * wb0, w1 = ca[q] * wa1 - cb[q] * wb1;
+        if (update_U) { un0 -= w0; un1 -= w1; } else { vn0 -= w0; vn1 -= w1; }
+        *reinterpret_cast<uint32_t*>(tile_gen + stoff[nt][q]) = pack_bf16(un0, un1);
+        *reinterpret_cast<uint32_t*>(tile_gen + (stoff[nt][q] ^ (uint32_t(HC) << 4))) = pack_bf16(vn0, vn1);
       }
     }
     __syncwarp();
-    // coalesced 16-byte stores, mirror image of lra_issue_chunk
-    constexpr int PIECES = 16 * Tl::CPR;
+    // coalesced 16-byte stores, mirror image of the loader
+    if (ck * 16 + 16 <= n) {
 #pragma unroll
-    for (int i = 0; i < PIECES / 32; ++i) {
-      const int p = lane + 32 * i;
-      const int row = p / Tl::CPR, lc = p % Tl::CPR;
-      const long long grow = ck * 16 + row;
-      if (grow < n) {
-        const uint4 val = *reinterpret_cast<const uint4*>(tile_gen + Tl::off(row, lc));
-        const bool isV = lc >= HC;
-        bf16* dst = (isV ? V : U) + grow * RP + (isV ? lc - HC : lc) * 8;
+      for (int i = 0; i < LraLoader<RP>::NP; ++i) {
+        const uint4 val = *reinterpret_cast<const uint4*>(tile_gen + loader.dst_off[i]);
+        bf16* dst = (((loader.is_v >> i) & 1u) ? V : U) + ck * 16 * RP + loader.src_off[i];
         *reinterpret_cast<uint4*>(dst) = val;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LraLoader<RP>::NP; ++i) {
+        if (ck * 16 + loader.row[i] < n) {
+          const uint4 val = *reinterpret_cast<const uint4*>(tile_gen + loader.dst_off[i]);
+          bf16* dst = (((loader.is_v >> i) & 1u) ? V : U) + ck * 16 * RP + loader.src_off[i];
+          *reinterpret_cast<uint4*>(dst) = val;
+        }
       }
     }
     __syncwarp();

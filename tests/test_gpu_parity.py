@@ -65,7 +65,9 @@ def _structured(m, n, seed, dtype):
 @pytest.mark.parametrize("shape,dtype,path", [
     ((256, 384), torch.bfloat16, 0),   # tcgen05 path, dense x dense, P-first on the left
     ((384, 256), torch.bfloat16, 0),   # P-first on the right
-    ((256, 256), torch.bfloat16, 0),   # square chain
+    ((256, 256), torch.bfloat16, 0),   # square: both P-first, SYRKs grouped
+    ((640, 896), torch.bfloat16, 0),   # several tile rows of the symmetric (upper-blocks-only) products
+    ((1024, 1024), torch.bfloat16, 0),
     ((256, 256), torch.bfloat16, 1),   # same through the SIMT kernels
     ((128, 2048), torch.bfloat16, 0),  # dense x diag (k_proj-like)
     ((2048, 128), torch.bfloat16, 0),  # diag x dense (gate_proj-like)
