@@ -101,6 +101,7 @@ struct KronWs {
   float* bal;       // 2 floats (max|QL|, max|QR|)
   // buffers
   float* qsq[2];    // fp32 squares of diagonal factors
+  float* presid[2]; // fp32 rounding residual of diag(P_L), diag(P_R)
   void* B0; void* B1; void* B2;   // m x n
   void* S[2][4];    // per dense factor, s x s each: T (Gram, later R), Qn, RQ, RRQ   (the Qn slots double as P_L / P_R in the chain)
   void* Va[2]; void* Vb[2];       // per dense factor: 32 x s probe buffers
@@ -137,6 +138,8 @@ static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
   w.zero_bytes = b.off - z0;
   w.qsq[0] = (float*)b.take(m * 4);
   w.qsq[1] = (float*)b.take(n * 4);
+  w.presid[0] = (float*)b.take(m * 4);
+  w.presid[1] = (float*)b.take(n * 4);
   w.B0 = b.take(m * n * es); w.B1 = b.take(m * n * es); w.B2 = b.take(m * n * es);
   for (int i = 0; i < 2; ++i) {
     const size_t sd = dense[i] ? (size_t)sdim[i] : 0;
@@ -315,6 +318,10 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
   auto set_final = [&](GemmDesc& gd) {
     gd.epi.row_scale = rs; gd.epi.col_scale = cs;
     gd.epi.row_sumsq = row_sumsq; gd.epi.col_sumsq = col_sumsq; gd.epi.total_sumsq = total_sumsq;
+    if (gd.epi.D) {  // the residual term resid * X must carry the diagonal factor's q^2 scaling too
+      if (rs && !gd.epi.d_row_scale) gd.epi.d_row_scale = rs;
+      if (cs && !gd.epi.d_col_scale) gd.epi.d_col_scale = cs;
+    }
   };
   // P-first (P = Q^T Q is symmetric: the tensor-core path computes its upper 128-blocks only, ~1.06 s^3 instead of 2 s^3) costs
   // 1.06 m^3 + 2 m^2 n on the left against 4 m^2 n for the chain Q_L^T (Q_L X): take it whenever m < 1.88 n (same on the right).
@@ -323,14 +330,16 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
   {
     GemmDesc sy[2];
     int ns = 0;
-    if (pl) { sy[ns] = gemm_desc(dt, k->QL, m, 1, k->QL, m, 0, m, m, m, PL, m); sy[ns].sym = 1; ++ns; }
-    if (pr) { sy[ns] = gemm_desc(dt, k->QR, n, 1, k->QR, n, 0, n, n, n, PR, n); sy[ns].sym = 1; ++ns; }
+    if (pl) { sy[ns] = gemm_desc(dt, k->QL, m, 1, k->QL, m, 0, m, m, m, PL, m); sy[ns].sym = 1; sy[ns].epi.diag_resid = w.presid[0]; ++ns; }
+    if (pr) { sy[ns] = gemm_desc(dt, k->QR, n, 1, k->QR, n, 0, n, n, n, PR, n); sy[ns].sym = 1; sy[ns].epi.diag_resid = w.presid[1]; ++ns; }
     rc = launch_gemm_group(ctx, sy, ns, st); if (rc) return rc;
   }
   if (dl) {
     if (pl) {
       void* dstL = dr ? ((X == w.B0) ? w.B2 : w.B0) : out;
       g = gemm_desc(dt, PL, m, 0, X, n, 0, m, n, m, dstL, n);
+      // (P_bf16 + diag(resid)) X: the diagonal of P is large and nearly constant, its bf16 rounding would be a systematic bias
+      g.epi.D = X; g.epi.ldd = n; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.d_row_scale = w.presid[0];
       if (!dr) set_final(g);
       rc = launch_gemm(ctx, g, st); if (rc) return rc;
       Y = dstL;
@@ -348,6 +357,7 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
   if (dr) {
     if (pr) {
       g = gemm_desc(dt, Y, n, 0, PR, n, 0, m, n, n, out, n);
+      g.epi.D = Y; g.epi.ldd = n; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.d_col_scale = w.presid[1];
       set_final(g);
       rc = launch_gemm(ctx, g, st); if (rc) return rc;
     } else {      // Y Q_R^T then (.) Q_R

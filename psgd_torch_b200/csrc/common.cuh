@@ -42,7 +42,7 @@ __host__ __device__ inline float dtype_tiny(int) { return 1.1754943508222875e-38
 
 // ---------------------------------------------------------------------------------------------
 // Fused GEMM epilogue, shared by the SIMT and the tcgen05 kernels:
-//   v        = acc * alpha * (*alpha_ptr) * row_scale[i] * col_scale[j]  +  beta * (*beta_ptr) * D[i,j]
+//   v        = acc * alpha * (*alpha_ptr) * row_scale[i] * col_scale[j]  +  beta * (*beta_ptr) * D[i,j] * d_row_scale[i] * d_col_scale[j]
 //   C[i,j]   = round_to(out_dtype, v)
 //   reductions below are taken over the ROUNDED values (the reference computes its norms / traces on the
 //   materialised low-precision tensors), accumulated with atomics into fp32 device buffers that the caller
@@ -61,6 +61,9 @@ struct Epi {
   const float* beta_ptr;
   const float* row_scale;  // length M (fp32) or null
   const float* col_scale;  // length N (fp32) or null
+  const float* d_row_scale;  // optional per-row / per-column factors of the D term (fp32): used to add back the bf16 rounding residual of
+  const float* d_col_scale;  // the diagonal of P = Q^T Q, (P_bf16 + diag(resid)) X = P_bf16 X + resid_i X_ij
+  float* diag_resid;       // [M]: (unrounded - rounded) value of C[i,i]
   float* row_sumsq;        // [M] += sum_j C[i,j]^2
   float* col_sumsq;        // [N] += sum_i C[i,j]^2
   float* diag_max;         // max_i C[i,i]   (values assumed >= 0; buffer zero-initialised)
@@ -74,7 +77,7 @@ __host__ inline Epi make_epi(void* C, int ldc, int out_dtype) {
   e.C = C; e.ldc = ldc; e.out_dtype = out_dtype;
   e.alpha = 1.f; e.alpha_ptr = nullptr;
   e.D = nullptr; e.ldd = 0; e.d_dtype = out_dtype; e.beta = 0.f; e.beta_ptr = nullptr;
-  e.row_scale = nullptr; e.col_scale = nullptr;
+  e.row_scale = nullptr; e.col_scale = nullptr; e.d_row_scale = nullptr; e.d_col_scale = nullptr; e.diag_resid = nullptr;
   e.row_sumsq = nullptr; e.col_sumsq = nullptr; e.diag_max = nullptr; e.abs_max = nullptr; e.trace = nullptr;
   e.total_sumsq = nullptr;
   return e;

@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
       if (gn >= N) continue;
       float v = acc[i][j] * alpha * rs;
       if (e.col_scale) v *= e.col_scale[gn];
-      if (e.D) v += beta * ld_as_float(e.D, e.d_dtype, (size_t)gm * e.ldd + gn);
+      if (e.D) v += beta * ld_as_float(e.D, e.d_dtype, (size_t)gm * e.ldd + gn) * (e.d_row_scale ? e.d_row_scale[gm] : 1.f) * (e.d_col_scale ? e.d_col_scale[gn] : 1.f);
       float r = round_to(e.out_dtype, v);
+      if (e.diag_resid && gm == gn) e.diag_resid[gm] = v - r;
       st_from_float(e.C, e.out_dtype, (size_t)gm * e.ldc + gn, v);
       rsum += r * r;
       csum[j] += r * r;

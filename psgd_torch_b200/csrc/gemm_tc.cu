@@ -195,6 +195,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
     for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < N) ? e.col_scale[col0 + j] : 0.f;
   }
   if (e.D && row_ok) {
+    const float drs = beta * (e.d_row_scale ? e.d_row_scale[row] : 1.f);
     if (e.d_dtype == PSGD_BF16) {
       const bf16* dp = reinterpret_cast<const bf16*>(e.D) + (size_t)row * e.ldd + col0;
 #pragma unroll
@@ -205,8 +206,9 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             float2 f = __bfloat1622float2(h[t]);
-            v[q * 8 + 2 * t] += beta * f.x;
-            v[q * 8 + 2 * t + 1] += beta * f.y;
+            const int cc = col0 + q * 8 + 2 * t;
+            v[q * 8 + 2 * t] += drs * f.x * (e.d_col_scale ? e.d_col_scale[cc] : 1.f);
+            v[q * 8 + 2 * t + 1] += drs * f.y * (e.d_col_scale ? e.d_col_scale[cc + 1] : 1.f);
           }
         }
       }
@@ -216,10 +218,19 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
       for (int q = 0; q < 8; ++q) {
         if (col0 + q * 4 < N) {
           float4 f = *reinterpret_cast<const float4*>(dp + q * 4);
-          v[q * 4] += beta * f.x; v[q * 4 + 1] += beta * f.y; v[q * 4 + 2] += beta * f.z; v[q * 4 + 3] += beta * f.w;
+          const int cc = col0 + q * 4;
+          v[q * 4] += drs * f.x * (e.d_col_scale ? e.d_col_scale[cc] : 1.f); v[q * 4 + 1] += drs * f.y * (e.d_col_scale ? e.d_col_scale[cc + 1] : 1.f);
+          v[q * 4 + 2] += drs * f.z * (e.d_col_scale ? e.d_col_scale[cc + 2] : 1.f); v[q * 4 + 3] += drs * f.w * (e.d_col_scale ? e.d_col_scale[cc + 3] : 1.f);
         }
       }
     }
+  }
+  float diag_unrounded = 0.f;
+  const bool on_diag = row >= col0 && row < col0 + 32;
+  if (e.diag_resid && on_diag) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\tselp.f32 %0, %1, %0, p;\n\t}" : "+f"(diag_unrounded) : "f"(v[j]), "r"(row - col0), "r"(j));
   }
   // round + store (N is a multiple of 8, so every 8-column vector is fully in or fully out of range)
   if (e.out_dtype == PSGD_BF16) {
@@ -244,6 +255,13 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
       if (row_ok && col0 + q * 4 < N)
         *reinterpret_cast<float4*>(cp + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
     }
+  }
+  if (e.diag_resid && on_diag && row_ok) {
+    float dr = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\tselp.f32 %0, %1, %0, p;\n\t}" : "+f"(dr) : "f"(v[j]), "r"(row - col0), "r"(j));
+    e.diag_resid[row] = diag_unrounded - dr;
   }
   if (mirror) {  // C[col0 + j][row] = v[j]: for a fixed j the 32 lanes (consecutive rows) write 64 contiguous bytes
     if (e.out_dtype == PSGD_BF16) {
