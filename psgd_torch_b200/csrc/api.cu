@@ -171,7 +171,7 @@ static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, cudaStream_t st) {
   const float tiny = dtype_tiny(dt);
   bool tc_form[2];
   for (int j = 0; j < n; ++j) {
-    tc_form[j] = ctx->gemm_path != 1 && dt == PSGD_BF16 && jb[j].s >= 128 && (jb[j].s % 8) == 0;
+    tc_form[j] = ctx->gemm_path != 1 && !(ctx->debug_flags & 4) && dt == PSGD_BF16 && jb[j].s >= 128 && (jb[j].s % 8) == 0;
     k_bound_prep<<<1, 1024, 0, st>>>(jb[j].row_sumsq, jb[j].s, jb[j].nf_src, tiny, jb[j].w->scal);
     LAUNCH_CHECK(ctx, "k_bound_prep");
     DISPATCH_T(dt, (k_probe_init<T><<<32, 256, 0, st>>>((const T*)jb[j].A, jb[j].s, (const T*)jb[j].V0, jb[j].w->scal, (T*)jb[j].Va)));
@@ -325,8 +325,8 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
   };
   // P-first (P = Q^T Q is symmetric: the tensor-core path computes its upper 128-blocks only, ~1.06 s^3 instead of 2 s^3) costs
   // 1.06 m^3 + 2 m^2 n on the left against 4 m^2 n for the chain Q_L^T (Q_L X): take it whenever m < 1.88 n (same on the right).
-  const bool pl = dl && (double)m < 1.88 * (double)n;
-  const bool pr = dr && (double)n < 1.88 * (double)m;
+  const bool pl = dl && (double)m < 1.88 * (double)n && !(ctx->debug_flags & 2);
+  const bool pr = dr && (double)n < 1.88 * (double)m && !(ctx->debug_flags & 2);
   {
     GemmDesc sy[2];
     int ns = 0;
@@ -481,6 +481,12 @@ int psgd_timing_read(psgd_handle_t h, int* launches, double* total_ms, double* f
     ms += t;
   }
   *launches = ctx->timing_count; *total_ms = ms; *flops = ctx->timing_flops;
+  return PSGD_OK;
+}
+
+int psgd_debug_set_flags(psgd_handle_t h, int flags) {
+  if (!h) return PSGD_ERR_INVALID_ARG;
+  reinterpret_cast<Ctx*>(h)->debug_flags = flags;
   return PSGD_OK;
 }
 

@@ -136,6 +136,7 @@ struct Ctx {
   int gemm_path;       // 0 auto, 1 simt, 2 tc
   int mn_lbo, mn_sbo;  // MN-major UMMA descriptor byte offsets
   int force_bn;        // debug: 0 = automatic tile width, else 128 / 256
+  int debug_flags;     // bit0: no symmetric (upper-blocks-only) products, bit1: no P-first chain, bit2: no tensor-core norm bounds
   int64_t launches;
   char last_error[256];
   void* encode_tiled;  // cuTensorMapEncodeTiled entry point

@@ -547,7 +547,7 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     p.tiles_m = (g.M + TC_BM - 1) / TC_BM;
     p.tiles_n = (g.N + BN - 1) / BN;
     p.tile_start = tiles;
-    p.sym = (g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
+    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
     if (p.sym) {
       for (int tm = 0; tm < p.tiles_m; ++tm) tiles += p.tiles_n - (tm * TC_BM) / BN;
     } else {

@@ -306,9 +306,11 @@ __global__ void k_absmax(const T* __restrict__ x, size_t numel, float* out) {
 template <typename T>
 __global__ void k_balance_scale(T* __restrict__ q, size_t numel, const float* __restrict__ norm_self,
                                 const float* __restrict__ norm_other, int dtype) {
-  float ns = round_to(dtype, *norm_self), no = round_to(dtype, *norm_other);
-  float g = round_to(dtype, sqrtf(round_to(dtype, ns * no)));
-  float f = round_to(dtype, g / ns);
+  // the factor gmean/norm is ~1.00x: rounding it to bf16 (as the reference's bf16 arithmetic does) quantises it to 2^-7 steps;
+  // it is kept in fp32 here (closer to the exact balance, and Q_L (x) Q_R is then preserved to fp32 accuracy)
+  (void)dtype;
+  const float ns = *norm_self, no = *norm_other;
+  const float f = sqrtf(ns * no) / ns;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < numel; i += stride) q[i] = from_f<T>(to_f<T>(q[i]) * f);
