@@ -485,6 +485,254 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
+
+// ================================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (one TPC) owns one 256 x 256 output tile.  Each CTA stages only ITS 128 rows
+// of A and ITS half (128 rows) of the B tile -- 32 KB per k-block per SM instead of 48 KB, which is what the 1-CTA kernel is
+// bound by (L2->SM and smem-read bandwidth; profiles/r01_ncu_full_gemm_tc_raw.csv: tensor pipe 75 %) -- and the leader CTA's
+// single thread issues tcgen05.mma.cta_group::2 with M = 256 whose accumulator halves live in the two CTAs' TMEM.
+//   full[s]   (leader): armed with both CTAs' bytes; both CTAs' TMA loads complete_tx on it
+//   empty[s]  (each CTA): tcgen05.commit multicast from the leader frees the slot in both CTAs
+//   tfull[a]  (each CTA): commit multicast publishes the accumulator to both epilogues
+//   tempty[a] (leader): 8 arrivals, the 4 epilogue warps of each CTA (the peer's arrive remotely through mapa)
+// ================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+constexpr int TC2_BM = 256;   // rows of the pair tile
+constexpr int TC2_BN = 256;
+
+// flat pair-tile -> (problem, pair row pm, tn)
+__device__ __forceinline__ void locate_tile2(const TcGroup& g, int t, int& pi, int& pm, int& tn) {
+  pi = 0;
+#pragma unroll
+  for (int i = 1; i < TC_MAX_PROBLEMS; ++i)
+    if (i < g.num_problems && t >= g.p[i].tile_start) pi = i;
+  const TcProblem& p = g.p[pi];
+  int lt = t - p.tile_start;
+  if (p.sym) {   // 256 x 256 pair tiles: row pm owns tn >= pm
+    pm = 0;
+    while (true) {
+      const int cnt = p.tiles_n - pm;
+      if (lt < cnt) break;
+      lt -= cnt;
+      ++pm;
+    }
+    tn = pm + lt;
+    return;
+  }
+  const int GROUP = 4;
+  int per_group = GROUP * p.tiles_n;
+  int gidx = lt / per_group;
+  int first_m = gidx * GROUP;
+  int gsz = min(GROUP, p.tiles_m - first_m);
+  int in_g = lt - gidx * per_group;
+  pm = first_m + in_g % gsz;
+  tn = in_g / gsz;
+}
+
+struct Tc2Cfg {
+  static constexpr int BN = TC2_BN;
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = 128 * TC_BK * 2;          // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;     // this CTA's half of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
+  using Cfg = Tc2Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    fence_barrier_init();
+    for (int i = 0; i < g.num_problems; ++i) { prefetch_tmap(&g.p[i].map_a); prefetch_tmap(&g.p[i].map_b); }
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive / multicast commit / peer TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; bytes are credited to the leader's full barrier) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < g.total_tiles; t += npairs) {
+        int pi, pm, tn;
+        locate_tile2(g, t, pi, pm, tn);
+        const TcProblem& p = g.p[pi];
+        const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+        const int row0 = pm * TC2_BM + (int)rank * 128;          // this CTA's rows of A / C
+        const int ncol0 = tn * BN + (int)rank * (BN / 2);         // this CTA's half of the B tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, g.error_flag);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t lbar = mapa_u32(full_bar(stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d_2sm(&p.map_a, lbar, sa, kb * TC_BK, row0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(&p.map_a, lbar, sa + c * (TC_BK * 128), row0 + c * 64, kb * TC_BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(&p.map_b, lbar, sb, kb * TC_BK, ncol0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c) tma_load_2d_2sm(&p.map_b, lbar, sb + c * (TC_BK * 128), ncol0 + c * 64, kb * TC_BK);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < g.total_tiles; t += npairs) {
+        int pi, pm, tn;
+        locate_tile2(g, t, pi, pm, tn);
+        const TcProblem& p = g.p[pi];
+        const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.a_mn) << 15) | (uint32_t(p.b_mn) << 16) |
+                               (uint32_t(BN >> 3) << 17) | (uint32_t(TC2_BM >> 4) << 24);
+        const uint32_t a_lbo = p.a_mn ? (uint32_t)g.mn_lbo : 0u, a_sbo = p.a_mn ? (uint32_t)g.mn_sbo : 1024u;
+        const uint32_t b_lbo = p.b_mn ? (uint32_t)g.mn_lbo : 0u, b_sbo = p.b_mn ? (uint32_t)g.mn_sbo : 1024u;
+        const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u;
+        const uint32_t b_kstep = p.b_mn ? 16u * 128u : 32u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, g.error_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, g.error_flag);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs; each CTA drains its own 128 accumulator rows) =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t leader_tempty0 = mapa_u32(tempty_bar(0), 0), leader_tempty1 = mapa_u32(tempty_bar(1), 0);
+    for (int t = pair; t < g.total_tiles; t += npairs) {
+      int pi, pm, tn;
+      locate_tile2(g, t, pi, pm, tn);
+      const TcProblem& p = g.p[pi];
+      const Epi& e = p.epi;
+      const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
+      const float beta = e.beta * (e.beta_ptr ? *e.beta_ptr : 1.f);
+      mbar_wait(tfull_bar(acc), acc_phase, g.error_flag);
+      tc_fence_after();
+      const int tm = pm * 2 + (int)rank;                 // this CTA's 128-row block
+      const int row = tm * TC_BM + quarter * 32 + lane;
+      RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = tn * BN + c * 32;
+        int mirror = 0;
+        if (p.sym) {
+          const int cb = col0 >> 7;
+          if (cb < tm) continue;
+          mirror = cb > tm;
+        }
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, raw);
+        tmem_ld_wait();
+        if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_tempty0 : leader_tempty1);
+      if (e.row_sumsq && row < p.M) atomicAdd(&e.row_sumsq[row], ra.row_sumsq);
+      if (e.total_sumsq) { float s = warp_sum(ra.tot); if (lane == 0) atomicAdd(e.total_sumsq, s); }
+      if (e.abs_max) { float s = warp_max(ra.amax); if (lane == 0) atomic_max_nonneg(e.abs_max, s); }
+      if (e.trace) { float s = warp_sum(ra.tr); if (lane == 0 && s != 0.f) atomicAdd(e.trace, s); }
+      if (e.diag_max) { float s = warp_max(ra.dmax); if (lane == 0) atomic_max_nonneg(e.diag_max, s); }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();    // neither CTA may free TMEM / exit while the peer's MMAs, multicast commits or remote arrives are in flight
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -579,6 +827,66 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
   return check_cuda(ctx, cudaGetLastError(), "gemm_tc");
 }
 
+
+// 2-CTA launch: every problem needs M >= 256-ish to make sense; tiles are 256 x 256 pairs
+static bool tc2_worthwhile(const GemmDesc* gs, int n) {
+  for (int i = 0; i < n; ++i)
+    if (gs[i].M < 256 || gs[i].N <= 128) return false;
+  return true;
+}
+
+static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStream_t st) {
+  using Cfg = Tc2Cfg;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmDesc& g = gs[i];
+    TcProblem& p = grp.p[i];
+    p.epi = g.epi;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.a_mn = g.ta ? 1 : 0;
+    p.b_mn = g.tb ? 0 : 1;
+    int rc;
+    if (!g.ta) rc = make_tmap(ctx, &p.map_a, g.A, g.M, g.K, g.lda, 128);
+    else rc = make_tmap(ctx, &p.map_a, g.A, g.K, g.M, g.lda, TC_BK);
+    if (rc) return rc;
+    if (g.tb) rc = make_tmap(ctx, &p.map_b, g.B, g.N, g.K, g.ldb, Cfg::BN / 2);
+    else rc = make_tmap(ctx, &p.map_b, g.B, g.K, g.N, g.ldb, TC_BK);
+    if (rc) return rc;
+    p.tiles_m = (g.M + TC2_BM - 1) / TC2_BM;
+    p.tiles_n = (g.N + Cfg::BN - 1) / Cfg::BN;
+    p.tile_start = tiles;
+    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
+    if (p.sym) {
+      for (int pm = 0; pm < p.tiles_m; ++pm) tiles += p.tiles_n - pm;
+    } else {
+      tiles += p.tiles_m * p.tiles_n;
+    }
+  }
+  grp.num_problems = n;
+  grp.total_tiles = tiles;
+  grp.mn_lbo = ctx->mn_lbo;
+  grp.mn_sbo = ctx->mn_sbo;
+  grp.error_flag = nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(gemm_tc2)");
+    attr_set = true;
+  }
+  const int max_pairs = ctx->num_sms / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  const bool timed = ctx->timing_on && ctx->timing_count < ctx->ev_capacity;
+  if (timed) cudaEventRecord(ctx->ev_begin[ctx->timing_count], st);
+  gemm_tc2_kernel<<<2 * pairs, TC_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
+  if (timed) {
+    cudaEventRecord(ctx->ev_end[ctx->timing_count], st);
+    ctx->timing_count++;
+    for (int i = 0; i < n; ++i) ctx->timing_flops += 2.0 * gs[i].M * (double)gs[i].N * gs[i].K;
+  }
+  ctx->launches++;
+  return check_cuda(ctx, cudaGetLastError(), "gemm_tc2");
+}
+
 int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
   if (n < 1 || n > TC_MAX_PROBLEMS) return PSGD_ERR_INVALID_ARG;
   int max_n = 0;
@@ -588,6 +896,7 @@ int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
   }
   TcGroup grp;
   memset(&grp, 0, sizeof(grp));
+  if (ctx->force_bn == 0 && !(ctx->debug_flags & 8) && tc2_worthwhile(gs, n)) return launch_tc2(ctx, grp, gs, n, st);
   if (ctx->force_bn == 128) return launch_tc<128>(ctx, grp, gs, n, st);
   if (ctx->force_bn == 256) return launch_tc<256>(ctx, grp, gs, n, st);
   if (max_n > 128) return launch_tc<256>(ctx, grp, gs, n, st);

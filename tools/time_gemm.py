@@ -20,13 +20,13 @@ for (M, N, K, ta, tb) in ((4096, 4096, 4096, 0, 0), (4096, 4096, 4096, 1, 0), (4
     A = torch.randn((K, M) if ta else (M, K), device=dev).bfloat16()
     B = torch.randn((N, K) if tb else (K, N), device=dev).bfloat16()
     res = []
-    for bn in (256, 128):
+    for name, bn in (("2cta", 0), ("1cta256", 256)):
         lib.psgd_debug_set_tile_n(h, bn)
         try:
             ms = t(lambda: psgd.gemm(A, B, trans_a=bool(ta), trans_b=bool(tb), path=2))
-            res.append(f"BN={bn}: {ms*1e3:8.1f} us {2*M*N*K/ms/1e9:7.1f} TF/s")
+            res.append(f"{name}: {ms*1e3:8.1f} us {2*M*N*K/ms/1e9:7.1f} TF/s")
         except Exception as ex:
-            res.append(f"BN={bn}: EXC {ex}")
+            res.append(f"{name}: EXC {ex}")
     lib.psgd_debug_set_tile_n(h, 0)
     Ao = A.T if ta else A
     Bo = B.T if tb else B
