@@ -441,11 +441,32 @@ int psgd_create(psgd_handle_t* out, int device) {
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
   ctx->encode_tiled = fn;
+  {  // split-K workspace: 160 slots of 128 x 256 fp32 (21 MB) + counters; all launches of a handle are expected on one stream at a time
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    ctx->ws_slots = 160;
+    const size_t bytes = (size_t)ctx->ws_slots * 128 * 256 * sizeof(float);
+    if (cudaMalloc(&ctx->ws, bytes) == cudaSuccess && cudaMalloc(&ctx->ws_count, ctx->ws_slots * sizeof(int)) == cudaSuccess) {
+      cudaMemset(ctx->ws, 0, bytes);
+      cudaMemset(ctx->ws_count, 0, ctx->ws_slots * sizeof(int));
+    } else {
+      ctx->ws = nullptr; ctx->ws_count = nullptr; ctx->ws_slots = 0;   // split-K simply stays off
+      cudaGetLastError();
+    }
+    cudaSetDevice(prev);
+  }
   *out = reinterpret_cast<psgd_handle_t>(ctx);
   return PSGD_OK;
 }
 
-void psgd_destroy(psgd_handle_t h) { delete reinterpret_cast<Ctx*>(h); }
+void psgd_destroy(psgd_handle_t h) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx) return;
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ws_count) cudaFree(ctx->ws_count);
+  delete ctx;
+}
 
 int psgd_set_gemm_path(psgd_handle_t h, int p) {
   if (!h || p < 0 || p > 2) return PSGD_ERR_INVALID_ARG;

@@ -147,6 +147,10 @@ struct Ctx {
   cudaEvent_t* ev_begin;
   cudaEvent_t* ev_end;
   int ev_capacity;
+  // split-K workspace of the tcgen05 GEMM (fp32 tile slots + arrival counters), zero between launches
+  float* ws;
+  int* ws_count;
+  int ws_slots;
 };
 
 // one GEMM problem: C = epi(op(A) op(B)), op(A) M x K, op(B) K x N

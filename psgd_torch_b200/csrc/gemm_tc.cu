@@ -36,7 +36,11 @@ struct alignas(64) TcProblem {
   int a_mn, b_mn;  // operand is MN-major in memory
   int sym;         // symmetric output: only tiles that reach the upper triangle are enumerated
   int tiles_m, tiles_n;
-  int tile_start;  // first flat tile index of this problem
+  int tile_start;  // first flat work-unit index of this problem
+  int tile_first;  // first tile (in this problem's own enumeration) this entry covers (tail entries start past 0)
+  int splits;      // K partitions per tile (1 = none); partial accumulators meet in the fp32 workspace
+  int kb_split;    // k-blocks per partition
+  int ws_slot0;    // first workspace tile slot of this entry
 };
 
 struct alignas(64) TcGroup {
@@ -45,6 +49,8 @@ struct alignas(64) TcGroup {
   int total_tiles;
   int mn_lbo, mn_sbo;
   int* error_flag;
+  float* ws;        // split-K workspace: slots of 128 x BN fp32, zero between launches
+  int* ws_count;    // arrival counter per slot, zero between launches
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -151,7 +157,7 @@ __device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int bn, int
   for (int i = 1; i < TC_MAX_PROBLEMS; ++i)
     if (i < g.num_problems && t >= g.p[i].tile_start) pi = i;
   const TcProblem& p = g.p[pi];
-  int lt = t - p.tile_start;
+  int lt = p.tile_first + (t - p.tile_start) / p.splits;
   if (p.sym) {
     // row tm owns the tiles tn >= tn_min(tm) = floor(tm * 128 / BN): those whose last column reaches the diagonal block of row tm
     tm = 0;
@@ -345,6 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+  volatile int* epi_flag = reinterpret_cast<volatile int*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4) + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -371,7 +378,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         locate_tile(g, t, BN, pi, tm, tn);
         const TcProblem& p = g.p[pi];
         const int num_kb = (p.K + TC_BK - 1) / TC_BK;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = (t - p.tile_start) % p.splits;
+        const int kb0 = split * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, g.error_flag);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -417,7 +426,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, g.error_flag);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = (t - p.tile_start) % p.splits;
+        const int kb0 = split * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase, g.error_flag);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -426,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // smem slot is free once these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
@@ -451,25 +462,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_after();
       const int row = tm * TC_BM + quarter * 32 + lane;
       RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
+      bool run_epilogue = true;
+      float* wsrow = nullptr;
+      if (p.splits > 1) {
+        // split-K unit: add the partial accumulator into the tile's fp32 workspace slot; the unit that arrives last owns the epilogue
+        const int slot = p.ws_slot0 + (t - p.tile_start) / p.splits;
+        wsrow = g.ws + ((size_t)slot * TC_BM + quarter * 32 + lane) * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = tn * BN + c * 32;
-        int mirror = 0;
-        if (p.sym) {  // 128-block classification: below the diagonal block -> produced by the mirror of its transpose, skip
-          const int cb = col0 >> 7;
-          if (cb < tm) continue;
-          mirror = cb > tm;
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = tn * BN + c * 32;
+          if (col0 >= p.N) break;
+          if (p.sym && (col0 >> 7) < tm) continue;
+          uint32_t raw[32];
+          const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
+          tmem_ld_32x32(taddr, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wsrow + c * 32 + q * 4), "f"(__uint_as_float(raw[4 * q])),
+                         "f"(__uint_as_float(raw[4 * q + 1])), "f"(__uint_as_float(raw[4 * q + 2])), "f"(__uint_as_float(raw[4 * q + 3]))
+                         : "memory");
         }
-        uint32_t raw[32];
-        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
-        tmem_ld_32x32(taddr, raw);
-        tmem_ld_wait();
-        if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));   // TMEM buffer is free already
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        if (threadIdx.x == 64) {
+          const int old = atomicAdd(&g.ws_count[slot], 1);
+          *epi_flag = (old == p.splits - 1) ? 1 : 0;
+          if (old == p.splits - 1) g.ws_count[slot] = 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        run_epilogue = (*epi_flag != 0);
+        if (run_epilogue) __threadfence();
       }
-      // release the accumulator buffer to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (run_epilogue) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = tn * BN + c * 32;
+          int mirror = 0;
+          if (p.sym) {  // 128-block classification: below the diagonal block -> produced by the mirror of its transpose, skip
+            const int cb = col0 >> 7;
+            if (cb < tm) continue;
+            mirror = cb > tm;
+          }
+          uint32_t raw[32];
+          if (p.splits > 1) {
+            if (col0 >= p.N) break;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {   // fetch the summed partials (L2, bypass L1) and leave the slot zeroed for the next launch
+              const float4 f = __ldcg(reinterpret_cast<const float4*>(wsrow + c * 32 + q * 4));
+              raw[4 * q] = __float_as_uint(f.x); raw[4 * q + 1] = __float_as_uint(f.y); raw[4 * q + 2] = __float_as_uint(f.z); raw[4 * q + 3] = __float_as_uint(f.w);
+              __stcg(reinterpret_cast<float4*>(wsrow + c * 32 + q * 4), make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+          } else {
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
+            tmem_ld_32x32(taddr, raw);
+            tmem_ld_wait();
+          }
+          if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
+        }
+      }
+      if (p.splits == 1) {
+        // release the accumulator buffer to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
       // per-row / per-warp reductions
       if (e.row_sumsq && row < p.M) atomicAdd(&e.row_sumsq[row], ra.row_sumsq);
       if (e.total_sumsq) { float s = warp_sum(ra.tot); if (lane == 0) atomicAdd(e.total_sumsq, s); }
@@ -777,7 +837,8 @@ bool tc_eligible(const GemmDesc& g) {
 template <int BN>
 static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  int tiles = 0;
+  int ntiles[TC_MAX_PROBLEMS];
+  int T = 0;
   for (int i = 0; i < n; ++i) {
     const GemmDesc& g = gs[i];
     TcProblem& p = grp.p[i];
@@ -794,19 +855,66 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     if (rc) return rc;
     p.tiles_m = (g.M + TC_BM - 1) / TC_BM;
     p.tiles_n = (g.N + BN - 1) / BN;
-    p.tile_start = tiles;
     p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
     if (p.sym) {
-      for (int tm = 0; tm < p.tiles_m; ++tm) tiles += p.tiles_n - (tm * TC_BM) / BN;
+      ntiles[i] = 0;
+      for (int tm = 0; tm < p.tiles_m; ++tm) ntiles[i] += p.tiles_n - (tm * TC_BM) / BN;
     } else {
-      tiles += p.tiles_m * p.tiles_n;
+      ntiles[i] = p.tiles_m * p.tiles_n;
+    }
+    p.tile_first = 0; p.splits = 1; p.kb_split = (g.K + TC_BK - 1) / TC_BK; p.ws_slot0 = 0;
+    T += ntiles[i];
+  }
+  // ---- split-K policy (K partitions meet in the fp32 workspace; the last arriver runs the epilogue) ----
+  const int sms = ctx->num_sms;
+  int nent = n;
+  int slots = 0;
+  const bool can_split = ctx->ws && !(ctx->debug_flags & 16);
+  if (can_split && T * 2 <= sms) {
+    // under-filled launch (32-probe norm-bound products, small Grams): split every problem so that ~all SMs get a unit
+    for (int i = 0; i < n; ++i) {
+      TcProblem& p = grp.p[i];
+      const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+      int sp = sms / T;
+      if (sp > 8) sp = 8;
+      if (sp > num_kb / 4) sp = num_kb / 4;
+      if (sp < 2 || slots + ntiles[i] > ctx->ws_slots) continue;
+      p.kb_split = (num_kb + sp - 1) / sp;
+      p.splits = (num_kb + p.kb_split - 1) / p.kb_split;
+      p.ws_slot0 = slots;
+      slots += ntiles[i];
+    }
+  } else if (can_split && T > sms && n < TC_MAX_PROBLEMS) {
+    // tail wave: the last (T mod SMs) tiles would occupy a fraction of the machine for a whole tile time -> split them along K
+    const int frac = T % sms;
+    const TcProblem& last = grp.p[n - 1];
+    const int num_kb = (last.K + TC_BK - 1) / TC_BK;
+    if (frac > 0 && frac * 2 <= sms && frac <= ntiles[n - 1] && num_kb >= 16 && frac <= ctx->ws_slots) {
+      int sp = sms / frac;
+      if (sp > 4) sp = 4;
+      if (sp > num_kb / 8) sp = num_kb / 8;
+      if (sp >= 2) {
+        grp.p[n] = grp.p[n - 1];
+        TcProblem& tail = grp.p[n];
+        tail.tile_first = ntiles[n - 1] - frac;
+        tail.kb_split = (num_kb + sp - 1) / sp;
+        tail.splits = (num_kb + tail.kb_split - 1) / tail.kb_split;
+        tail.ws_slot0 = 0;
+        ntiles[n] = frac;
+        ntiles[n - 1] -= frac;
+        nent = n + 1;
+      }
     }
   }
-  grp.num_problems = n;
-  grp.total_tiles = tiles;
+  int units = 0;
+  for (int i = 0; i < nent; ++i) { grp.p[i].tile_start = units; units += ntiles[i] * grp.p[i].splits; }
+  grp.num_problems = nent;
+  grp.total_tiles = units;
   grp.mn_lbo = ctx->mn_lbo;
   grp.mn_sbo = ctx->mn_sbo;
   grp.error_flag = nullptr;
+  grp.ws = ctx->ws;
+  grp.ws_count = ctx->ws_count;
   static bool attr_set[2] = {false, false};
   const int ai = (BN == 256) ? 0 : 1;
   if (!attr_set[ai]) {
@@ -814,7 +922,7 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(gemm_tc)");
     attr_set[ai] = true;
   }
-  int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  int grid = units < sms ? units : sms;
   const bool timed = ctx->timing_on && BN == 256 && ctx->timing_count < ctx->ev_capacity;
   if (timed) cudaEventRecord(ctx->ev_begin[ctx->timing_count], st);
   gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
@@ -826,7 +934,6 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "gemm_tc");
 }
-
 
 // 2-CTA launch: every problem needs M >= 256-ish to make sense; tiles are 256 x 256 pairs
 static bool tc2_worthwhile(const GemmDesc* gs, int n) {
@@ -854,7 +961,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
     if (rc) return rc;
     p.tiles_m = (g.M + TC2_BM - 1) / TC2_BM;
     p.tiles_n = (g.N + Cfg::BN - 1) / Cfg::BN;
-    p.tile_start = tiles;
+    p.tile_start = tiles; p.tile_first = 0; p.splits = 1; p.kb_split = 0; p.ws_slot0 = 0;
     p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
     if (p.sym) {
       for (int pm = 0; pm < p.tiles_m; ++pm) tiles += p.tiles_n - pm;
@@ -896,7 +1003,7 @@ int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
   }
   TcGroup grp;
   memset(&grp, 0, sizeof(grp));
-  if (ctx->force_bn == 0 && !(ctx->debug_flags & 8) && tc2_worthwhile(gs, n)) return launch_tc2(ctx, grp, gs, n, st);
+  if (ctx->force_bn == 0 && (ctx->debug_flags & 8) && tc2_worthwhile(gs, n)) return launch_tc2(ctx, grp, gs, n, st);  // measured slower than 1-CTA + split-K on this part: opt-in
   if (ctx->force_bn == 128) return launch_tc<128>(ctx, grp, gs, n, st);
   if (ctx->force_bn == 256) return launch_tc<256>(ctx, grp, gs, n, st);
   if (max_n > 128) return launch_tc<256>(ctx, grp, gs, n, st);

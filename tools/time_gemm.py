@@ -20,14 +20,14 @@ for (M, N, K, ta, tb) in ((4096, 4096, 4096, 0, 0), (4096, 4096, 4096, 1, 0), (4
     A = torch.randn((K, M) if ta else (M, K), device=dev).bfloat16()
     B = torch.randn((N, K) if tb else (K, N), device=dev).bfloat16()
     res = []
-    for name, bn in (("2cta", 0), ("1cta256", 256)):
-        lib.psgd_debug_set_tile_n(h, bn)
+    for name, fl in (("splitK", 0), ("nosplit", 16), ("2cta", 8)):
+        lib.psgd_debug_set_flags(h, fl)
         try:
             ms = t(lambda: psgd.gemm(A, B, trans_a=bool(ta), trans_b=bool(tb), path=2))
             res.append(f"{name}: {ms*1e3:8.1f} us {2*M*N*K/ms/1e9:7.1f} TF/s")
         except Exception as ex:
             res.append(f"{name}: EXC {ex}")
-    lib.psgd_debug_set_tile_n(h, 0)
+    lib.psgd_debug_set_flags(h, 0)
     Ao = A.T if ta else A
     Bo = B.T if tb else B
     ms = t(lambda: Ao @ Bo)
