@@ -441,11 +441,11 @@ int psgd_create(psgd_handle_t* out, int device) {
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
   ctx->encode_tiled = fn;
-  {  // split-K workspace: 160 slots of 128 x 256 fp32 (21 MB) + counters; all launches of a handle are expected on one stream at a time
+  {  // split-K workspace: partial-tile slots + arrival counters; all launches of a handle are expected on one stream at a time
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(device);
-    ctx->ws_slots = 160;
+    ctx->ws_slots = 320;   // partial tiles of 128 x 256 fp32 (42 MB)
     const size_t bytes = (size_t)ctx->ws_slots * 128 * 256 * sizeof(float);
     if (cudaMalloc(&ctx->ws, bytes) == cudaSuccess && cudaMalloc(&ctx->ws_count, ctx->ws_slots * sizeof(int)) == cudaSuccess) {
       cudaMemset(ctx->ws, 0, bytes);

@@ -463,11 +463,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const int row = tm * TC_BM + quarter * 32 + lane;
       RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
       bool run_epilogue = true;
-      float* wsrow = nullptr;
+      const float* ws_tile = nullptr;   // partial tiles of this output tile: [split][128 rows][BN] fp32
+      const int my_split = (t - p.tile_start) % p.splits;
       if (p.splits > 1) {
-        // split-K unit: add the partial accumulator into the tile's fp32 workspace slot; the unit that arrives last owns the epilogue
-        const int slot = p.ws_slot0 + (t - p.tile_start) / p.splits;
-        wsrow = g.ws + ((size_t)slot * TC_BM + quarter * 32 + lane) * BN;
+        // split-K unit: publish the partial accumulator (plain 16-byte stores), then count arrivals; the unit that arrives last sums
+        // the other partials with its own accumulator (still in TMEM) in split order and runs the epilogue
+        const int tile_local = (t - p.tile_start) / p.splits;
+        float* tbase = g.ws + (size_t)(p.ws_slot0 + tile_local * p.splits) * TC_BM * BN;
+        ws_tile = tbase;
+        float* myrow = tbase + ((size_t)my_split * TC_BM + quarter * 32 + lane) * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int col0 = tn * BN + c * 32;
@@ -479,19 +483,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wsrow + c * 32 + q * 4), "f"(__uint_as_float(raw[4 * q])),
-                         "f"(__uint_as_float(raw[4 * q + 1])), "f"(__uint_as_float(raw[4 * q + 2])), "f"(__uint_as_float(raw[4 * q + 3]))
-                         : "memory");
+            __stcg(reinterpret_cast<float4*>(myrow + c * 32 + q * 4),
+                   make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3])));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));   // TMEM buffer is free already
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
         if (threadIdx.x == 64) {
-          const int old = atomicAdd(&g.ws_count[slot], 1);
+          const int cslot = p.ws_slot0 + tile_local;     // one counter per output tile (slot numbering of the first partial / splits is unique enough: see host)
+          const int old = atomicAdd(&g.ws_count[cslot], 1);
           *epi_flag = (old == p.splits - 1) ? 1 : 0;
-          if (old == p.splits - 1) g.ws_count[slot] = 0;
+          if (old == p.splits - 1) g.ws_count[cslot] = 0;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         run_epilogue = (*epi_flag != 0);
@@ -507,29 +508,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             if (cb < tm) continue;
             mirror = cb > tm;
           }
+          if (p.splits > 1 && col0 >= p.N) break;
           uint32_t raw[32];
+          const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
+          tmem_ld_32x32(taddr, raw);
+          tmem_ld_wait();
           if (p.splits > 1) {
-            if (col0 >= p.N) break;
+            float sum[32];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {   // fetch the summed partials (L2, bypass L1) and leave the slot zeroed for the next launch
-              const float4 f = __ldcg(reinterpret_cast<const float4*>(wsrow + c * 32 + q * 4));
-              raw[4 * q] = __float_as_uint(f.x); raw[4 * q + 1] = __float_as_uint(f.y); raw[4 * q + 2] = __float_as_uint(f.z); raw[4 * q + 3] = __float_as_uint(f.w);
-              __stcg(reinterpret_cast<float4*>(wsrow + c * 32 + q * 4), make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+            for (int sp = 0; sp < p.splits; ++sp) {   // fixed order -> the result does not depend on which unit arrived last
+              if (sp == my_split) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(raw[j]);
+              } else {
+                const float* prow = ws_tile + ((size_t)sp * TC_BM + quarter * 32 + lane) * BN + c * 32;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 f = __ldcg(reinterpret_cast<const float4*>(prow + q * 4));
+                  sum[4 * q] += f.x; sum[4 * q + 1] += f.y; sum[4 * q + 2] += f.z; sum[4 * q + 3] += f.w;
+                }
+              }
             }
-          } else {
-            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
-            tmem_ld_32x32(taddr, raw);
-            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(sum[j]);
           }
           if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
         }
       }
-      if (p.splits == 1) {
-        // release the accumulator buffer to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-      }
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       // per-row / per-warp reductions
       if (e.row_sumsq && row < p.M) atomicAdd(&e.row_sumsq[row], ra.row_sumsq);
       if (e.total_sumsq) { float s = warp_sum(ra.tot); if (lane == 0) atomicAdd(e.total_sumsq, s); }
@@ -878,18 +888,21 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
       int sp = sms / T;
       if (sp > 8) sp = 8;
       if (sp > num_kb / 4) sp = num_kb / 4;
-      if (sp < 2 || slots + ntiles[i] > ctx->ws_slots) continue;
-      p.kb_split = (num_kb + sp - 1) / sp;
-      p.splits = (num_kb + p.kb_split - 1) / p.kb_split;
+      if (sp < 2) continue;
+      const int kbs = (num_kb + sp - 1) / sp;
+      const int spl = (num_kb + kbs - 1) / kbs;
+      if (spl < 2 || slots + ntiles[i] * spl > ctx->ws_slots) continue;
+      p.kb_split = kbs;
+      p.splits = spl;
       p.ws_slot0 = slots;
-      slots += ntiles[i];
+      slots += ntiles[i] * spl;
     }
   } else if (can_split && T > sms && n < TC_MAX_PROBLEMS) {
     // tail wave: the last (T mod SMs) tiles would occupy a fraction of the machine for a whole tile time -> split them along K
     const int frac = T % sms;
     const TcProblem& last = grp.p[n - 1];
     const int num_kb = (last.K + TC_BK - 1) / TC_BK;
-    if (frac > 0 && frac * 2 <= sms && frac <= ntiles[n - 1] && num_kb >= 16 && frac <= ctx->ws_slots) {
+    if (frac > 0 && frac * 2 <= sms && frac <= ntiles[n - 1] && num_kb >= 16 && frac * 4 <= ctx->ws_slots) {
       int sp = sms / frac;
       if (sp > 4) sp = 4;
       if (sp > num_kb / 8) sp = num_kb / 8;
