@@ -41,6 +41,9 @@ struct alignas(64) TcProblem {
   int splits;      // K partitions per tile (1 = none); partial accumulators meet in the fp32 workspace
   int kb_split;    // k-blocks per partition
   int ws_slot0;    // first workspace tile slot of this entry
+  int nsplit;      // BN / bn_eff: a full-width tile position is covered by nsplit consecutive units
+  int bn_eff;      // tile width of this entry: BN, or BN/2 = 128 for tail-wave entries (half tiles fill the last wave without a reduction)
+  CUtensorMap map_b_half;  // K-major B with a 128-row box (only used when bn_eff < BN)
 };
 
 struct alignas(64) TcGroup {
@@ -150,24 +153,30 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-// flat tile -> (problem, tile_m, tile_n); m-grouped rasterisation (8 row-tiles per group) for L2 reuse
-__device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int bn, int& pi, int& tm, int& tn) {
+// flat work unit -> (problem, tile_m, tile_n in units of bn_eff, K slice).  A unit is (full-width tile position, N half, K slice); tile
+// positions follow an m-grouped rasterisation (8 row-tiles per group) for L2 reuse, symmetric problems enumerate the tiles that reach
+// the upper triangle only.
+__device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int bn_full, int& pi, int& tm, int& tn, int& kslice) {
   pi = 0;
 #pragma unroll
   for (int i = 1; i < TC_MAX_PROBLEMS; ++i)
     if (i < g.num_problems && t >= g.p[i].tile_start) pi = i;
   const TcProblem& p = g.p[pi];
-  int lt = p.tile_first + (t - p.tile_start) / p.splits;
+  int u = t - p.tile_start;
+  kslice = u % p.splits;
+  u /= p.splits;
+  const int nhalf = u % p.nsplit;
+  int lt = p.tile_first + u / p.nsplit;
   if (p.sym) {
     // row tm owns the tiles tn >= tn_min(tm) = floor(tm * 128 / BN): those whose last column reaches the diagonal block of row tm
     tm = 0;
     while (true) {
-      const int cnt = p.tiles_n - (tm * TC_BM) / bn;
+      const int cnt = p.tiles_n - (tm * TC_BM) / bn_full;
       if (lt < cnt) break;
       lt -= cnt;
       ++tm;
     }
-    tn = (tm * TC_BM) / bn + lt;
+    tn = ((tm * TC_BM) / bn_full + lt) * p.nsplit + nhalf;
     return;
   }
   const int GROUP = 8;
@@ -177,7 +186,7 @@ __device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int bn, int
   int gsz = min(GROUP, p.tiles_m - first_m);
   int in_g = lt - gidx * per_group;
   tm = first_m + in_g % gsz;
-  tn = in_g / gsz;
+  tn = (in_g / gsz) * p.nsplit + nhalf;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -374,17 +383,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-        int pi, tm, tn;
-        locate_tile(g, t, BN, pi, tm, tn);
+        int pi, tm, tn, kslice;
+        locate_tile(g, t, BN, pi, tm, tn, kslice);
         const TcProblem& p = g.p[pi];
         const int num_kb = (p.K + TC_BK - 1) / TC_BK;
-        const int split = (t - p.tile_start) % p.splits;
-        const int kb0 = split * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
+        const int kb0 = kslice * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, g.error_flag);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const int bn = p.bn_eff;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + bn * TC_BK * 2);
           if (!p.a_mn) {
             tma_load_2d(&p.map_a, full_bar(stage), sa, kb * TC_BK, tm * TC_BM);
           } else {
@@ -393,11 +402,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
               tma_load_2d(&p.map_a, full_bar(stage), sa + c * (TC_BK * 128), tm * TC_BM + c * 64, kb * TC_BK);
           }
           if (!p.b_mn) {
-            tma_load_2d(&p.map_b, full_bar(stage), sb, kb * TC_BK, tn * BN);
+            tma_load_2d(bn == BN ? &p.map_b : &p.map_b_half, full_bar(stage), sb, kb * TC_BK, tn * bn);
           } else {
-#pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(&p.map_b, full_bar(stage), sb + c * (TC_BK * 128), tn * BN + c * 64, kb * TC_BK);
+            for (int c = 0; c < bn / 64; ++c)
+              tma_load_2d(&p.map_b, full_bar(stage), sb + c * (TC_BK * 128), tn * bn + c * 64, kb * TC_BK);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -411,14 +419,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-        int pi, tm, tn;
-        locate_tile(g, t, BN, pi, tm, tn);
+        int pi, tm, tn, kslice;
+        locate_tile(g, t, BN, pi, tm, tn, kslice);
         const TcProblem& p = g.p[pi];
         const int num_kb = (p.K + TC_BK - 1) / TC_BK;
         // instruction descriptor: D=f32 (bit4), A=bf16 (bit7), B=bf16 (bit10), a_major bit15, b_major bit16,
         // N>>3 at bits 17-22, M>>4 at bits 24-28
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.a_mn) << 15) | (uint32_t(p.b_mn) << 16) |
-                               (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
+                               (uint32_t(p.bn_eff >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
         const uint32_t a_lbo = p.a_mn ? (uint32_t)g.mn_lbo : 0u, a_sbo = p.a_mn ? (uint32_t)g.mn_sbo : 1024u;
         const uint32_t b_lbo = p.b_mn ? (uint32_t)g.mn_lbo : 0u, b_sbo = p.b_mn ? (uint32_t)g.mn_sbo : 1024u;
         const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u;  // bytes to advance per UMMA_K=16
@@ -426,8 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, g.error_flag);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        const int split = (t - p.tile_start) % p.splits;
-        const int kb0 = split * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
+        const int kb0 = kslice * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase, g.error_flag);
           tc_fence_after();
@@ -452,8 +459,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-      int pi, tm, tn;
-      locate_tile(g, t, BN, pi, tm, tn);
+      int pi, tm, tn, kslice;
+      locate_tile(g, t, BN, pi, tm, tn, kslice);
       const TcProblem& p = g.p[pi];
       const Epi& e = p.epi;
       const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
@@ -462,19 +469,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc_fence_after();
       const int row = tm * TC_BM + quarter * 32 + lane;
       RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
+      const int bn = p.bn_eff;
+      const int nchunks = bn / 32;
       bool run_epilogue = true;
-      const float* ws_tile = nullptr;   // partial tiles of this output tile: [split][128 rows][BN] fp32
-      const int my_split = (t - p.tile_start) % p.splits;
+      const float4* ws_tile = nullptr;   // partial tiles of this output tile, fragment layout: [split][chunk][q][warp][lane] float4
+      const int my_split = kslice;
+      const size_t part_f4 = (size_t)TC_BM * BN / 4;   // float4 per partial tile slot
       if (p.splits > 1) {
-        // split-K unit: publish the partial accumulator (plain 16-byte stores), then count arrivals; the unit that arrives last sums
-        // the other partials with its own accumulator (still in TMEM) in split order and runs the epilogue
-        const int tile_local = (t - p.tile_start) / p.splits;
-        float* tbase = g.ws + (size_t)(p.ws_slot0 + tile_local * p.splits) * TC_BM * BN;
+        // split-K unit: publish the partial accumulator (every warp-level store is 512 contiguous bytes), then count arrivals; the unit
+        // that arrives last sums the other partials with its own accumulator (still in TMEM) in split order and runs the epilogue
+        const int tile_local = (t - p.tile_start) / p.splits;   // (tile position, N half) index inside this entry
+        float4* tbase = reinterpret_cast<float4*>(g.ws) + (size_t)(p.ws_slot0 + tile_local * p.splits) * part_f4;
         ws_tile = tbase;
-        float* myrow = tbase + ((size_t)my_split * TC_BM + quarter * 32 + lane) * BN;
+        float4* mine = tbase + (size_t)my_split * part_f4;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = tn * BN + c * 32;
+        for (int c = 0; c < nchunks; ++c) {
+          const int col0 = tn * bn + c * 32;
           if (col0 >= p.N) break;
           if (p.sym && (col0 >> 7) < tm) continue;
           uint32_t raw[32];
@@ -483,13 +493,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            __stcg(reinterpret_cast<float4*>(myrow + c * 32 + q * 4),
+            __stcg(mine + ((c * 8 + q) * 4 + quarter) * 32 + lane,
                    make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3])));
         }
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
         if (threadIdx.x == 64) {
-          const int cslot = p.ws_slot0 + tile_local;     // one counter per output tile (slot numbering of the first partial / splits is unique enough: see host)
+          const int cslot = p.ws_slot0 + tile_local;
           const int old = atomicAdd(&g.ws_count[cslot], 1);
           *epi_flag = (old == p.splits - 1) ? 1 : 0;
           if (old == p.splits - 1) g.ws_count[cslot] = 0;
@@ -500,8 +510,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       if (run_epilogue) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = tn * BN + c * 32;
+        for (int c = 0; c < nchunks; ++c) {
+          const int col0 = tn * bn + c * 32;
           int mirror = 0;
           if (p.sym) {  // 128-block classification: below the diagonal block -> produced by the mirror of its transpose, skip
             const int cb = col0 >> 7;
@@ -512,26 +522,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           uint32_t raw[32];
           const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
           tmem_ld_32x32(taddr, raw);
-          tmem_ld_wait();
           if (p.splits > 1) {
+            // other splits' partials: issue all loads of a half chunk before touching them (latency, not bandwidth, is the cost here)
             float sum[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum[j] = 0.f;
-            for (int sp = 0; sp < p.splits; ++sp) {   // fixed order -> the result does not depend on which unit arrived last
-              if (sp == my_split) {
+            bool own_added = false;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(raw[j]);
-              } else {
-                const float* prow = ws_tile + ((size_t)sp * TC_BM + quarter * 32 + lane) * BN + c * 32;
+            for (int half = 0; half < 2; ++half) {
+              float4 buf[3][4];
+              for (int s0 = 0; s0 < p.splits; s0 += 3) {     // up to 3 foreign partials per batch
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 f = __ldcg(reinterpret_cast<const float4*>(prow + q * 4));
-                  sum[4 * q] += f.x; sum[4 * q + 1] += f.y; sum[4 * q + 2] += f.z; sum[4 * q + 3] += f.w;
+                for (int u = 0; u < 3; ++u) {
+                  const int sp = s0 + u;
+                  if (sp < p.splits && sp != my_split) {
+                    const float4* src = ws_tile + (size_t)sp * part_f4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) buf[u][q] = __ldcg(src + ((c * 8 + half * 4 + q) * 4 + quarter) * 32 + lane);
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                  const int sp = s0 + u;
+                  if (sp < p.splits && sp != my_split) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const int j = (half * 4 + q) * 4;
+                      sum[j] += buf[u][q].x; sum[j + 1] += buf[u][q].y; sum[j + 2] += buf[u][q].z; sum[j + 3] += buf[u][q].w;
+                    }
+                  }
                 }
               }
             }
+            (void)own_added;
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(sum[j]);
+            for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(sum[j] + __uint_as_float(raw[j]));
+          } else {
+            tmem_ld_wait();
           }
           if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
         }
@@ -872,55 +900,58 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     } else {
       ntiles[i] = p.tiles_m * p.tiles_n;
     }
-    p.tile_first = 0; p.splits = 1; p.kb_split = (g.K + TC_BK - 1) / TC_BK; p.ws_slot0 = 0;
+    p.tile_first = 0; p.splits = 1; p.kb_split = (g.K + TC_BK - 1) / TC_BK; p.ws_slot0 = 0; p.nsplit = 1; p.bn_eff = BN;
+    if (BN == 256 && g.tb) { rc = make_tmap(ctx, &p.map_b_half, g.B, g.N, g.K, g.ldb, 128); if (rc) return rc; }
     T += ntiles[i];
   }
-  // ---- split-K policy (K partitions meet in the fp32 workspace; the last arriver runs the epilogue) ----
+  // ---- filling the machine ----
+  //  * under-filled launch (T*2 <= SMs): first halve the tile width (128 x 128 tiles, twice as many, no reduction needed), then, if still
+  //    under-filled (the 32-probe norm-bound products, small Grams), split K: partial accumulators meet in the fp32 workspace and the
+  //    unit that arrives last runs the epilogue
+  //  * otherwise, if the last wave would use at most half of the SMs, its tiles are issued as half-width tiles (2 units each)
   const int sms = ctx->num_sms;
   int nent = n;
   int slots = 0;
-  const bool can_split = ctx->ws && !(ctx->debug_flags & 16);
+  const bool can_split = !(ctx->debug_flags & 16);
   if (can_split && T * 2 <= sms) {
-    // under-filled launch (32-probe norm-bound products, small Grams): split every problem so that ~all SMs get a unit
+    int T2 = 0;
     for (int i = 0; i < n; ++i) {
       TcProblem& p = grp.p[i];
-      const int num_kb = (p.K + TC_BK - 1) / TC_BK;
-      int sp = sms / T;
-      if (sp > 8) sp = 8;
-      if (sp > num_kb / 4) sp = num_kb / 4;
-      if (sp < 2) continue;
-      const int kbs = (num_kb + sp - 1) / sp;
-      const int spl = (num_kb + kbs - 1) / kbs;
-      if (spl < 2 || slots + ntiles[i] * spl > ctx->ws_slots) continue;
-      p.kb_split = kbs;
-      p.splits = spl;
-      p.ws_slot0 = slots;
-      slots += ntiles[i] * spl;
+      if (BN == 256 && p.N > 128) { p.nsplit = 2; p.bn_eff = 128; }
+      T2 += ntiles[i] * p.nsplit;
     }
-  } else if (can_split && T > sms && n < TC_MAX_PROBLEMS) {
-    // tail wave: the last (T mod SMs) tiles would occupy a fraction of the machine for a whole tile time -> split them along K
-    const int frac = T % sms;
-    const TcProblem& last = grp.p[n - 1];
-    const int num_kb = (last.K + TC_BK - 1) / TC_BK;
-    if (frac > 0 && frac * 2 <= sms && frac <= ntiles[n - 1] && num_kb >= 16 && frac * 4 <= ctx->ws_slots) {
-      int sp = sms / frac;
-      if (sp > 4) sp = 4;
-      if (sp > num_kb / 8) sp = num_kb / 8;
-      if (sp >= 2) {
-        grp.p[n] = grp.p[n - 1];
-        TcProblem& tail = grp.p[n];
-        tail.tile_first = ntiles[n - 1] - frac;
-        tail.kb_split = (num_kb + sp - 1) / sp;
-        tail.splits = (num_kb + tail.kb_split - 1) / tail.kb_split;
-        tail.ws_slot0 = 0;
-        ntiles[n] = frac;
-        ntiles[n - 1] -= frac;
-        nent = n + 1;
+    if (T2 * 2 <= sms && ctx->ws) {
+      for (int i = 0; i < n; ++i) {
+        TcProblem& p = grp.p[i];
+        const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+        int sp = sms / T2;
+        if (sp > 8) sp = 8;
+        if (sp > num_kb / 4) sp = num_kb / 4;
+        if (sp < 2) continue;
+        const int kbs = (num_kb + sp - 1) / sp;
+        const int spl = (num_kb + kbs - 1) / kbs;
+        if (spl < 2 || slots + ntiles[i] * p.nsplit * spl > ctx->ws_slots) continue;
+        p.kb_split = kbs;
+        p.splits = spl;
+        p.ws_slot0 = slots;
+        slots += ntiles[i] * p.nsplit * spl;
       }
+    }
+  } else if (can_split && BN == 256 && T > sms && n < TC_MAX_PROBLEMS) {
+    const int frac = T % sms;
+    if (frac > 0 && frac * 2 <= sms && frac <= ntiles[n - 1] && grp.p[n - 1].N > 128) {
+      grp.p[n] = grp.p[n - 1];
+      TcProblem& tail = grp.p[n];
+      tail.tile_first = ntiles[n - 1] - frac;
+      tail.nsplit = 2;
+      tail.bn_eff = 128;
+      ntiles[n] = frac;
+      ntiles[n - 1] -= frac;
+      nent = n + 1;
     }
   }
   int units = 0;
-  for (int i = 0; i < nent; ++i) { grp.p[i].tile_start = units; units += ntiles[i] * grp.p[i].splits; }
+  for (int i = 0; i < nent; ++i) { grp.p[i].tile_start = units; units += ntiles[i] * grp.p[i].nsplit * grp.p[i].splits; }
   grp.num_problems = nent;
   grp.total_tiles = units;
   grp.mn_lbo = ctx->mn_lbo;
@@ -974,7 +1005,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
     if (rc) return rc;
     p.tiles_m = (g.M + TC2_BM - 1) / TC2_BM;
     p.tiles_n = (g.N + Cfg::BN - 1) / Cfg::BN;
-    p.tile_start = tiles; p.tile_first = 0; p.splits = 1; p.kb_split = 0; p.ws_slot0 = 0;
+    p.tile_start = tiles; p.tile_first = 0; p.splits = 1; p.kb_split = 0; p.ws_slot0 = 0; p.nsplit = 1; p.bn_eff = Cfg::BN;
     p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
     if (p.sym) {
       for (int pm = 0; pm < p.tiles_m; ++pm) tiles += p.tiles_n - pm;
