@@ -56,6 +56,7 @@ SYMBOLS = {
     "psgd_norm_lower_bound_spd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "psgd_norm_lower_bound_skh": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "psgd_procrustes_step2": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _sz, _vp]),
+    "psgd_kron_factor_update": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "psgd_kwns4_head": (_i, [_vp, _i64, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp, _i, _f, _vp]),
     "psgd_kwns4_tail": (_i, [_vp, _i64, _i64, _vp, _i, _vp, _i, _vp, _f, _f, _f, _vp]),
     "psgd_lra_workspace_bytes": (_sz, [_vp, C.POINTER(LraT)]),

@@ -702,6 +702,31 @@ int psgd_norm_lower_bound_skh(psgd_handle_t h, int dt, const void* A, int s, con
   return bound_entry(h, dt, A, s, V0, out, ws, wsb, stream, false);
 }
 
+// one factor's share of psgd.py:404-416 given its Gram / sums of squares (building block of the order >= 3 host composition)
+int psgd_kron_factor_update(psgd_handle_t h, int dt, int kind, int s, void* q, float* L, const void* term1, float t2, float lr, float betaL,
+                            const void* V0_spd, const void* V0_skh, void* workspace, size_t wsb, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !q || !L || !term1 || s < 1) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (kind == PSGD_DIAG) {
+    DISPATCH_T(dt, (k_diag_update<T><<<1, 1024, 0, st>>>((T*)q, (const float*)term1, s, t2, lr, betaL, L)));
+    LAUNCH_CHECK(ctx, "k_diag_update");
+    return PSGD_OK;
+  }
+  if (!V0_spd || !V0_skh) return PSGD_ERR_INVALID_ARG;
+  HelperWs w;
+  layout_helper(s, dt, workspace, w);
+  if (!workspace || wsb < w.total) return PSGD_ERR_WORKSPACE;
+  int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+  rc = check_cuda(ctx, cudaMemcpyAsync(w.R, term1, (size_t)s * s * dtype_size(dt), cudaMemcpyDeviceToDevice, st), "memcpy"); if (rc) return rc;
+  DISPATCH_T(dt, (k_rowstats<T><<<s, 256, 0, st>>>((const T*)w.R, s, w.row_sumsq, w.nf, nullptr)));
+  LAUNCH_CHECK(ctx, "k_rowstats");
+  DenseItem it;
+  it.s = s; it.q = q; it.L = L; it.t2 = t2; it.T = w.R; it.Qn = w.Qn; it.RQ = w.RQ; it.RRQ = w.RRQ; it.Va = w.Va; it.Vb = w.Vb;
+  it.v_spd = V0_spd; it.v_skh = V0_skh; it.f = &w.f;
+  return run_dense_factors(ctx, dt, &it, 1, lr, betaL, st);
+}
+
 int psgd_procrustes_step2(psgd_handle_t h, int dt, void* Q, int s, const void* V0, float max_step_size, void* workspace, size_t wsb,
                           void* stream) {
   Ctx* ctx = reinterpret_cast<Ctx*>(h);

@@ -60,7 +60,10 @@ class _ExprG:
             return X * Y
         if self.order == 1:
             return gemm(X.reshape(-1, 1), Y.reshape(-1, 1), trans_b=True) if self.dense else X * Y
-        assert self.order == 2
+        if self.order > 2:
+            Mx = X.movedim(self.i, 0).reshape(X.shape[self.i], -1)
+            My = Y.movedim(self.i, 0).reshape(Y.shape[self.i], -1)
+            return gemm(Mx, My, trans_b=True) if self.dense else torch.sum(Mx * My, dim=1)
         if self.dense:
             return gemm(X, Y, trans_b=True) if self.i == 0 else gemm(X, Y, trans_a=True)
         return torch.sum(X * Y, dim=1 - self.i)
@@ -97,9 +100,7 @@ def init_kron(t, Scale=1.0, max_size=float("inf"), max_skew=1.0, dQ="Q0.5EQ1.5")
 # ------------------------------------------------------------------------------------------------
 def _kron_desc(Q, L, G):
     order = G.dim()
-    if order > 2:
-        raise NotImplementedError("tensors of order >= 3 are SURVEY.md 8(f) item 3 (not built yet); "
-                                  "KWNS4 squeezes singleton dims first, reshape the rest to 2-D")
+    assert order <= 2, "order >= 3 tensors take the host-side composition (_update_kron_nd / _apply_kron_nd)"
     if len(Q) != max(order, 1):
         raise EngineError("Q does not match the tensor order")
     for q in Q:
@@ -131,10 +132,66 @@ def _dummy(device):
     return d
 
 
+def _mode_product(q, X, i, transpose):
+    """Apply a dense factor along dim i of an order >= 3 tensor: a GEMM on the mode-i matricisation (engine), permutes by torch."""
+    Xi = X.movedim(i, 0)
+    shp = Xi.shape
+    Y = gemm(q, Xi.reshape(shp[0], -1), trans_a=transpose)
+    return Y.reshape(shp).movedim(0, i)
+
+
+def _apply_kron_nd(Q, G):
+    """psgd.py:322-327 for tensors of order >= 3: host-side composition of engine GEMMs, one mode at a time."""
+    X = G
+    for i, q in enumerate(Q):
+        if q.dim() == 2:
+            X = _mode_product(q, X, i, False)
+    for i, q in enumerate(Q):
+        if q.dim() == 2:
+            X = _mode_product(q, X, i, True)
+        else:
+            shp = [1] * X.dim()
+            shp[i] = -1
+            X = X * (q * q).reshape(shp)
+    return X.contiguous()
+
+
+def _update_kron_nd(Q, L, G, lr, betaL, damping, noise):
+    """psgd.py:394-419 for order >= 3: Pg by mode products, then per factor the engine's factor update (bound, L, Newton-Schulz,
+    procrustes) on the mode-i Gram."""
+    lib = _lib.load_library()
+    h = _lib.handle_for(G.device)
+    dt = _lib.dtype_code(G)
+    damp = damping + torch.finfo(G.dtype).eps * G.abs()
+    Pg = _apply_kron_nd(Q, G + damp * noise["N"])
+    numel = G.numel()
+    for i, q in enumerate(Q):
+        M = Pg.movedim(i, 0).reshape(Pg.shape[i], -1).contiguous()
+        s = q.shape[0]
+        if q.dim() == 2:
+            term1 = gemm(M, M, trans_b=True)
+            ws = _lib.workspace(G.device, lib.psgd_helper_workspace_bytes(h, s, dt))
+            rc = lib.psgd_kron_factor_update(h, dt, _lib.PSGD_DENSE, s, _lib.ptr(q), _lib.ptr(L[i]), _lib.ptr(term1), float(numel / s),
+                                             float(lr), float(betaL), _lib.ptr(noise["spd"][i]), _lib.ptr(noise["skh"][i]), _lib.ptr(ws),
+                                             ws.numel(), _lib.stream_ptr(G.device))
+        else:
+            term1 = torch.sum(M.float() * M.float(), dim=1).contiguous()
+            rc = lib.psgd_kron_factor_update(h, dt, _lib.PSGD_DIAG, s, _lib.ptr(q), _lib.ptr(L[i]), _lib.ptr(term1), float(numel / s),
+                                             float(lr), float(betaL), None, None, None, 0, _lib.stream_ptr(G.device))
+        _lib.check(h, rc, "psgd_kron_factor_update")
+    if noise.get("balance", False):
+        balance_kron_precond(Q)
+
+
 def _apply_kron(Q, G, sumsq_out=None):
     if not G.is_cuda:
         raise EngineError("psgd_torch_b200 runs on CUDA (sm_100a) tensors only")
     G = G.contiguous()
+    if G.dim() > 2:
+        out = _apply_kron_nd(Q, G)
+        if sumsq_out is not None:
+            sumsq_out.copy_(torch.sum(out.float() ** 2).reshape(sumsq_out.shape))
+        return out
     k = _kron_desc(Q, None, G)
     d = _dummy(G.device)  # the apply never touches L; the descriptor validator wants non-null pointers
     k.LL, k.LR = d.data_ptr(), d.data_ptr() + 4
@@ -180,6 +237,8 @@ def update_precond_kron_whiten_q0p5eq1p5(QL, exprs, G, lr=0.1, betaL=0.9, dampin
     G = G.contiguous()
     if noise is None:
         noise = draw_kron_noise(G, Q)
+    if G.dim() > 2:
+        return _update_kron_nd(Q, L, G, lr, betaL, damping, noise)
     k = _kron_desc(Q, L, G)
     nz = KronNoiseT()
     nz.N = noise["N"].data_ptr()
@@ -203,8 +262,12 @@ def balance_kron_precond(Q):
     """psgd.py:266-275, in place."""
     if len(Q) <= 1:
         return
-    if len(Q) > 2:
-        raise NotImplementedError("order >= 3: SURVEY.md 8(f) item 3")
+    if len(Q) > 2:  # order >= 3: host-side composition (fp32 factors, cf. k_balance_scale)
+        norms = torch.stack([q.abs().max().float() for q in Q])
+        gmean = torch.prod(norms) ** (1 / len(Q))
+        for q, nrm in zip(Q, norms):
+            q.mul_(gmean / nrm)
+        return
     G = torch.empty(Q[0].shape[0], Q[1].shape[0], dtype=Q[0].dtype, device="meta")
     k = KronT()
     k.m, k.n, k.has_r = Q[0].shape[0], Q[1].shape[0], 1

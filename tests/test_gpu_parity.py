@@ -17,7 +17,7 @@ from conftest import GOLDEN, load_golden, relerr
 
 pytestmark = pytest.mark.gpu
 
-KRON = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "kron_*.pt")) if "order3" not in p)
+KRON = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "kron_*.pt")))
 LRA = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "lra_*.pt")))
 TOL = {"torch.float32": 1e-5, "torch.bfloat16": 2e-2}
 
@@ -259,3 +259,28 @@ def test_lra_tensor_core_sweeps_match_oracle(n, r):
         Pe = psgd.precond_grad_lra(UVe, g.to(dev))
         P64 = orc.precond_grad_lra([x.detach().cpu().double() for x in UVe], g.double())
         assert relerr(Pe, P64) < 1e-2
+
+
+def test_kwns4_on_the_reference_demo_shape():
+    """The reference's own DDP demo parameter (1 x 2 x 3 x 4, ddp.py:193): squeeze -> order-3 tensor -> host-side composition path."""
+    from psgd_torch_b200 import KWNS4, psgd
+    from oracle import psgd_oracle as orc
+    dev = _dev()
+    torch.manual_seed(7)
+    p0 = torch.randn(1, 2, 3, 4)
+    p = torch.nn.Parameter(p0.clone().to(dev))
+    p_o = p0.clone()
+    opt = KWNS4([p], preconditioner_dtype=torch.float32, lr_params=1e-2)
+    state = {}
+    import unittest.mock as mock
+    for step in range(4):
+        grad = torch.randn(1, 2, 3, 4)
+        Qcur = state["QL"][0] if state else orc.init_kron(grad.squeeze())[0]
+        noise = orc.draw_kron_noise(grad.squeeze(), Qcur)
+        orc.kwns4_param_step(p_o, grad.clone(), state, noise, preconditioner_dtype=torch.float32, lr_params=1e-2)
+        p.grad = grad.to(dev)
+        with mock.patch.object(psgd, "draw_kron_noise", lambda G, Q: _noise_to(noise, dev)):
+            opt.step()
+        assert relerr(p, p_o) < 1e-5
+        for q, qo in zip(opt.state[p]["QL"][0], state["QL"][0]):
+            assert relerr(q, qo) < 1e-5
