@@ -52,6 +52,7 @@ struct alignas(64) TcGroup {
   int total_tiles;
   int mn_lbo, mn_sbo;
   int* error_flag;
+  int l2_prefetch;  // k-blocks of L2 prefetch distance (0 = off)
   float* ws;        // split-K workspace: slots of 128 x BN fp32, zero between launches
   int* ws_count;    // arrival counter per slot, zero between launches
 };
@@ -113,6 +114,10 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// bring a box into L2 ahead of the TMA load that will need it (first-touch DRAM latency is what stalls a 4-stage ring)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -405,6 +410,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           const int bn = p.bn_eff;
+          if (g.l2_prefetch > 0 && kb + g.l2_prefetch < kb1) {
+            const int kp = (kb + g.l2_prefetch) * TC_BK;
+            if (!p.a_mn) tma_prefetch_l2_2d(&p.map_a, kp, tm * TC_BM);
+            else { tma_prefetch_l2_2d(&p.map_a, tm * TC_BM, kp); tma_prefetch_l2_2d(&p.map_a, tm * TC_BM + 64, kp); }
+            if (!p.b_mn) tma_prefetch_l2_2d(bn == BN ? &p.map_b : &p.map_b_half, kp, tn * bn);
+            else for (int c = 0; c < bn / 64; ++c) tma_prefetch_l2_2d(&p.map_b, tn * bn + c * 64, kp);
+          }
           mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + bn * TC_BK * 2);
           if (!p.a_mn) {
             tma_load_2d(&p.map_a, full_bar(stage), sa, kb * TC_BK, tm * TC_BM);
@@ -447,14 +459,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
         const int kb0 = kslice * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
-        // the barrier probe of stage s+1 is issued BEFORE the MMAs of stage s, so its ~90-cycle latency hides behind the MMA issue
-        // instead of leaving the tensor pipe idle between k-blocks (ncu: 35 % idle with a serial wait -> issue -> commit loop)
-        uint32_t ready = mbar_try(full_bar(stage), phase);
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (!ready) mbar_wait(full_bar(stage), phase, g.error_flag);
+          mbar_wait(full_bar(stage), phase, g.error_flag);
           int nstage = stage + 1; uint32_t nphase = phase;
           if (nstage == Cfg::STAGES) { nstage = 0; nphase ^= 1u; }
-          ready = (kb + 1 < kb1) ? mbar_try(full_bar(nstage), nphase) : 0u;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -981,6 +989,7 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
   grp.error_flag = nullptr;
   grp.ws = ctx->ws;
   grp.ws_count = ctx->ws_count;
+  grp.l2_prefetch = (ctx->debug_flags >> 8) & 31;
   static bool attr_set[2] = {false, false};
   const int ai = (BN == 256) ? 0 : 1;
   if (!attr_set[ai]) {
