@@ -34,6 +34,7 @@ struct alignas(64) TcProblem {
   Epi epi;
   int M, N, K;
   int a_mn, b_mn;  // operand is MN-major in memory
+  int a_3d, b_3d;  // MN-major operand whose MN extent is a multiple of 64: the whole tile is ONE 3-D TMA box {64, 64 k-rows, chunks}
   int sym;         // symmetric output: only tiles that reach the upper triangle are enumerated
   int tiles_m, tiles_n;
   int tile_start;  // first flat work-unit index of this problem
@@ -118,6 +119,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
 // bring a box into L2 ahead of the TMA load that will need it (first-touch DRAM latency is what stalls a 4-stage ring)
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -410,16 +417,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           const int bn = p.bn_eff;
-          if (g.l2_prefetch > 0 && kb + g.l2_prefetch < kb1) {
-            const int kp = (kb + g.l2_prefetch) * TC_BK;
-            if (!p.a_mn) tma_prefetch_l2_2d(&p.map_a, kp, tm * TC_BM);
-            else { tma_prefetch_l2_2d(&p.map_a, tm * TC_BM, kp); tma_prefetch_l2_2d(&p.map_a, tm * TC_BM + 64, kp); }
-            if (!p.b_mn) tma_prefetch_l2_2d(bn == BN ? &p.map_b : &p.map_b_half, kp, tn * bn);
-            else for (int c = 0; c < bn / 64; ++c) tma_prefetch_l2_2d(&p.map_b, tn * bn + c * 64, kp);
-          }
           mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + bn * TC_BK * 2);
+          // the producer thread's issue rate is a real limit (each TMA op costs tens of cycles): one op per operand whenever possible
           if (!p.a_mn) {
             tma_load_2d(&p.map_a, full_bar(stage), sa, kb * TC_BK, tm * TC_BM);
+          } else if (p.a_3d) {
+            tma_load_3d(&p.map_a, full_bar(stage), sa, 0, kb * TC_BK, tm * (TC_BM / 64));
           } else {
 #pragma unroll
             for (int c = 0; c < TC_BM / 64; ++c)
@@ -427,6 +430,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           if (!p.b_mn) {
             tma_load_2d(bn == BN ? &p.map_b : &p.map_b_half, full_bar(stage), sb, kb * TC_BK, tn * bn);
+          } else if (p.b_3d) {
+            tma_load_3d(bn == BN ? &p.map_b : &p.map_b_half, full_bar(stage), sb, 0, kb * TC_BK, tn * (bn / 64));
           } else {
             for (int c = 0; c < bn / 64; ++c)
               tma_load_2d(&p.map_b, full_bar(stage), sb + c * (TC_BK * 128), tn * bn + c * 64, kb * TC_BK);
@@ -886,6 +891,24 @@ static int make_tmap(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int 
   return PSGD_OK;
 }
 
+// MN-major operand (rows = K, cols = MN, cols % 64 == 0) as a 3-D tensor {64 elems, rows, cols/64}: box {64, 64, chunks} lands in smem as
+// [chunk][k row][64 elems] -- the same layout the per-chunk 2-D boxes produce -- with a single TMA operation
+static int make_tmap_mn3(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int chunks) {
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  if (!fn) return PSGD_ERR_CUDA;
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, (cuuint32_t)chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(ctx->last_error, sizeof(ctx->last_error), "cuTensorMapEncodeTiled(3d) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return PSGD_ERR_CUDA;
+  }
+  return PSGD_OK;
+}
+
 bool tc_eligible(const GemmDesc& g) {
   if (g.in_dtype != PSGD_BF16) return false;
   if (g.M < 128 || g.N < 8 || g.K < 64) return false;  // narrow N (the 32-probe norm-bound products) rides on TMA zero fill
@@ -915,10 +938,14 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     p.a_mn = g.ta ? 1 : 0;        // A stored K x M: M runs along the contiguous dimension
     p.b_mn = g.tb ? 0 : 1;        // B stored K x N: N runs along the contiguous dimension
     int rc;
+    p.a_3d = (g.ta && g.M % 64 == 0 && !(ctx->debug_flags & 32)) ? 1 : 0;
+    p.b_3d = (!g.tb && g.N % 64 == 0 && !(ctx->debug_flags & 32)) ? 1 : 0;
     if (!g.ta) rc = make_tmap(ctx, &p.map_a, g.A, g.M, g.K, g.lda, TC_BM);
+    else if (p.a_3d) rc = make_tmap_mn3(ctx, &p.map_a, g.A, g.K, g.M, g.lda, TC_BM / 64);
     else rc = make_tmap(ctx, &p.map_a, g.A, g.K, g.M, g.lda, TC_BK);
     if (rc) return rc;
     if (g.tb) rc = make_tmap(ctx, &p.map_b, g.B, g.N, g.K, g.ldb, BN);
+    else if (p.b_3d) rc = make_tmap_mn3(ctx, &p.map_b, g.B, g.K, g.N, g.ldb, BN / 64);
     else rc = make_tmap(ctx, &p.map_b, g.B, g.K, g.N, g.ldb, TC_BK);
     if (rc) return rc;
     p.tiles_m = (g.M + TC_BM - 1) / TC_BM;
@@ -932,6 +959,7 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     }
     p.tile_first = 0; p.splits = 1; p.kb_split = (g.K + TC_BK - 1) / TC_BK; p.ws_slot0 = 0; p.nsplit = 1; p.bn_eff = BN;
     if (BN == 256 && g.tb) { rc = make_tmap(ctx, &p.map_b_half, g.B, g.N, g.K, g.ldb, 128); if (rc) return rc; }
+    if (BN == 256 && p.b_3d) { rc = make_tmap_mn3(ctx, &p.map_b_half, g.B, g.K, g.N, g.ldb, 2); if (rc) return rc; }
     T += ntiles[i];
   }
   // ---- filling the machine ----
@@ -1027,6 +1055,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.a_mn = g.ta ? 1 : 0;
     p.b_mn = g.tb ? 0 : 1;
+    p.a_3d = 0; p.b_3d = 0;
     int rc;
     if (!g.ta) rc = make_tmap(ctx, &p.map_a, g.A, g.M, g.K, g.lda, 128);
     else rc = make_tmap(ctx, &p.map_a, g.A, g.K, g.M, g.lda, TC_BK);
