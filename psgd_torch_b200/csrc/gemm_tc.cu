@@ -26,7 +26,8 @@ namespace psgd {
 constexpr int TC_MAX_PROBLEMS = 4;
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;   // warp 0: TMA producer of A, warp 1: MMA issuer, warps 2-5: epilogue, warp 6: TMA producer of B
+constexpr int TC2_THREADS = 192;
 
 struct alignas(64) TcProblem {
   CUtensorMap map_a;
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }   // full: one arrival per producer warp
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
     fence_barrier_init();
     for (int i = 0; i < g.num_problems; ++i) { prefetch_tmap(&g.p[i].map_a); prefetch_tmap(&g.p[i].map_b); }
@@ -401,9 +402,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == 6) {
+    // ===================== TMA producers: warp 0 streams A, warp 6 streams B =====================
+    // (the issue rate of a single producer thread is a measurable limit: every TMA op costs tens of cycles next to the ~90-cycle
+    //  barrier probe, and a 128 x 256 x 64 k-block leaves only 512 cycles)
     if (lane == 0) {
+      const bool do_a = warp == 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
@@ -412,29 +416,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const TcProblem& p = g.p[pi];
         const int num_kb = (p.K + TC_BK - 1) / TC_BK;
         const int kb0 = kslice * p.kb_split, kb1 = min(num_kb, kb0 + p.kb_split);
+        const int bn = p.bn_eff;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, g.error_flag);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
-          const int bn = p.bn_eff;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + bn * TC_BK * 2);
-          // the producer thread's issue rate is a real limit (each TMA op costs tens of cycles): one op per operand whenever possible
-          if (!p.a_mn) {
-            tma_load_2d(&p.map_a, full_bar(stage), sa, kb * TC_BK, tm * TC_BM);
-          } else if (p.a_3d) {
-            tma_load_3d(&p.map_a, full_bar(stage), sa, 0, kb * TC_BK, tm * (TC_BM / 64));
-          } else {
+          if (do_a) {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d(&p.map_a, full_bar(stage), sa, kb * TC_BK, tm * TC_BM);
+            } else if (p.a_3d) {
+              tma_load_3d(&p.map_a, full_bar(stage), sa, 0, kb * TC_BK, tm * (TC_BM / 64));
+            } else {
 #pragma unroll
-            for (int c = 0; c < TC_BM / 64; ++c)
-              tma_load_2d(&p.map_a, full_bar(stage), sa + c * (TC_BK * 128), tm * TC_BM + c * 64, kb * TC_BK);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(bn == BN ? &p.map_b : &p.map_b_half, full_bar(stage), sb, kb * TC_BK, tn * bn);
-          } else if (p.b_3d) {
-            tma_load_3d(bn == BN ? &p.map_b : &p.map_b_half, full_bar(stage), sb, 0, kb * TC_BK, tn * (bn / 64));
+              for (int c = 0; c < TC_BM / 64; ++c)
+                tma_load_2d(&p.map_a, full_bar(stage), sa + c * (TC_BK * 128), tm * TC_BM + c * 64, kb * TC_BK);
+            }
           } else {
-            for (int c = 0; c < bn / 64; ++c)
-              tma_load_2d(&p.map_b, full_bar(stage), sb + c * (TC_BK * 128), tn * bn + c * 64, kb * TC_BK);
+            mbar_arrive_expect_tx(full_bar(stage), bn * TC_BK * 2);
+            if (!p.b_mn) {
+              tma_load_2d(bn == BN ? &p.map_b : &p.map_b_half, full_bar(stage), sb, kb * TC_BK, tn * bn);
+            } else if (p.b_3d) {
+              tma_load_3d(bn == BN ? &p.map_b : &p.map_b_half, full_bar(stage), sb, 0, kb * TC_BK, tn * (bn / 64));
+            } else {
+              for (int c = 0; c < bn / 64; ++c)
+                tma_load_2d(&p.map_b, full_bar(stage), sb + c * (TC_BK * 128), tn * bn + c * 64, kb * TC_BK);
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -707,7 +714,7 @@ struct Tc2Cfg {
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
   using Cfg = Tc2Cfg;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -1088,7 +1095,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   const bool timed = ctx->timing_on && ctx->timing_count < ctx->ev_capacity;
   if (timed) cudaEventRecord(ctx->ev_begin[ctx->timing_count], st);
-  gemm_tc2_kernel<<<2 * pairs, TC_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
+  gemm_tc2_kernel<<<2 * pairs, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
   if (timed) {
     cudaEventRecord(ctx->ev_end[ctx->timing_count], st);
     ctx->timing_count++;
