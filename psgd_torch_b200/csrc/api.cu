@@ -167,21 +167,24 @@ struct BoundJob {
   const void* A; int s; const void* V0; const float* row_sumsq; const float* nf_src; BoundWs* w; void* Va; void* Vb;
 };
 
-static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, cudaStream_t st) {
+// finish: mode 0 -> dense-factor L update + step (needs t2, lr, betaL, L, fs); mode 1 -> procrustes normaliser (fs); mode 2 -> bound only
+struct BoundFinish { int mode; float t2, lr, betaL; float* L; float* fs; };
+
+static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st) {
   const float tiny = dtype_tiny(dt);
   bool tc_form[2];
   for (int j = 0; j < n; ++j) {
     tc_form[j] = ctx->gemm_path != 1 && !(ctx->debug_flags & 4) && dt == PSGD_BF16 && jb[j].s >= 128 && (jb[j].s % 8) == 0;
-    k_bound_prep<<<1, 1024, 0, st>>>(jb[j].row_sumsq, jb[j].s, jb[j].nf_src, tiny, jb[j].w->scal);
-    LAUNCH_CHECK(ctx, "k_bound_prep");
-    DISPATCH_T(dt, (k_probe_init<T><<<32, 256, 0, st>>>((const T*)jb[j].A, jb[j].s, (const T*)jb[j].V0, jb[j].w->scal, (T*)jb[j].Va)));
+    DISPATCH_T(dt, (k_probe_init<T><<<32, 1024, 0, st>>>((const T*)jb[j].A, jb[j].s, (const T*)jb[j].V0, jb[j].row_sumsq, jb[j].nf_src, tiny,
+                                                          jb[j].w->scal, (T*)jb[j].Va)));
     LAUNCH_CHECK(ctx, "k_probe_init");
   }
   GemmDesc g[2];
   // four products W <- W A / nf with a row normalisation after the 1st and 3rd (psgd.py:64-67).
   // tensor-core formulation: the probes stay transposed, X = W^T (s x 32), X_new = A^T X: the s-long dimension is the UMMA M
   // dimension, the 32 probes ride in N, A is read through MN-major descriptors (no transposed copy); probe norms are column
-  // sums of squares and the normalisation a column scale.  SIMT formulation (small / fp32): W (32 x s) row-major as written.
+  // sums of squares and the normalisation a column factor computed in the consumer's epilogue from those sums (no glue kernel).
+  // SIMT formulation (small / fp32): W (32 x s) row-major as written.
   for (int step = 0; step < 4; ++step) {
     for (int j = 0; j < n; ++j) {
       const BoundJob& J = jb[j];
@@ -189,32 +192,28 @@ static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, cudaStream_t st) {
       void* src = (step & 1) ? J.Vb : J.Va;
       void* dst = (step & 1) ? J.Va : J.Vb;
       const int s = J.s;
+      const int axis = tc_form[j] ? 2 : 1;
       if (tc_form[j]) {
         if (step == 0) g[j] = gemm_desc(dt, J.A, s, 1, src, s, 1, s, 32, s, dst, 32);   // V1 is stored 32 x s
         else g[j] = gemm_desc(dt, J.A, s, 1, src, 32, 0, s, 32, s, dst, 32);
-        if (step == 0 || step == 2) g[j].epi.alpha_ptr = w.scal + SC_INV_NF; else g[j].epi.col_scale = (step == 1) ? w.sc1 : w.sc3;
-        if (step == 0) g[j].epi.col_sumsq = w.rn1;
-        if (step == 2) g[j].epi.col_sumsq = w.rn3;
-        if (step == 3) g[j].epi.col_sumsq = w.rn4;
       } else {
         g[j] = gemm_desc(dt, src, s, 0, J.A, s, 0, 32, s, s, dst, s);
-        if (step == 0 || step == 2) g[j].epi.alpha_ptr = w.scal + SC_INV_NF; else g[j].epi.row_scale = (step == 1) ? w.sc1 : w.sc3;
-        if (step == 0) g[j].epi.row_sumsq = w.rn1;
-        if (step == 2) g[j].epi.row_sumsq = w.rn3;
-        if (step == 3) g[j].epi.row_sumsq = w.rn4;
       }
+      Epi& e = g[j].epi;
+      if (step == 0 || step == 2) {
+        e.alpha_ptr = w.scal + SC_INV_NF;
+      } else {
+        e.norm_axis = axis; e.norm_sumsq = (step == 1) ? w.rn1 : w.rn3; e.norm_inv_nf = w.scal + SC_INV_NF; e.norm_tiny = tiny;
+      }
+      float* sums = step == 0 ? w.rn1 : (step == 2 ? w.rn3 : (step == 3 ? w.rn4 : nullptr));
+      if (sums) { if (tc_form[j]) e.col_sumsq = sums; else e.row_sumsq = sums; }
     }
     int rc = launch_gemm_group(ctx, g, n, st); if (rc) return rc;
-    if (step == 0 || step == 2) {
-      for (int j = 0; j < n; ++j) {
-        k_rowscale<<<1, 32, 0, st>>>(step == 0 ? jb[j].w->rn1 : jb[j].w->rn3, jb[j].w->scal, tiny, step == 0 ? jb[j].w->sc1 : jb[j].w->sc3, 32);
-        LAUNCH_CHECK(ctx, "k_rowscale");
-      }
-    }
   }
   for (int j = 0; j < n; ++j) {
-    k_bound_final<<<1, 32, 0, st>>>(jb[j].w->rn4, 32, jb[j].w->scal, dt);
-    LAUNCH_CHECK(ctx, "k_bound_final");
+    const BoundFinish f = fin ? fin[j] : BoundFinish{2, 0.f, 0.f, 0.f, nullptr, nullptr};
+    k_bound_finish<<<1, 32, 0, st>>>(jb[j].w->rn4, 32, jb[j].w->scal, dt, f.mode, f.t2, f.lr, f.betaL, f.L, f.fs, tiny);
+    LAUNCH_CHECK(ctx, "k_bound_finish");
   }
   return PSGD_OK;
 }
@@ -235,14 +234,18 @@ static int run_procrustes(Ctx* ctx, int dt, DenseItem* it, int n, float max_step
   for (int i = 0; i < n; ++i) {
     const int s = it[i].s;
     dim3 grid((s + 63) / 64, (s + 63) / 64);
-    DISPATCH_T(dt, (k_skew<T><<<grid, 256, 0, st>>>((const T*)it[i].Qn, (T*)it[i].T, s, it[i].f->r_abs_max, it[i].f->r_row_sumsq)));
+    if (dt == PSGD_BF16 && s % 8 == 0 && (reinterpret_cast<uintptr_t>(it[i].Qn) & 15u) == 0 && (reinterpret_cast<uintptr_t>(it[i].T) & 15u) == 0) {
+      k_skew_bf16x8<<<grid, 256, 0, st>>>((const bf16*)it[i].Qn, (bf16*)it[i].T, s, it[i].f->r_abs_max, it[i].f->r_row_sumsq);
+    } else {
+      DISPATCH_T(dt, (k_skew<T><<<grid, 256, 0, st>>>((const T*)it[i].Qn, (T*)it[i].T, s, it[i].f->r_abs_max, it[i].f->r_row_sumsq)));
+    }
     LAUNCH_CHECK(ctx, "k_skew");
     jb[i] = BoundJob{it[i].T, s, it[i].v_skh, it[i].f->r_row_sumsq, it[i].f->r_abs_max, &it[i].f->b_skh, it[i].Va, it[i].Vb};
   }
-  int rc = run_bounds(ctx, dt, jb, n, st); if (rc) return rc;
+  BoundFinish fin[2];
+  for (int i = 0; i < n; ++i) fin[i] = BoundFinish{1, 0.f, 0.f, 0.f, nullptr, it[i].f->fs};
+  int rc = run_bounds(ctx, dt, jb, n, fin, st); if (rc) return rc;
   for (int i = 0; i < n; ++i) {
-    k_procrustes_scal<<<1, 32, 0, st>>>(it[i].f->b_skh.scal, dtype_tiny(dt), it[i].f->fs);
-    LAUNCH_CHECK(ctx, "k_procrustes_scal");
     g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].Qn, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].RQ, it[i].s);     // RQ = R Qn / |R|
     g[i].epi.alpha_ptr = it[i].f->fs + FS_INV_SR; g[i].epi.trace = it[i].f->fs + FS_TR1;
   }
@@ -274,10 +277,10 @@ static int run_dense_factors(Ctx* ctx, int dt, DenseItem* it, int n, float lr, f
   GemmDesc g[2];
   for (int i = 0; i < n; ++i)
     jb[i] = BoundJob{it[i].T, it[i].s, it[i].v_spd, it[i].f->row_sumsq, it[i].f->diag_max, &it[i].f->b_spd, it[i].Va, it[i].Vb};
-  int rc = run_bounds(ctx, dt, jb, n, st); if (rc) return rc;
+  BoundFinish fin[2];
+  for (int i = 0; i < n; ++i) fin[i] = BoundFinish{0, it[i].t2, lr, betaL, it[i].L, it[i].f->fs};
+  int rc = run_bounds(ctx, dt, jb, n, fin, st); if (rc) return rc;
   for (int i = 0; i < n; ++i) {
-    k_dense_L_update<<<1, 32, 0, st>>>(it[i].f->b_spd.scal, it[i].t2, lr, betaL, it[i].L, it[i].f->fs, dt);
-    LAUNCH_CHECK(ctx, "k_dense_L_update");
     // Qn = Q - lr/L (term1 Q - t2 Q)    psgd.py:415   (out of place: Q is an operand of the product)
     g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].q, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].Qn, it[i].s);
     g[i].epi.alpha_ptr = it[i].f->fs + FS_ALPHA; g[i].epi.D = it[i].q; g[i].epi.ldd = it[i].s; g[i].epi.d_dtype = dt; g[i].epi.beta = 1.f;
@@ -688,7 +691,7 @@ static int bound_entry(psgd_handle_t h, int dt, const void* A, int s, const void
   DISPATCH_T(dt, (k_rowstats<T><<<s, 256, 0, st>>>((const T*)A, s, w.row_sumsq, spd ? w.nf : nullptr, spd ? nullptr : w.nf)));
   LAUNCH_CHECK(ctx, "k_rowstats");
   BoundJob jb{A, s, V0, w.row_sumsq, w.nf, &w.f.b_spd, w.Va, w.Vb};
-  rc = run_bounds(ctx, dt, &jb, 1, st); if (rc) return rc;
+  rc = run_bounds(ctx, dt, &jb, 1, nullptr, st); if (rc) return rc;
   k_copy_scalar<<<1, 32, 0, st>>>(w.f.b_spd.scal + SC_BOUND, out);
   LAUNCH_CHECK(ctx, "k_copy_scalar");
   return PSGD_OK;

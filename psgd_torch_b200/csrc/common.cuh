@@ -64,6 +64,12 @@ struct Epi {
   const float* d_row_scale;  // optional per-row / per-column factors of the D term (fp32): used to add back the bf16 rounding residual of
   const float* d_col_scale;  // the diagonal of P = Q^T Q, (P_bf16 + diag(resid)) X = P_bf16 X + resid_i X_ij
   float* diag_resid;       // [M]: (unrounded - rounded) value of C[i,i]
+  // row (axis 1) / column (axis 2) normalisation folded with a device scalar: factor = min(*norm_inv_nf / (sqrt(norm_sumsq[idx]) + norm_tiny), 3e38)
+  // (psgd.py:66 `V /= |V| + tiny` followed by the /nf of the next product; the clamp keeps 0 * factor = 0 when a probe row is exactly 0)
+  const float* norm_sumsq;
+  const float* norm_inv_nf;
+  float norm_tiny;
+  int norm_axis;
   float* row_sumsq;        // [M] += sum_j C[i,j]^2
   float* col_sumsq;        // [N] += sum_i C[i,j]^2
   float* diag_max;         // max_i C[i,i]   (values assumed >= 0; buffer zero-initialised)
@@ -78,6 +84,7 @@ __host__ inline Epi make_epi(void* C, int ldc, int out_dtype) {
   e.alpha = 1.f; e.alpha_ptr = nullptr;
   e.D = nullptr; e.ldd = 0; e.d_dtype = out_dtype; e.beta = 0.f; e.beta_ptr = nullptr;
   e.row_scale = nullptr; e.col_scale = nullptr; e.d_row_scale = nullptr; e.d_col_scale = nullptr; e.diag_resid = nullptr;
+  e.norm_sumsq = nullptr; e.norm_inv_nf = nullptr; e.norm_tiny = 0.f; e.norm_axis = 0;
   e.row_sumsq = nullptr; e.col_sumsq = nullptr; e.diag_max = nullptr; e.abs_max = nullptr; e.trace = nullptr;
   e.total_sumsq = nullptr;
   return e;
@@ -86,6 +93,10 @@ __host__ inline Epi make_epi(void* C, int ldc, int out_dtype) {
 // non-negative float max via integer atomics (buffer initialised to 0)
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
   if (v > 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+__device__ __forceinline__ float epi_norm_factor(const Epi& e, int idx) {
+  return fminf(*e.norm_inv_nf / (sqrtf(e.norm_sumsq[idx]) + e.norm_tiny), 3.0e38f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
     int gm = m0 + ty * 4 + i;
     if (gm >= M) continue;
     float rs = e.row_scale ? e.row_scale[gm] : 1.f;
+    if (e.norm_axis == 1) rs *= epi_norm_factor(e, gm);
     float rsum = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
       if (gn >= N) continue;
       float v = acc[i][j] * alpha * rs;
       if (e.col_scale) v *= e.col_scale[gn];
+      if (e.norm_axis == 2) v *= epi_norm_factor(e, gn);
       if (e.D) v += beta * ld_as_float(e.D, e.d_dtype, (size_t)gm * e.ldd + gn) * (e.d_row_scale ? e.d_row_scale[gm] : 1.f) * (e.d_col_scale ? e.d_col_scale[gn] : 1.f);
       float r = round_to(e.out_dtype, v);
       if (e.diag_resid && gm == gn) e.diag_resid[gm] = v - r;

@@ -227,12 +227,17 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
                                                float beta, int lane, RowAcc& ra, int mirror) {
   float v[32];
   const bool row_ok = row < M;
-  const float rs = (e.row_scale && row_ok) ? e.row_scale[row] : 1.f;
+  float rs = (e.row_scale && row_ok) ? e.row_scale[row] : 1.f;
+  if (e.norm_axis == 1 && row_ok) rs *= epi_norm_factor(e, row);
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * alpha * rs;
   if (e.col_scale) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < N) ? e.col_scale[col0 + j] : 0.f;
+  }
+  if (e.norm_axis == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= (col0 + j < N) ? epi_norm_factor(e, col0 + j) : 0.f;
   }
   if (e.D && row_ok) {
     const float drs = beta * (e.d_row_scale ? e.d_row_scale[row] : 1.f);
@@ -957,7 +962,7 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     if (rc) return rc;
     p.tiles_m = (g.M + TC_BM - 1) / TC_BM;
     p.tiles_n = (g.N + BN - 1) / BN;
-    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
+    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis) ? 1 : 0;
     if (p.sym) {
       ntiles[i] = 0;
       for (int tm = 0; tm < p.tiles_m; ++tm) ntiles[i] += p.tiles_n - (tm * TC_BM) / BN;
@@ -1073,7 +1078,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
     p.tiles_m = (g.M + TC2_BM - 1) / TC2_BM;
     p.tiles_n = (g.N + Cfg::BN - 1) / Cfg::BN;
     p.tile_start = tiles; p.tile_first = 0; p.splits = 1; p.kb_split = 0; p.ws_slot0 = 0; p.nsplit = 1; p.bn_eff = Cfg::BN;
-    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq) ? 1 : 0;
+    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis) ? 1 : 0;
     if (p.sym) {
       for (int pm = 0; pm < p.tiles_m; ++pm) tiles += p.tiles_n - pm;
     } else {

@@ -140,28 +140,82 @@ __global__ void __launch_bounds__(256) k_skew(const T* __restrict__ Q, T* __rest
   if (tid == 0 && abs_max) atomic_max_nonneg(abs_max, am);
 }
 
-// j = argmax_i rowsumsq[i]; nf = *nf_src + tiny   (psgd.py:58-61 / 83-86). One block.
-__global__ void k_bound_prep(const float* __restrict__ row_sumsq, int s, const float* __restrict__ nf_src, float tiny,
-                             float* scal) {
+// bf16, s % 8 == 0: same tile-pair scheme with 16-byte global accesses (8 columns per thread)
+__global__ void __launch_bounds__(256) k_skew_bf16x8(const bf16* __restrict__ Q, bf16* __restrict__ R, int s, float* abs_max, float* row_sumsq) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi > bj) return;
+  __shared__ float tA[64][65];  // Q[i0 + y][j0 + x]
+  __shared__ float tB[64][65];  // Q[j0 + y][i0 + x]
+  __shared__ float red[32];
+  const int i0 = bi * 64, j0 = bj * 64, tid = threadIdx.x;
+  const int cg = tid & 7, r0 = tid >> 3;   // column group (8 elements), row within a 32-row half
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int y = r0 + 32 * hh;
+    float a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
+    if (i0 + y < s && j0 + 8 * cg < s) ld8(Q + (size_t)(i0 + y) * s + j0 + 8 * cg, a);
+    if (j0 + y < s && i0 + 8 * cg < s) ld8(Q + (size_t)(j0 + y) * s + i0 + 8 * cg, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { tA[y][8 * cg + e] = a[e]; tB[y][8 * cg + e] = b[e]; }
+  }
+  __syncthreads();
+  float am = 0.f;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {     // pass 0: tile (bi, bj); pass 1: its mirror (bj, bi)
+    if (pass == 1 && bi == bj) break;
+    const float(*S)[65] = pass == 0 ? tB : tA;   // transposed source
+    const float(*D)[65] = pass == 0 ? tA : tB;   // direct source
+    const int ri0 = pass == 0 ? i0 : j0, ci0 = pass == 0 ? j0 : i0;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int y = r0 + 32 * hh;
+      float o[8];
+      float rs = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float f = rbf(S[8 * cg + e][y] - D[y][8 * cg + e]);
+        o[e] = f;
+        rs = fmaf(f, f, rs);
+        am = fmaxf(am, fabsf(f));
+      }
+      const bool ok = ri0 + y < s && ci0 + 8 * cg < s;
+      if (ok) st8(R + (size_t)(ri0 + y) * s + ci0 + 8 * cg, o); else rs = 0.f;
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1); rs += __shfl_xor_sync(0xffffffffu, rs, 2); rs += __shfl_xor_sync(0xffffffffu, rs, 4);
+      if (cg == 0 && ri0 + y < s && row_sumsq) atomicAdd(&row_sumsq[ri0 + y], rs);
+    }
+  }
+  am = block_max(am, red);
+  if (tid == 0 && abs_max) atomic_max_nonneg(abs_max, am);
+}
+
+// Fused psgd.py:58-63: j = argmax_i rowsumsq[i], nf = *nf_src + tiny, and the rotated probe V[p,:] = A[j,:]/nf + sgn(<A[j,:]/nf, V0[p,:]>) V0[p,:].
+// grid = k (one block of 1024 threads per probe row); every block recomputes the (tiny) argmax, block 0 publishes nf, 1/nf and j.
+template <typename T>
+__global__ void __launch_bounds__(1024) k_probe_init(const T* __restrict__ A, int s, const T* __restrict__ V0, const float* __restrict__ row_sumsq,
+                                                     const float* __restrict__ nf_src, float tiny, float* scal, T* __restrict__ V) {
   __shared__ float sv[32];
   __shared__ int si[32];
+  __shared__ float red[32];
+  __shared__ float sgn_s;
+  __shared__ int j_s;
   float best = -1.f;
   int bi = 0x7fffffff;
   for (int i = threadIdx.x; i < s; i += blockDim.x) {
     float v = row_sumsq[i];
-    if (v > best) { best = v; bi = i; }  // first occurrence within this thread's strided subsequence
+    if (v > best) { best = v; bi = i; }
   }
-  // warp argmax (ties -> smallest index, torch.argmax returns the first maximal element)
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = 16; o > 0; o >>= 1) {   // ties -> smallest index (torch.argmax returns the first maximal element)
     float ov = __shfl_xor_sync(0xffffffffu, best, o);
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) { sv[w] = best; si[w] = bi; }
   __syncthreads();
   if (w == 0) {
-    int nw = (blockDim.x + 31) >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
     best = lane < nw ? sv[lane] : -1.f;
     bi = lane < nw ? si[lane] : 0x7fffffff;
     for (int o = 16; o > 0; o >>= 1) {
@@ -169,24 +223,18 @@ __global__ void k_bound_prep(const float* __restrict__ row_sumsq, int s, const f
       int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (lane == 0) {
-      float nf = *nf_src + tiny;
-      scal[SC_NF] = nf;
-      scal[SC_INV_NF] = 1.f / nf;
-      reinterpret_cast<int*>(scal)[SC_J] = (bi == 0x7fffffff) ? 0 : bi;
-    }
+    if (lane == 0) j_s = (bi == 0x7fffffff) ? 0 : bi;
   }
-}
-
-// V[p,:] = A[j,:]/nf + sgn(<A[j,:]/nf, V0[p,:]>) * V0[p,:]     psgd.py:62-63. grid = k (one block per probe row)
-template <typename T>
-__global__ void k_probe_init(const T* __restrict__ A, int s, const T* __restrict__ V0, const float* __restrict__ scal,
-                             T* __restrict__ V) {
-  __shared__ float red[32];
-  __shared__ float sgn_s;
+  __syncthreads();
+  const int j = j_s;
+  const float nf = *nf_src + tiny;
+  const float inv_nf = 1.f / nf;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[SC_NF] = nf;
+    scal[SC_INV_NF] = inv_nf;
+    reinterpret_cast<int*>(scal)[SC_J] = j;
+  }
   const int p = blockIdx.x;
-  const int j = reinterpret_cast<const int*>(scal)[SC_J];
-  const float inv_nf = scal[SC_INV_NF];
   const T* arow = A + (size_t)j * s;
   const T* v0 = V0 + (size_t)p * s;
   float dot = 0.f;
@@ -217,6 +265,29 @@ __global__ void k_bound_final(const float* __restrict__ rn, int k, float* scal, 
   float v = threadIdx.x < k ? rn[threadIdx.x] : 0.f;
   v = warp_max(v);
   if (threadIdx.x == 0) scal[SC_BOUND] = round_to(dtype, scal[SC_NF] * round_to(dtype, sqrtf(v)));
+}
+
+// bound = nf * max_p sqrt(rn[p]) (psgd.py:68) fused with its consumer:
+//   mode 0: dense-factor L update + step size (psgd.py:412-415): fs[FS_ALPHA] = -lr/L, fs[FS_BETA] = 1 + lr/L*t2
+//   mode 1: procrustes normaliser (psgd.py:118): fs[FS_INV_SR] = 1 / (bound + tiny)
+__global__ void k_bound_finish(const float* __restrict__ rn, int k, float* scal, int dtype, int mode, float t2, float lr, float betaL, float* L,
+                               float* fs, float tiny) {
+  float v = threadIdx.x < k ? rn[threadIdx.x] : 0.f;
+  v = warp_max(v);
+  if (threadIdx.x == 0) {
+    const float bound = round_to(dtype, scal[SC_NF] * round_to(dtype, sqrtf(v)));
+    scal[SC_BOUND] = bound;
+    if (mode == 0) {
+      const float ell = round_to(dtype, bound + t2);
+      const float Ln = fmaxf(betaL * (*L) + (1.f - betaL) * ell, ell);
+      *L = Ln;
+      const float c = lr / Ln;
+      fs[FS_ALPHA] = -c;
+      fs[FS_BETA] = 1.f + c * t2;
+    } else if (mode == 1) {
+      fs[FS_INV_SR] = 1.f / (bound + tiny);
+    }
+  }
 }
 
 // dense factor: ell = bound + t2; L = max(betaL*L + (1-betaL)*ell, ell); c = lr/L   psgd.py:412-415
