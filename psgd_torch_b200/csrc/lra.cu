@@ -730,13 +730,29 @@ int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
     long long need = ((n + rpi - 1) / rpi + 4 * 8 - 1) / (4 * 8);   // blocks of 8 warps x 4 groups
     int gridc = (int)(need < (long long)ctx->num_sms * 8 ? need : (long long)ctx->num_sms * 8);
     if (gridc < 1) gridc = 1;
+    const bool ring_ok = al16(l->d) && al16(g) && !(ctx->debug_flags & 64);
+    const int smem_ring = 8 * 8 * (32 * r * 2 + 256);
+    static bool attr_a = false;
+    if (!attr_a) {
+      cudaFuncSetAttribute(k_lra_apply_ring<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * (32 * 32 * 2 + 256));
+      cudaFuncSetAttribute(k_lra_apply_ring<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * (32 * 16 * 2 + 256));
+      attr_a = true;
+    }
+    long long chunks = (n + 31) / 32;
+    int gridr = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
+    if (gridr < 1) gridr = 1;
     for (int mode = 0; mode < 3; ++mode) {
       const bf16* Mx = (const bf16*)(mode == 1 ? l->U : l->V);
       const float* pin = mode == 0 ? nullptr : (mode == 1 ? w.p1 : w.p2);
       float* pout = mode == 0 ? w.p1 : (mode == 1 ? w.p2 : nullptr);
-      if (r == 32) k_lra_apply_bf16<32><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
-      else k_lra_apply_bf16<16><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
-      ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply_bf16"); if (rc) return rc;
+      if (ring_ok) {
+        if (r == 32) k_lra_apply_ring<32><<<gridr, 256, smem_ring, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
+        else k_lra_apply_ring<16><<<gridr, 256, smem_ring, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
+      } else {
+        if (r == 32) k_lra_apply_bf16<32><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
+        else k_lra_apply_bf16<16><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
+      }
+      ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply"); if (rc) return rc;
     }
     return PSGD_OK;
   }
