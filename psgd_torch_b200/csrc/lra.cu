@@ -730,29 +730,35 @@ int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
     long long need = ((n + rpi - 1) / rpi + 4 * 8 - 1) / (4 * 8);   // blocks of 8 warps x 4 groups
     int gridc = (int)(need < (long long)ctx->num_sms * 8 ? need : (long long)ctx->num_sms * 8);
     if (gridc < 1) gridc = 1;
-    const bool ring_ok = al16(l->d) && al16(g) && !(ctx->debug_flags & 64);
-    const int smem_ring = 8 * 8 * (32 * r * 2 + 256);
+    // whole 256-row blocks through the bulk-copy ring, the remainder (< 256 rows) through the direct-load kernel on offset pointers
+    const bool tma_ok = al16(l->d) && al16(g) && !(ctx->debug_flags & 64);
+    const long long n_full = tma_ok ? n / 256 : 0;
+    const long long n_rem = n - n_full * 256;
+    const int tile_bytes = 256 * r * 2 + 256 * 2 + 256 * 2 + 256 * 4;
     static bool attr_a = false;
     if (!attr_a) {
-      cudaFuncSetAttribute(k_lra_apply_ring<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * (32 * 32 * 2 + 256));
-      cudaFuncSetAttribute(k_lra_apply_ring<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * (32 * 16 * 2 + 256));
+      cudaFuncSetAttribute(k_lra_apply_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (256 * 32 * 2 + 2048));
+      cudaFuncSetAttribute(k_lra_apply_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (256 * 16 * 2 + 2048));
       attr_a = true;
     }
-    long long chunks = (n + 31) / 32;
-    int gridr = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
-    if (gridr < 1) gridr = 1;
+    int gridt = (int)(n_full < (long long)ctx->num_sms ? n_full : (long long)ctx->num_sms);
+    long long need_r = ((n_rem + rpi - 1) / rpi + 4 * 8 - 1) / (4 * 8);
+    int gridrem = (int)(need_r < 1 ? 1 : need_r);
     for (int mode = 0; mode < 3; ++mode) {
       const bf16* Mx = (const bf16*)(mode == 1 ? l->U : l->V);
       const float* pin = mode == 0 ? nullptr : (mode == 1 ? w.p1 : w.p2);
       float* pout = mode == 0 ? w.p1 : (mode == 1 ? w.p2 : nullptr);
-      if (ring_ok) {
-        if (r == 32) k_lra_apply_ring<32><<<gridr, 256, smem_ring, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
-        else k_lra_apply_ring<16><<<gridr, 256, smem_ring, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
-      } else {
-        if (r == 32) k_lra_apply_bf16<32><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
-        else k_lra_apply_bf16<16><<<gridc, 256, 0, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n, mode, pin, pout, sumsq_out);
+      if (n_full > 0) {
+        if (r == 32) k_lra_apply_tma<32><<<gridt, 288, 8 * tile_bytes, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n_full, mode, pin, pout, sumsq_out);
+        else k_lra_apply_tma<16><<<gridt, 288, 8 * tile_bytes, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n_full, mode, pin, pout, sumsq_out);
+        ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply_tma"); if (rc) return rc;
       }
-      ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply"); if (rc) return rc;
+      if (n_rem > 0) {
+        const long long o = n_full * 256;
+        if (r == 32) k_lra_apply_bf16<32><<<gridrem, 256, 0, st>>>(Mx + o * r, (const bf16*)l->d + o, (const bf16*)g + o, w.dd + o, (bf16*)out + o, n_rem, mode, pin, pout, sumsq_out);
+        else k_lra_apply_bf16<16><<<gridrem, 256, 0, st>>>(Mx + o * r, (const bf16*)l->d + o, (const bf16*)g + o, w.dd + o, (bf16*)out + o, n_rem, mode, pin, pout, sumsq_out);
+        ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply_bf16"); if (rc) return rc;
+      }
     }
     return PSGD_OK;
   }

@@ -687,4 +687,136 @@ __global__ void __launch_bounds__(256, 1) k_lra_apply_ring(const bf16* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// apply sweeps fed by the bulk-copy engine: one producer thread issues cp.async.bulk (TMA 1-D) copies of whole 256-row blocks of the
+// factor (16 KB for r = 32) plus the block's d / g / g2 slices into an 8-stage mbarrier ring; 8 consumer warps do the row dot products
+// from shared memory.  ~130 KB in flight per SM for one instruction per 16 KB: the per-thread-load versions topped out at 3.2-3.8 TB/s.
+// n_full = number of whole 256-row blocks; the (< 256 rows) remainder is handled by k_lra_apply_bf16 on offset pointers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lra_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void lra_mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void lra_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void lra_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins == 1024u) t0 = clock64();
+    if (spins > 1024u && (spins & 1023u) == 0u && clock64() - t0 > 8000000000LL) __trap();   // never hang the GPU on a pipeline bug
+  }
+}
+__device__ __forceinline__ void lra_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int RP>
+__global__ void __launch_bounds__(288, 1) k_lra_apply_tma(const bf16* __restrict__ Mtx, const bf16* __restrict__ d, const bf16* __restrict__ g,
+                                                          float* __restrict__ g2, bf16* __restrict__ out, long long n_full, int mode,
+                                                          const float* __restrict__ pin, float* __restrict__ pout, float* sumsq) {
+  constexpr int ROWS = 256;
+  constexpr int PPR = RP / 8;
+  constexpr int MAT_BYTES = ROWS * RP * 2;
+  constexpr int OFF_D = MAT_BYTES, OFF_G = OFF_D + ROWS * 2, OFF_G2 = OFF_G + ROWS * 2;
+  constexpr int TILE = OFF_G2 + ROWS * 4;
+  constexpr int STAGES = 8;
+  constexpr int NP = 32 * PPR / 32;   // 16-byte pieces per lane for a warp's 32 rows
+  extern __shared__ __align__(128) uint8_t smem_lra[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES];
+  __shared__ float pacc[RP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32_generic(smem_lra);
+  const uint32_t bbase = smem_u32_generic(bars);
+  if (threadIdx.x == 0) {
+    for (int s0 = 0; s0 < STAGES; ++s0) { lra_mbar_init(bbase + 8 * s0, 1); lra_mbar_init(bbase + 8 * (STAGES + s0), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < RP) pacc[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long blk = blockIdx.x; blk < n_full; blk += gridDim.x) {
+        lra_mbar_wait(bbase + 8 * (STAGES + stage), phase ^ 1u);
+        const uint32_t tile = sbase + stage * TILE, fb = bbase + 8 * stage;
+        const long long r0 = blk * ROWS;
+        const uint32_t vbytes = (mode == 2) ? ROWS * 4 : ROWS * 2;
+        lra_mbar_expect_tx(fb, MAT_BYTES + ROWS * 2 + vbytes);
+        lra_bulk_g2s(tile, Mtx + r0 * RP, MAT_BYTES, fb);
+        lra_bulk_g2s(tile + OFF_D, d + r0, ROWS * 2, fb);
+        if (mode == 2) lra_bulk_g2s(tile + OFF_G2, g2 + r0, ROWS * 4, fb);
+        else lra_bulk_g2s(tile + OFF_G, g + r0, ROWS * 2, fb);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    const int cw = warp - 1;             // consumer warp 0..7 -> rows [32 cw, 32 cw + 32) of the stage
+    const int piece = lane % PPR;
+    float pv[8], acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { pv[c] = (mode > 0) ? pin[piece * 8 + c] : 0.f; acc[c] = 0.f; }
+    float ssq = 0.f;
+    int stage = 0; uint32_t phase = 0;
+    for (long long blk = blockIdx.x; blk < n_full; blk += gridDim.x) {
+      lra_mbar_wait(bbase + 8 * stage, phase);
+      const uint8_t* tile = smem_lra + stage * TILE;
+      const bf16* dv = reinterpret_cast<const bf16*>(tile + OFF_D);
+      const bf16* gv = reinterpret_cast<const bf16*>(tile + OFF_G);
+      const float* g2v = reinterpret_cast<const float*>(tile + OFF_G2);
+      const long long r0 = blk * ROWS;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int p = lane + 32 * i;
+        const int lrow = cw * 32 + p / PPR;
+        const uint4 raw = *reinterpret_cast<const uint4*>(tile + (size_t)lrow * RP * 2 + (p % PPR) * 16);
+        float x[8];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { float2 f = __bfloat1622float2(h2[c]); x[2 * c] = f.x; x[2 * c + 1] = f.y; }
+        const float dd = __bfloat162float(dv[lrow]);
+        if (mode == 0) {
+          const float y = __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(gv[lrow])));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = fmaf(x[c], y, acc[c]);
+        } else {
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dot = fmaf(x[c], pv[c], dot);
+#pragma unroll
+          for (int o = 1; o < PPR; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          if (mode == 1) {
+            const float y = __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(gv[lrow]))) + dot;
+            if (piece == 0) g2[r0 + lrow] = y;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fmaf(x[c], y, acc[c]);
+          } else if (piece == 0) {
+            const bf16 o = __float2bfloat16_rn(dd * (g2v[lrow] + dot));
+            out[r0 + lrow] = o;
+            const float f = __bfloat162float(o);
+            ssq = fmaf(f, f, ssq);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) lra_mbar_arrive(bbase + 8 * (STAGES + stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+    if (mode < 2) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v = acc[c];
+#pragma unroll
+        for (int o = PPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < PPR) atomicAdd(&pacc[piece * 8 + c], v);
+      }
+    } else if (sumsq) {
+      float v = warp_sum(ssq);
+      if (lane == 0) atomicAdd(sumsq, v);
+    }
+  }
+  __syncthreads();
+  if (mode < 2 && threadIdx.x < RP) atomicAdd(&pout[threadIdx.x], pacc[threadIdx.x]);
+}
+
 }  // namespace psgd
