@@ -351,6 +351,7 @@ def run_engine(args):
     launches = lib.psgd_launch_count(h) - l0
     n_l, t_ms, fl = C.c_int(), C.c_double(), C.c_double()
     lib.psgd_timing_read(h, C.byref(n_l), C.byref(t_ms), C.byref(fl))
+    fl_exec = lib.psgd_timing_executed_flops(h)
     lib.psgd_timing_enable(h, 0)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -376,6 +377,10 @@ def run_engine(args):
                 "peak_source": peak_src + ", sustained cuBLAS bf16 figure (kernel timed inside a long step)",
                 "launches_timed": n_l.value, "avg_launch_ms": (t_ms.value / n_l.value) if n_l.value else None,
                 "algorithmic_flops_per_launch": (fl.value / n_l.value) if n_l.value else None,
+                "executed_tflops": (fl_exec / (t_ms.value * 1e-3) / 1e12) if t_ms.value > 0 else None,
+                "note": "achieved = algorithmic FLOPs (2MNK of the true sizes, full-GEMM counting of SURVEY.md 8d: symmetric Grams / Q^T Q counted in "
+                        "full) / CUDA-event time; executed_tflops = what the tensor cores actually did (symmetric products compute only their upper "
+                        "128-blocks, tiles padded to 128x256)",
                 "traffic": None, "traffic_note": "see profiles/ for the ncu --set full capture of this kernel"}
         prof = os.path.join(ROOT, "profiles", "gemm_tc_traffic.json")
         if os.path.exists(prof):

@@ -66,6 +66,7 @@ SYMBOLS = {
     "psgd_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _f, _vp, _i, _f, _vp]),
     "psgd_timing_enable": (_i, [_vp, _i]),
     "psgd_timing_read": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "psgd_timing_executed_flops": (C.c_double, [_vp]),
     "psgd_debug_set_flags": (_i, [_vp, _i]),
     "psgd_debug_set_tile_n": (_i, [_vp, _i]),
     "psgd_debug_set_mn_desc": (_i, [_vp, _i, _i]),

@@ -492,6 +492,7 @@ int psgd_timing_enable(psgd_handle_t h, int on) {
   ctx->timing_on = on ? 1 : 0;
   ctx->timing_count = 0;
   ctx->timing_flops = 0.0;
+  ctx->timing_flops_exec = 0.0;
   return PSGD_OK;
 }
 
@@ -507,6 +508,8 @@ int psgd_timing_read(psgd_handle_t h, int* launches, double* total_ms, double* f
   *launches = ctx->timing_count; *total_ms = ms; *flops = ctx->timing_flops;
   return PSGD_OK;
 }
+
+double psgd_timing_executed_flops(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->timing_flops_exec : 0.0; }
 
 int psgd_debug_set_flags(psgd_handle_t h, int flags) {
   if (!h) return PSGD_ERR_INVALID_ARG;

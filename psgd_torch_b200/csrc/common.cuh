@@ -155,6 +155,7 @@ struct Ctx {
   int timing_on;
   int timing_count;      // event pairs recorded since the last reset
   double timing_flops;   // algorithmic FLOPs (2*M*N*K, true sizes) of the recorded launches
+  double timing_flops_exec;  // FLOPs the tensor cores actually executed for them (tile-padded, upper-blocks-only for symmetric products)
   cudaEvent_t* ev_begin;
   cudaEvent_t* ev_end;
   int ev_capacity;

@@ -1045,6 +1045,7 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     cudaEventRecord(ctx->ev_end[ctx->timing_count], st);
     ctx->timing_count++;
     for (int i = 0; i < n; ++i) ctx->timing_flops += 2.0 * gs[i].M * (double)gs[i].N * gs[i].K;
+    for (int i = 0; i < nent; ++i) ctx->timing_flops_exec += 2.0 * ntiles[i] * (double)TC_BM * BN * grp.p[i].K;
   }
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "gemm_tc");

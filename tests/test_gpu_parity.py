@@ -284,3 +284,65 @@ def test_kwns4_on_the_reference_demo_shape():
         assert relerr(p, p_o) < 1e-5
         for q, qo in zip(opt.state[p]["QL"][0], state["QL"][0]):
             assert relerr(q, qo) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE-size cases (4096 x 4096 bf16, 4096 x 14336): too slow for the CPU oracle inside a test, so checked through
+# size-independent properties of the math.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4096, 4096), (4096, 14336)])
+def test_full_size_properties(shape):
+    from psgd_torch_b200 import psgd
+    dev = _dev()
+    m, n = shape
+    gen = torch.Generator(device=dev).manual_seed(11)
+    G = (0.01 * torch.randn(m, n, device=dev, generator=gen)).bfloat16()
+    QL, exprs = psgd.init_kron(G)
+    for _ in range(3):
+        psgd.update_precond_kron_whiten_q0p5eq1p5(QL, exprs, G, lr=0.5)
+    Q, L = QL
+    assert all(torch.isfinite(q.float()).all() for q in Q) and all(float(l) > 0 for l in L)
+    # (1) dense factors stay (nearly) symmetric: procrustes_step2 drives Q^T - Q -> 0 (psgd.py:101-124)
+    for q in Q:
+        if q.dim() == 2:
+            asym = float((q.float() - q.float().T).norm() / q.float().norm())
+            assert asym < 2e-2
+    # (2) the apply is linear: P(aX + bY) = a P(X) + b P(Y)
+    X = (0.01 * torch.randn(m, n, device=dev, generator=gen)).bfloat16()
+    Y = (0.01 * torch.randn(m, n, device=dev, generator=gen)).bfloat16()
+    lhs = psgd.precond_grad_kron(QL, exprs, (2.0 * X.float() - 0.5 * Y.float()).bfloat16())
+    rhs = 2.0 * psgd.precond_grad_kron(QL, exprs, X).float() - 0.5 * psgd.precond_grad_kron(QL, exprs, Y).float()
+    assert relerr(lhs, rhs) < 2e-2
+    # (3) the apply equals (Q_L^T Q_L) X (Q_R^T Q_R) evaluated by torch in fp32 on the same bf16 state
+    def PX(Z):
+        Zf = Z.float()
+        Zf = (Q[0].float().T @ (Q[0].float() @ Zf)) if Q[0].dim() == 2 else Zf * (Q[0].float() ** 2)[:, None]
+        Zf = ((Zf @ Q[1].float().T) @ Q[1].float()) if Q[1].dim() == 2 else Zf * (Q[1].float() ** 2)[None, :]
+        return Zf
+    assert relerr(psgd.precond_grad_kron(QL, exprs, X), PX(X)) < 1e-2
+    # (4) sum of squares fused into the last product (KWNS4's clipping input) matches the output
+    ss = torch.zeros(1, device=dev)
+    H = psgd.precond_grad_kron(QL, exprs, X, sumsq_out=ss)
+    assert abs(float(ss) - float((H.float() ** 2).sum())) / float(ss) < 1e-3
+    # (5) an update with a vanishing step leaves Q (essentially) unchanged while L still tracks the bound
+    Q0 = [q.clone() for q in Q]
+    psgd.update_precond_kron_whiten_q0p5eq1p5(QL, exprs, G, lr=1e-6)
+    for q, q0 in zip(Q, Q0):
+        assert relerr(q, q0) < 2e-2
+
+
+def test_norm_bound_is_a_lower_bound_at_full_size():
+    """psgd.py:46-68 at s = 4096 on the tensor-core formulation: bound <= ||A||_2, and not loose by more than 2x."""
+    from psgd_torch_b200 import psgd
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(5)
+    W = torch.randn(4096, 4096 + 64, device=dev, generator=gen)
+    A = (W @ W.T / 4096).bfloat16()
+    b = float(psgd.norm_lower_bound_spd(A))
+    x = torch.randn(4096, 1, device=dev, generator=gen)
+    Af = A.float()
+    for _ in range(60):
+        x = Af @ x
+        x = x / x.norm()
+    lam = float((x.T @ Af @ x))
+    assert 0.5 * lam <= b <= lam * 1.02
