@@ -418,6 +418,12 @@ def precond_grad_lra(UVd, g, sumsq_out=None):
     return out
 
 
+def update_precond_lra_newton(UVd, Luvd, v, h, lr=0.1, betaL=0.9, damping=1e-9, update_U=None):
+    """psgd.py:1193-1198: LRA Newton update = update_precond_lra on (v, h + damping * randn_like(h)) (independent noise on the Hvp).
+    RNG order: randn_like(h) then the CPU coin of update_precond_lra."""
+    update_precond_lra(UVd, Luvd, v, h + damping * torch.randn_like(h), lr=lr, betaL=betaL, update_U=update_U)
+
+
 # north_star's names for the LRA functions (old.py:657,744; SURVEY.md 0): thin aliases of the psgd.py math
 update_precond_UVd = update_precond_lra
 precond_grad_UVd = precond_grad_lra
@@ -438,5 +444,4 @@ for _n in ("eq", "qep", "qeq", "pro4p", "quad", "quad4p"):
 for _n in ("eq", "qep", "qeq", "q0p5eq1p5", "pro4p", "quad", "quad4p"):
     globals()[f"update_precond_kron_newton_{_n}"] = _not_built(f"update_precond_kron_newton_{_n}", "SURVEY.md 8a K10")
 update_precond_kron_eq = _not_built("update_precond_kron_eq", "SURVEY.md 8a K8")
-update_precond_lra_newton = _not_built("update_precond_lra_newton", "SURVEY.md 8a L5")
 procrustes_step3 = _not_built("procrustes_step3", "SURVEY.md 8a K9")

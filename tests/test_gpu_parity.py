@@ -346,3 +346,46 @@ def test_norm_bound_is_a_lower_bound_at_full_size():
         x = x / x.norm()
     lam = float((x.T @ Af @ x))
     assert 0.5 * lam <= b <= lam * 1.02
+
+
+def test_kwns4_state_dict_roundtrip_and_dtensor_variant():
+    """Checkpoint path: state_dict() pickles (exprs are picklable callables), a fresh optimizer that loads it continues
+    identically; the DTensor variant on plain (non-DTensor) parameters is the same optimizer."""
+    import io, os
+    import torch.distributed as dist
+    from psgd_torch_b200 import KWNS4, psgd
+    from psgd_torch_b200.kwns4_dtensor import KWNS4 as KWNS4DT
+    dev = _dev()
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+        created = True
+    try:
+        torch.manual_seed(3)
+        w0 = torch.randn(48, 40)
+        grads = [torch.randn(48, 40) for _ in range(4)]
+        def run(cls, resume_at=None):
+            p = torch.nn.Parameter(w0.clone().to(dev))
+            opt = cls([p], lr_params=1e-2)
+            torch.manual_seed(99); torch.cuda.manual_seed(99)
+            for i, g in enumerate(grads):
+                if resume_at is not None and i == resume_at:
+                    buf = io.BytesIO(); torch.save(opt.state_dict(), buf); buf.seek(0)
+                    rng = (opt.cpu_rng_state.clone(), opt.cuda_rng_state.clone())
+                    p2 = torch.nn.Parameter(p.detach().clone())
+                    opt2 = cls([p2], lr_params=1e-2)
+                    opt2.load_state_dict(torch.load(buf, weights_only=False))
+                    opt2.cpu_rng_state, opt2.cuda_rng_state = rng   # the reference does not checkpoint its private RNG states either
+                    p, opt = p2, opt2
+                p.grad = g.to(dev)
+                opt.step()
+            return p.detach().clone()
+        a = run(KWNS4)
+        b = run(KWNS4, resume_at=2)
+        c = run(KWNS4DT)
+        assert relerr(b, a) < 1e-6
+        assert relerr(c, a) < 1e-6
+    finally:
+        if created:
+            dist.destroy_process_group()
