@@ -421,6 +421,7 @@ def precond_grad_lra(UVd, g, sumsq_out=None):
 def update_precond_lra_newton(UVd, Luvd, v, h, lr=0.1, betaL=0.9, damping=1e-9, update_U=None):
     """psgd.py:1193-1198: LRA Newton update = update_precond_lra on (v, h + damping * randn_like(h)) (independent noise on the Hvp).
     RNG order: randn_like(h) then the CPU coin of update_precond_lra."""
+    damping = damping + torch.finfo(h.dtype).eps * h.abs()   # psgd.py:1197
     update_precond_lra(UVd, Luvd, v, h + damping * torch.randn_like(h), lr=lr, betaL=betaL, update_U=update_U)
 
 
