@@ -134,6 +134,23 @@ class KWNS4(torch.optim.Optimizer):
             self._sumsq[device] = b
         return b
 
+    def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict casts every floating state tensor to the PARAMETER's dtype, which would silently turn a
+        bf16 preconditioner (and its momentum buffer) into fp32 on resume -- the reference has the same quirk.  Restore the group's
+        preconditioner_dtype for Q and ema (L stays fp32, psgd.py:96-98) so that a resumed run continues on the same arithmetic."""
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:
+            pd = group["preconditioner_dtype"]
+            for p in group["params"]:
+                st = self.state.get(p)
+                if not st:
+                    continue
+                dt = pd or p.dtype
+                Q, L = st["QL"]
+                st["QL"] = [[q.to(dt).contiguous() for q in Q], [l.to(torch.float32) for l in L]]
+                if st.get("ema") is not None:
+                    st["ema"] = st["ema"].to(dt).contiguous()
+
     @torch.no_grad()
     def step(self):
         if self.is_distributed:  # ddp.py:100-104
