@@ -5,6 +5,7 @@
 
 #include <new>
 
+#include <stdlib.h>
 #include "common.cuh"
 #include "kron_kernels.cuh"
 
@@ -439,6 +440,7 @@ int psgd_create(psgd_handle_t* out, int device) {
   ctx->gemm_path = 0;
   ctx->mn_lbo = 8192;
   ctx->mn_sbo = 1024;
+  if (const char* dbg = getenv("PSGD_B200_DEBUG_FLAGS")) ctx->debug_flags = (int)strtol(dbg, nullptr, 0);   // experiments only (see psgd_debug_set_flags)
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);

@@ -54,7 +54,6 @@ struct alignas(64) TcGroup {
   int total_tiles;
   int mn_lbo, mn_sbo;
   int* error_flag;
-  int l2_prefetch;  // k-blocks of L2 prefetch distance (0 = off)
   float* ws;        // split-K workspace: slots of 128 x BN fp32, zero between launches
   int* ws_count;    // arrival counter per slot, zero between launches
 };
@@ -105,6 +104,28 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "r"(bar), "r"(parity)
       : "memory");
   return done;
+}
+// latency-insensitive wait (epilogue warps waiting a whole mainloop for their accumulator): back off with nanosleep so that the four
+// spinning warps stop competing for issue slots and power with the MMA / TMA threads (the chip runs at its power cap)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* error_flag) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(spins < 8 ? 32 : 256);
+    if (++spins == 64u) t0 = clock64();
+    if (spins > 64u && (spins & 255u) == 0u && clock64() - t0 > 8000000000LL) {
+      if (error_flag) atomicExch(error_flag, 1);
+      __trap();
+    }
+  }
+}
+// one elected lane of a fully converged warp (elect.sync): the surrounding code stays warp-uniform, so smem/instruction descriptors are
+// kept in uniform registers -- running the issue loops under `if (lane == 0)` instead makes every UTCHMMA / UTMALDG pay an ELECT loop
+// plus ~8 R2UR moves (seen in SASS), which is of the order of the 128-cycle MMA itself
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -411,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     // ===================== TMA producers: warp 0 streams A, warp 6 streams B =====================
     // (the issue rate of a single producer thread is a measurable limit: every TMA op costs tens of cycles next to the ~90-cycle
     //  barrier probe, and a 128 x 256 x 64 k-block leaves only 512 cycles)
-    if (lane == 0) {
+    {
       const bool do_a = warp == 0;
       int stage = 0;
       uint32_t phase = 0;
@@ -426,7 +447,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1u, g.error_flag);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
-          if (do_a) {
+          if (!elect_one()) {
+            // not the issuing lane
+          } else if (do_a) {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES);
             if (!p.a_mn) {
               tma_load_2d(&p.map_a, full_bar(stage), sa, kb * TC_BK, tm * TC_BM);
@@ -448,13 +471,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                 tma_load_2d(&p.map_b, full_bar(stage), sb + c * (TC_BK * 128), tn * bn + c * 64, kb * TC_BK);
             }
           }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (the whole warp runs the loop; one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -483,16 +507,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
-            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+              const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));  // smem slot is free once these MMAs have read it
+            if (kb + 1 == kb1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
           }
-          umma_commit(empty_bar(stage));  // smem slot is free once these MMAs have read it
+          __syncwarp();
           stage = nstage; phase = nphase;
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -508,7 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const Epi& e = p.epi;
       const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
       const float beta = e.beta * (e.beta_ptr ? *e.beta_ptr : 1.f);
-      mbar_wait(tfull_bar(acc), acc_phase, g.error_flag);
+      mbar_wait_relaxed(tfull_bar(acc), acc_phase, g.error_flag);
       tc_fence_after();
       const int row = tm * TC_BM + quarter * 32 + lane;
       RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -753,7 +780,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; bytes are credited to the leader's full barrier) =====================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < g.total_tiles; t += npairs) {
@@ -768,6 +795,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint32_t lbar = mapa_u32(full_bar(stage), 0);
+          if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
           if (!p.a_mn) {
             tma_load_2d_2sm(&p.map_a, lbar, sa, kb * TC_BK, row0);
@@ -781,13 +809,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm
 #pragma unroll
             for (int c = 0; c < BN / 128; ++c) tma_load_2d_2sm(&p.map_b, lbar, sb + c * (TC_BK * 128), ncol0 + c * 64, kb * TC_BK);
           }
+          }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -815,16 +845,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
-            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
-            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+              const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+              umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(empty_bar(stage));
+            if (kb + 1 == num_kb) umma_commit_2sm(tfull_bar(acc));
           }
-          umma_commit_2sm(empty_bar(stage));
+          __syncwarp();
           stage = nstage; phase = nphase;
         }
-        umma_commit_2sm(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -841,7 +874,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm
       const Epi& e = p.epi;
       const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
       const float beta = e.beta * (e.beta_ptr ? *e.beta_ptr : 1.f);
-      mbar_wait(tfull_bar(acc), acc_phase, g.error_flag);
+      mbar_wait_relaxed(tfull_bar(acc), acc_phase, g.error_flag);
       tc_fence_after();
       const int tm = pm * 2 + (int)rank;                 // this CTA's 128-row block
       const int row = tm * TC_BM + quarter * 32 + lane;
@@ -1029,7 +1062,6 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
   grp.error_flag = nullptr;
   grp.ws = ctx->ws;
   grp.ws_count = ctx->ws_count;
-  grp.l2_prefetch = (ctx->debug_flags >> 8) & 31;
   static bool attr_set[2] = {false, false};
   const int ai = (BN == 256) ? 0 : 1;
   if (!attr_set[ai]) {
@@ -1051,18 +1083,42 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
   return check_cuda(ctx, cudaGetLastError(), "gemm_tc");
 }
 
-// 2-CTA launch: every problem needs M >= 256-ish to make sense; tiles are 256 x 256 pairs
-static bool tc2_worthwhile(const GemmDesc* gs, int n) {
-  for (int i = 0; i < n; ++i)
-    if (gs[i].M < 256 || gs[i].N <= 128) return false;
-  return true;
+// 2-CTA launch (256 x 256 pair tiles, B split between the two SMs: 64 B/clk/SM of operand traffic instead of 96).  Measured on B200 the
+// same work costs a 1-CTA wave ~1.2x a pair wave, but the 1-CTA kernel has finer tiles (half-width tail wave, split-K), so the choice is
+// made on modelled waves: pair waves are whole, 1-CTA waves round up to the next half.
+static bool tc2_worthwhile(const Ctx* ctx, const GemmDesc* gs, int n) {
+  if (ctx->debug_flags & 8) return false;
+  const int pairs = ctx->num_sms / 2;
+  long t2 = 0, t1 = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmDesc& g = gs[i];
+    if (g.M < 256 || g.N <= 128) return false;
+    const bool sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis);
+    const long pm = (g.M + TC2_BM - 1) / TC2_BM, pn = (g.N + TC2_BN - 1) / TC2_BN;
+    const long tm = (g.M + TC_BM - 1) / TC_BM;
+    if (sym) {
+      for (long r = 0; r < pm; ++r) t2 += pn - r;
+      for (long r = 0; r < tm; ++r) t1 += pn - (r * TC_BM) / 256;
+    } else {
+      t2 += pm * pn;
+      t1 += tm * pn;
+    }
+  }
+  if (t2 < pairs) return false;                 // under-filled: the 1-CTA kernel's narrow tiles / split-K fill the machine better
+  const double w2 = (double)((t2 + pairs - 1) / pairs);
+  const long full = t1 / ctx->num_sms, frac = t1 % ctx->num_sms;
+  const double w1 = (double)full + (frac == 0 ? 0.0 : (frac * 2 <= ctx->num_sms ? 0.5 : 1.0));
+  const int pct = (ctx->debug_flags >> 8) & 0xff;     // experiment knob: relative cost of a 1-CTA wave in percent (default 118)
+  return w2 <= w1 * (pct ? pct * 0.01 : 1.18);
 }
 
 static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStream_t st) {
   using Cfg = Tc2Cfg;
   int tiles = 0;
+  double exec_flops = 0.0;
   for (int i = 0; i < n; ++i) {
     const GemmDesc& g = gs[i];
+    const int tiles_before = tiles;
     TcProblem& p = grp.p[i];
     p.epi = g.epi;
     p.M = g.M; p.N = g.N; p.K = g.K;
@@ -1085,6 +1141,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
     } else {
       tiles += p.tiles_m * p.tiles_n;
     }
+    exec_flops += 2.0 * (tiles - tiles_before) * (double)TC2_BM * Cfg::BN * g.K;
   }
   grp.num_problems = n;
   grp.total_tiles = tiles;
@@ -1106,6 +1163,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
     cudaEventRecord(ctx->ev_end[ctx->timing_count], st);
     ctx->timing_count++;
     for (int i = 0; i < n; ++i) ctx->timing_flops += 2.0 * gs[i].M * (double)gs[i].N * gs[i].K;
+    ctx->timing_flops_exec += exec_flops;
   }
   ctx->launches++;
   return check_cuda(ctx, cudaGetLastError(), "gemm_tc2");
@@ -1120,7 +1178,7 @@ int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
   }
   TcGroup grp;
   memset(&grp, 0, sizeof(grp));
-  if (ctx->force_bn == 0 && (ctx->debug_flags & 8) && tc2_worthwhile(gs, n)) return launch_tc2(ctx, grp, gs, n, st);  // measured slower than 1-CTA + split-K on this part: opt-in
+  if (ctx->force_bn == 0 && tc2_worthwhile(ctx, gs, n)) return launch_tc2(ctx, grp, gs, n, st);
   if (ctx->force_bn == 128) return launch_tc<128>(ctx, grp, gs, n, st);
   if (ctx->force_bn == 256) return launch_tc<256>(ctx, grp, gs, n, st);
   if (max_n > 128) return launch_tc<256>(ctx, grp, gs, n, st);

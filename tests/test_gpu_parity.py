@@ -367,8 +367,8 @@ def test_kwns4_state_dict_roundtrip_and_dtensor_variant():
         grads = [torch.randn(48, 40) for _ in range(4)]
         def run(cls, resume_at=None):
             p = torch.nn.Parameter(w0.clone().to(dev))
+            torch.manual_seed(99); torch.cuda.manual_seed(99)   # before construction: the optimizer snapshots its private RNG states there (ddp.py:88-96)
             opt = cls([p], lr_params=1e-2)
-            torch.manual_seed(99); torch.cuda.manual_seed(99)
             for i, g in enumerate(grads):
                 if resume_at is not None and i == resume_at:
                     buf = io.BytesIO(); torch.save(opt.state_dict(), buf); buf.seek(0)
