@@ -172,6 +172,294 @@ def update_precond_kron_whiten_q0p5eq1p5(QL, G, noise, lr=0.1, betaL=0.9, dampin
 
 
 # --------------------------------------------------------------------------------------
+# The other Kron geometries and the Newton-pair updates (psgd.py:127-155, 278-391,
+# 422-513, 657-829).  Random draws come from a NoiseTape so that data-dependent draw counts (the
+# procrustes_step3 loop of PRO4P, psgd.py:444-449) stay in the reference's order.
+# --------------------------------------------------------------------------------------
+class NoiseTape:
+    """Records (items=None) or replays (items=list) the random draws of one update, in draw order.
+    Record mode draws from the torch global generators exactly where the reference does."""
+
+    def __init__(self, items=None):
+        self.replay = items is not None
+        self.items = list(items) if items is not None else []
+        self.pos = 0
+
+    def _next(self, make):
+        if self.replay:
+            v = self.items[self.pos]
+            self.pos += 1
+            return v
+        v = make()
+        self.items.append(v)
+        return v
+
+    def randn_like(self, x):
+        return self._next(lambda: torch.randn_like(x))
+
+    def randn(self, k, s, like):
+        return self._next(lambda: torch.randn(k, s, dtype=like.dtype, device=like.device))
+
+    def rand(self):
+        """CPU coin torch.rand([]) (default-device generator), stored as a python float"""
+        return self._next(lambda: float(torch.rand([])))
+
+
+def init_kron_dq(t, Scale=1.0, max_size=float("inf"), max_skew=1.0, dQ="Q0.5EQ1.5"):
+    """psgd.py:161-263 incl. the squared Scale of the two geometries that fit P directly (psgd.py:186-187)."""
+    if dQ in ("QUAD4P", "PRO4P"):
+        Scale = Scale ** 2
+    return init_kron(t, Scale=Scale, max_size=max_size, max_skew=max_skew)
+
+
+def apply_all_factors(Q, X):
+    """exprA(*Q, X) psgd.py:248-249: every factor applied once along its own dim (no transposes)."""
+    for i, q in enumerate(Q):
+        X = _mode_apply(q, X, i, transpose=False)
+    return X
+
+
+def procrustes_step3(Q, V0, max_step_size=1 / 3):
+    """psgd.py:127-155, in place on Q; V0 = probe of the inner norm_lower_bound_skh (psgd.py:142)."""
+    R = Q.T - Q
+    R = R / (norm_lower_bound_skh(R, V0) + torch.finfo(R.dtype).smallest_normal)
+    RQ = R @ Q
+    RRQ = R @ RQ
+    RRRQ = R @ RRQ
+    tr_RQ = RQ.diagonal().sum()
+    tr_RRQ = RRQ.diagonal().sum()
+    tr_RRRQ = RRRQ.diagonal().sum()
+    if tr_RQ > 0 and tr_RRRQ < 0:  # psgd.py:149
+        if torch.finfo(tr_RQ.dtype).eps > 1e-6:  # psgd.py:151-152
+            tr_RQ, tr_RRQ, tr_RRRQ = tr_RQ.float(), tr_RRQ.float(), tr_RRRQ.float()
+        a = (-tr_RRQ - torch.sqrt(tr_RRQ * tr_RRQ - 1.5 * tr_RQ * tr_RRRQ)) / (0.75 * tr_RRRQ)
+        a = torch.clamp(a, max=max_step_size)
+        Q.add_(a * (RQ + 0.5 * a * (RRQ + 0.25 * a * RRRQ)))
+
+
+def _solve_right_upper(B, A):
+    """B @ inv(A) for upper-triangular A, solved in fp32 and cast back (psgd.py:288-293)."""
+    if B.dim() > 1:
+        return torch.linalg.solve_triangular(lift2single(A), lift2single(B), upper=True, left=False).to(B.dtype)
+    return torch.linalg.solve_triangular(lift2single(A), lift2single(B[None, :]), upper=True, left=False)[0].to(B.dtype)
+
+
+def inv_q_apply(Q, V):
+    """conjB of psgd.py:297-303 for real tensors: V with every dim i multiplied from the right by inv(Q_i)
+    (diagonal factors: division), i.e. kron_i(Q_i^{-T}) V; each solve rounded to V's dtype like the reference."""
+    X = V
+    for i, q in enumerate(Q):
+        if X.dim() == 0:
+            return X / q
+        Xi = X.movedim(i, -1)
+        Xi = Xi / q if q.dim() < 2 else _solve_right_upper(Xi, q)
+        X = Xi.movedim(-1, i)
+    return X
+
+
+def update_precond_kron_eq(QL, V, Hvp, tape, lr=0.1, betaL=0.9):
+    """psgd.py:278-319 (dQ = E*Q, triangular Q), in place. Draws: per dense factor randn(32,s) (psgd.py:62), then the coin (318)."""
+    Q, L = QL
+    A = apply_all_factors(Q, Hvp)
+    conjB = inv_q_apply(Q, V)
+    for i, q in enumerate(Q):
+        dense = q.dim() >= 2
+        term1 = _gram(A, i, dense)
+        term2 = _gram(conjB, i, dense)
+        if not dense:
+            ell = torch.max(term1 + term2)
+            L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+            q.sub_(lr / L[i] * (term1 - term2) * q)
+        else:
+            ell = norm_lower_bound_spd(term1 + term2, tape.randn(32, q.shape[1], q))
+            L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+            q.sub_(lr / L[i] * torch.triu(term1 - term2) @ q)
+    if tape.rand() < 0.01:
+        balance_kron_precond(Q)
+
+
+def _damped(X, damping, tape):
+    """X + (damping + eps|X|) * randn_like(X)   (psgd.py:334-335, 352-353, 661-662, ...)"""
+    damp = damping + torch.finfo(X.dtype).eps * X.abs()
+    return X + damp * tape.randn_like(X)
+
+
+def _factor_loop(Q, L, Pg, term2_of, tape, lr, betaL, dense_step, diag_step, after_dense=None):
+    """Shared skeleton of the per-factor loops of psgd.py:354-364, 377-388, 433-449, 466-479, 496-510, 675-829:
+    term2_of(i, q, dense) returns (term2, is_scalar)."""
+    for i, q in enumerate(Q):
+        dense = q.dim() >= 2
+        term1 = _gram(Pg[i] if isinstance(Pg, list) else Pg, i, dense)
+        term2, scalar = term2_of(i, q, dense)
+        if not dense:
+            ell = (torch.max(term1) + term2) if scalar else torch.max(term1 + term2)
+            L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+            diag_step(q, lr / L[i], term1, term2)
+        else:
+            V0 = tape.randn(32, q.shape[1], q)
+            ell = (norm_lower_bound_spd(term1, V0) + term2) if scalar else norm_lower_bound_spd(term1 + term2, V0)
+            L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+            dense_step(q, lr / L[i], term1, term2, scalar)
+            if after_dense is not None:
+                after_dense(q)
+
+
+def _E_left(q, c, term1, term2, scalar):
+    """q <- q - c (term1 - term2) q     (psgd.py:364, 415, 441, 689, 737, 764)"""
+    if scalar:
+        q.sub_(c * (term1 @ q - term2 * q))
+    else:
+        q.sub_(c * (term1 - term2) @ q)
+
+
+def _E_right(q, c, term1, term2, scalar):
+    """q <- q - c q (term1 - term2)     (psgd.py:388, 713)"""
+    if scalar:
+        q.sub_(c * (q @ term1 - q * term2))
+    else:
+        q.sub_(c * q @ (term1 - term2))
+
+
+def _quad_dense(half):
+    def step(q, c, term1, term2, scalar):
+        """psgd.py:476-479 / 506-509 (whitening), 791-794 / 821-824 (Newton)"""
+        if half:
+            c = c / 2
+        if scalar:
+            p = q - c * (term1 @ q - term2 * q)
+            p = p - c * (p @ term1 - p * term2)
+        else:
+            err = c * (term1 - term2)
+            p = q - err @ q
+            p = p - p @ err
+        q.copy_((p + p.T) / 2)
+    return step
+
+
+def _quad_diag(half):
+    def step(q, c, term1, term2):
+        gain = 1 - (c / 2 if half else c) * (term1 - term2)
+        q.mul_(gain * gain)
+    return step
+
+
+def _mul_diag(q, c, term1, term2):
+    q.mul_(1 - c * (term1 - term2))
+
+
+def _pro4p_after(tape):
+    def after(q):
+        """psgd.py:444-449: up to ten procrustes_step3 rotations, stop once q is almost symmetric (host-side branch)."""
+        for _ in range(10):
+            procrustes_step3(q, tape.randn(32, q.shape[1], q))
+            if (q.T - q).abs().amax() < 0.001 * q.abs().amax():
+                break
+    return after
+
+
+def update_precond_kron_whiten(dQ, QL, G, tape, lr=0.1, betaL=0.9, damping=1e-9):
+    """update_precond_kron_whiten_{eq,qep,qeq,q0p5eq1p5,pro4p,quad,quad4p} (psgd.py:330-513), in place on Q, L."""
+    Q, L = QL
+    numel = G.numel()
+    if dQ == "EQ":  # psgd.py:330-336: the probe V is also the damping noise
+        V = tape.randn_like(G)
+        damp = damping + torch.finfo(G.dtype).eps * G.abs()
+        return update_precond_kron_eq(QL, V, G + damp * V, tape, lr=lr, betaL=betaL)
+    if dQ == "QEP":  # psgd.py:339-364
+        balance_kron_precond(Q)
+        Pg = precond_grad_kron(Q, _damped(G, damping, tape))
+        QPg = None
+
+        def term2_of(i, q, dense):
+            return (numel / q.numel() * q * q, False) if not dense else (numel / q.shape[0] * q @ q.T, False)
+        # term1 uses exprQs[i](q, Pg) with the factor as it is when its turn comes (earlier factors already updated, Pg fixed)
+        for i, q in enumerate(Q):
+            dense = q.dim() >= 2
+            QPg = _mode_apply(q, Pg, i, transpose=False)
+            term1 = _gram(QPg, i, dense)
+            term2, _ = term2_of(i, q, dense)
+            if not dense:
+                ell = torch.max(term1 + term2)
+                L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+                q.mul_(1 - lr / L[i] * (term1 - term2))
+            else:
+                ell = norm_lower_bound_spd(term1 + term2, tape.randn(32, q.shape[1], q))
+                L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+                q.sub_(lr / L[i] * (term1 - term2) @ q)
+        return None
+    fit_p = dQ in ("PRO4P", "QUAD4P")
+    H = _damped(G, damping, tape)
+    Pg = apply_all_factors(Q, H) if fit_p else precond_grad_kron(Q, H)
+
+    def term2_of(i, q, dense):
+        return numel / (q.shape[0] if dense else q.numel()), True
+    if dQ == "QEQ":  # psgd.py:367-391
+        _factor_loop(Q, L, Pg, term2_of, tape, lr, betaL, _E_right, _mul_diag)
+    elif dQ in ("Q0.5EQ1.5", "Q0p5EQ1p5"):  # psgd.py:394-419
+        _factor_loop(Q, L, Pg, term2_of, tape, lr, betaL, _E_left, _mul_diag,
+                     after_dense=lambda q: procrustes_step2(q, tape.randn(32, q.shape[1], q)))
+    elif dQ == "PRO4P":  # psgd.py:422-452
+        _factor_loop(Q, L, Pg, term2_of, tape, lr, betaL, _E_left, _mul_diag, after_dense=_pro4p_after(tape))
+    elif dQ == "QUAD":  # psgd.py:455-482
+        _factor_loop(Q, L, Pg, term2_of, tape, lr, betaL, _quad_dense(True), _quad_diag(True))
+    elif dQ == "QUAD4P":  # psgd.py:485-513
+        _factor_loop(Q, L, Pg, term2_of, tape, lr, betaL, _quad_dense(False), _quad_diag(False))
+    else:
+        raise ValueError(dQ)
+    if tape.rand() < 0.01:
+        balance_kron_precond(Q)
+
+
+def update_precond_kron_newton(dQ, QL, V, Hvp, tape, lr=0.1, betaL=0.9, damping=1e-9):
+    """update_precond_kron_newton_{eq,qep,qeq,q0p5eq1p5,pro4p,quad,quad4p} (psgd.py:657-829), in place on Q, L."""
+    Q, L = QL
+    if dQ == "EQ":  # psgd.py:657-662
+        return update_precond_kron_eq(QL, V, _damped(Hvp, damping, tape), tape, lr=lr, betaL=betaL)
+    if dQ == "QEP":  # psgd.py:665-689
+        balance_kron_precond(Q)
+        Ph = precond_grad_kron(Q, _damped(Hvp, damping, tape))
+        for i, q in enumerate(Q):
+            dense = q.dim() >= 2
+            term1 = _gram(_mode_apply(q, Ph, i, transpose=False), i, dense)
+            term2 = _gram(_mode_apply(q, V, i, transpose=False), i, dense)
+            if not dense:
+                ell = torch.max(term1 + term2)
+                L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+                q.mul_(1 - lr / L[i] * (term1 - term2))
+            else:
+                ell = norm_lower_bound_spd(term1 + term2, tape.randn(32, q.shape[1], q))
+                L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
+                q.sub_(lr / L[i] * (term1 - term2) @ q)
+        return None
+    fit_p = dQ in ("PRO4P", "QUAD4P")
+    H = _damped(Hvp, damping, tape)
+    Ph = apply_all_factors(Q, H) if fit_p else precond_grad_kron(Q, H)
+
+    def term2_of(i, q, dense):
+        return _gram(V, i, dense), False
+    if dQ == "QEQ":  # psgd.py:692-716
+        _factor_loop(Q, L, Ph, term2_of, tape, lr, betaL, _E_right, _mul_diag)
+    elif dQ in ("Q0.5EQ1.5", "Q0p5EQ1p5"):  # psgd.py:719-741
+        _factor_loop(Q, L, Ph, term2_of, tape, lr, betaL, _E_left, _mul_diag,
+                     after_dense=lambda q: procrustes_step2(q, tape.randn(32, q.shape[1], q)))
+    elif dQ == "PRO4P":  # psgd.py:744-771
+        _factor_loop(Q, L, Ph, term2_of, tape, lr, betaL, _E_left, _mul_diag, after_dense=_pro4p_after(tape))
+    elif dQ == "QUAD":  # psgd.py:774-799
+        _factor_loop(Q, L, Ph, term2_of, tape, lr, betaL, _quad_dense(True), _quad_diag(True))
+    elif dQ == "QUAD4P":  # psgd.py:802-829
+        _factor_loop(Q, L, Ph, term2_of, tape, lr, betaL, _quad_dense(False), _quad_diag(False))
+    else:
+        raise ValueError(dQ)
+    if tape.rand() < 0.01:
+        balance_kron_precond(Q)
+
+
+def precond_grad_kron_dq(dQ, Q, G):
+    """What KronWhiten/KronNewton apply (psgd.py:573, 581): exprA(*Q, G) when P is fitted directly, else exprP."""
+    return apply_all_factors(Q, G) if dQ in ("PRO4P", "QUAD4P") else precond_grad_kron(Q, G)
+
+
+# --------------------------------------------------------------------------------------
 # LRA (psgd.py:987-1072)
 # --------------------------------------------------------------------------------------
 def IpUVtmatvec(U, V, x):

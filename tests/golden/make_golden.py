@@ -150,6 +150,77 @@ def kwns4_case(name, shape, pdtype, steps=5, **kw):
     return worst
 
 
+DQ_FUNCS = {"EQ": "eq", "QEP": "qep", "QEQ": "qeq", "Q0.5EQ1.5": "q0p5eq1p5", "PRO4P": "pro4p", "QUAD": "quad", "QUAD4P": "quad4p"}
+
+
+def spd_pair(shape, dtype, gen_seed):
+    """(V, Hvp) with Hvp = H_L V H_R for SPD H_L, H_R: a Hessian-vector-product pair for the Newton-type updates."""
+    g = torch.Generator().manual_seed(gen_seed)
+    V = torch.randn(*shape, generator=g)
+    if len(shape) == 2:
+        m, n = shape
+        WL = torch.randn(m, m, generator=g) / m ** 0.5
+        WR = torch.randn(n, n, generator=g) / n ** 0.5
+        H = (WL @ WL.T + 0.3 * torch.eye(m)) @ V @ (WR @ WR.T + 0.3 * torch.eye(n))
+    else:
+        d = 0.3 + torch.rand(*shape, generator=g)
+        H = d * V
+    return V.to(dtype), (0.5 * H).to(dtype)
+
+
+def geom_cases(dq):
+    """All golden cases of one geometry: whitening and Newton-pair updates by the unmodified reference (psgd.py:330-513,
+    657-829), with the oracle run side by side in record mode on the same seed (its NoiseTape is stored for replay)."""
+    f32, bf16 = torch.float32, torch.bfloat16
+    fn = DQ_FUNCS[dq]
+    specs = [("whiten", (24, 40), f32, 3), ("whiten", (8, 300), f32, 3), ("whiten", (300, 8), f32, 2), ("whiten", (50,), f32, 3),
+             ("whiten", (136, 200), f32, 2), ("newton", (24, 40), f32, 3), ("newton", (8, 300), f32, 2)]
+    if dq not in ("PRO4P",):
+        specs += [("whiten", (24, 40), bf16, 3), ("whiten", (136, 200), bf16, 2), ("newton", (24, 40), bf16, 2)]
+    if dq == "Q0.5EQ1.5":
+        specs = [s for s in specs if s[0] == "newton"]  # the whitening form has its own fixtures (kron_*.pt)
+    out = []
+    for (mode, shape, dtype, steps) in specs:
+        t0 = torch.zeros(*shape, dtype=dtype)
+        QL_ref, exprs = ref.init_kron(t0, Scale=1.0, max_size=float("inf"), max_skew=1.0, dQ=dq)
+        QL_o = orc.init_kron_dq(t0, Scale=1.0, dQ=dq)
+        lr = 0.5 if dq not in ("PRO4P", "QUAD4P") else 0.2
+        case = {"dQ": dq, "mode": mode, "shape": list(shape), "dtype": str(dtype), "lr": lr, "betaL": 0.9, "damping": 1e-9,
+                "Q0": [q.clone() for q in QL_ref[0]], "steps": []}
+        worst = 0.0
+        for s in range(steps):
+            seed = 777 + 13 * s
+            if mode == "whiten":
+                G = structured_grad(shape, dtype, 5000 + s)
+                torch.manual_seed(seed)
+                getattr(ref, f"update_precond_kron_whiten_{fn}")(QL_ref, exprs, G, lr=lr, betaL=0.9, damping=1e-9)
+                torch.manual_seed(seed)
+                tape = orc.NoiseTape()
+                orc.update_precond_kron_whiten(dq, QL_o, G, tape, lr=lr, betaL=0.9, damping=1e-9)
+                inputs = {"G": G}
+            else:
+                V, Hvp = spd_pair(shape, dtype, 6000 + s)
+                torch.manual_seed(seed)
+                getattr(ref, f"update_precond_kron_newton_{fn}")(QL_ref, exprs, V, Hvp, lr=lr, betaL=0.9, damping=1e-9)
+                torch.manual_seed(seed)
+                tape = orc.NoiseTape()
+                orc.update_precond_kron_newton(dq, QL_o, V, Hvp, tape, lr=lr, betaL=0.9, damping=1e-9)
+                inputs = {"V": V, "Hvp": Hvp}
+            X = structured_grad(shape, dtype, 7000 + s)
+            Pg = exprs[0](*QL_ref[0], X) if dq in ("PRO4P", "QUAD4P") else ref.precond_grad_kron(QL_ref, exprs, X)
+            Pg_o = orc.precond_grad_kron_dq(dq, QL_o[0], X)
+            for a, b in zip(list(QL_ref[0]) + [Pg], list(QL_o[0]) + [Pg_o]):
+                worst = max(worst, float((a.float() - b.float()).norm() / a.float().norm()))
+            for a, b in zip(QL_ref[1], QL_o[1]):
+                worst = max(worst, float((a - b).abs() / a.abs()))
+            case["steps"].append({**inputs, "seed": seed, "tape": list(tape.items), "X": X, "Q": [q.clone() for q in QL_ref[0]],
+                                  "L": [l.clone() for l in QL_ref[1]], "Pg": Pg.clone()})
+        print(f"geom {dq:10s} {mode:6s} shape={tuple(shape)} {dtype}: oracle-vs-reference worst rel err {worst:.3e}")
+        case["oracle_vs_reference"] = worst
+        out.append(case)
+    torch.save(out, os.path.join(OUT, f"geom_{fn}.pt"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # deterministic reduction order
     f32, bf16 = torch.float32, torch.bfloat16
@@ -171,3 +242,5 @@ if __name__ == "__main__":
     kwns4_case("bf16", (16, 24), bf16, steps=5, lr_params=1e-2)
     kwns4_case("bf16_squeeze", (1, 12, 1, 20), bf16, steps=4, lr_params=1e-2, momentum=0.0, whiten_grad=True,
                weight_decay=0.0, update_preconditioner_first=False)
+    for dq in DQ_FUNCS:
+        geom_cases(dq)

@@ -16,6 +16,7 @@ TOL = {"torch.float32": 5e-6, "torch.bfloat16": 3e-2}
 KRON = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "kron_*.pt")))
 LRA = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "lra_*.pt")))
 KWNS4 = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "kwns4_*.pt")))
+GEOM = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "geom_*.pt")))
 
 
 def test_fixtures_present():
@@ -68,6 +69,34 @@ def test_kwns4_oracle_matches_reference(fname):
         orc.kwns4_param_step(p, st["grad"].clone(), state, st["noise"], preconditioner_dtype=pdtype,
                              do_update=st["do_update"], **kw)
         assert relerr(p, st["p"]) < (1e-6 if pdtype == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("fname", GEOM)
+def test_geometry_oracle_matches_reference(fname):
+    """The other Kron geometries and the Newton-pair updates: the oracle replays the stored NoiseTape."""
+    torch.set_num_threads(1)
+    cases = load_golden(fname)
+    assert len(cases) >= 3
+    for case in cases:
+        tol = TOL[case["dtype"]]
+        if case["dQ"] == "PRO4P":
+            tol *= 10   # the procrustes_step3 loop amplifies contraction-order rounding (1.2e-5 measured when the fixtures were made)
+        dq = case["dQ"]
+        Q = [q.clone() for q in case["Q0"]]
+        L = [torch.zeros([], dtype=torch.float32) for _ in Q]
+        for st in case["steps"]:
+            tape = orc.NoiseTape(st["tape"])
+            if case["mode"] == "whiten":
+                orc.update_precond_kron_whiten(dq, [Q, L], st["G"], tape, lr=case["lr"], betaL=case["betaL"], damping=case["damping"])
+            else:
+                orc.update_precond_kron_newton(dq, [Q, L], st["V"], st["Hvp"], tape, lr=case["lr"], betaL=case["betaL"],
+                                               damping=case["damping"])
+            assert tape.pos == len(tape.items), "the oracle must consume exactly the draws the reference made"
+            for q, qr in zip(Q, st["Q"]):
+                assert relerr(q, qr) < tol, (dq, case["mode"], case["shape"])
+            for l, lr_ in zip(L, st["L"]):
+                assert relerr(l, lr_) < tol
+            assert relerr(orc.precond_grad_kron_dq(dq, Q, st["X"]), st["Pg"]) < tol
 
 
 def test_norm_lower_bound_is_a_lower_bound():
