@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libpsgd_b200.so")
 
 PSGD_BF16, PSGD_F32 = 0, 1
 PSGD_DIAG, PSGD_DENSE = 0, 1
+# psgd_dq_t / stage bits of psgd_kron_update
+DQ_CODES = {"Q0.5EQ1.5": 0, "Q0p5EQ1p5": 0, "EQ": 1, "QEP": 2, "QEQ": 3, "QUAD": 4, "QUAD4P": 5, "PRO4P": 6}
+STAGE_PREPARE, STAGE_FACTOR_L, STAGE_FACTOR_R, STAGE_BALANCE = 1, 2, 4, 8
 
 _DTYPES = {torch.bfloat16: PSGD_BF16, torch.float32: PSGD_F32}
 
@@ -52,6 +55,12 @@ SYMBOLS = {
     "psgd_kron_whiten_q0p5eq1p5_update": (_i, [_vp, C.POINTER(KronT), _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),
     "psgd_kron_precond_grad": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _vp, _sz, _vp]),
     "psgd_kron_balance": (_i, [_vp, C.POINTER(KronT), _vp, _sz, _vp]),
+    "psgd_kron_update_workspace_bytes": (_sz, [_vp, C.POINTER(KronT), _i]),
+    "psgd_kron_update": (_i, [_vp, C.POINTER(KronT), _i, _vp, _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),
+    "psgd_kron_apply_factors": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "psgd_kron_solve_factors": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _sz, _vp]),
+    "psgd_procrustes_step3": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _sz, _vp]),
+    "psgd_symmetry_gap": (_i, [_vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "psgd_helper_workspace_bytes": (_sz, [_vp, _i, _i]),
     "psgd_norm_lower_bound_spd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "psgd_norm_lower_bound_skh": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -19,8 +19,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-DPSGD_NO_FAST_MATH"]
 
 
-def _headers():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl"))]
+# headers each translation unit includes (directly or through common.cuh); the public header reaches all of them
+DEPS = {"api.cu": ["common.cuh", "kron_kernels.cuh", "kron_geom.cuh"], "gemm_simt.cu": ["common.cuh"], "gemm_tc.cu": ["common.cuh"],
+        "lra.cu": ["common.cuh", "lra_mma.cuh"]}
+
+
+def _headers(src):
+    deps = [os.path.join(CSRC, f) for f in DEPS.get(src, [f for f in os.listdir(CSRC) if f.endswith(".cuh")])]
     deps.append(os.path.join(HERE, "..", "include", "psgd_b200.h"))
     return [d for d in deps if os.path.exists(d)]
 
@@ -35,13 +40,12 @@ def _newer(target, deps):
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    hdrs = _headers()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     jobs = []
     for s in srcs:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJ, s[:-3] + ".o")
-        if force or _newer(obj, [src] + hdrs):
+        if force or _newer(obj, [src] + _headers(s)):
             jobs.append((src, obj))
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
     if not jobs and not _newer(LIB, objs):

@@ -400,6 +400,8 @@ static int run_balance(Ctx* ctx, const psgd_kron_t* k, KronWs& w, cudaStream_t s
   return PSGD_OK;
 }
 
+#include "kron_geom.cuh"
+
 }  // namespace psgd
 
 using namespace psgd;
@@ -635,7 +637,7 @@ int psgd_kron_balance(psgd_handle_t h, const psgd_kron_t* k, void* workspace, si
 
 // ------------------------------- helpers exposed like the reference exposes them -------------------------------
 struct HelperWs {
-  float* row_sumsq; float* nf; FactorWs f; void* R; void* RQ; void* RRQ; void* Qn; void* Va; void* Vb;
+  float* row_sumsq; float* nf; FactorWs f; void* R; void* RQ; void* RRQ; void* RRRQ; void* Qn; void* Va; void* Vb;
   char* zero_begin; size_t zero_bytes; size_t total;
 };
 static void layout_helper(int s, int dt, void* base, HelperWs& w) {
@@ -656,6 +658,7 @@ static void layout_helper(int s, int dt, void* base, HelperWs& w) {
   w.R = b.take((size_t)s * s * es); w.RQ = b.take((size_t)s * s * es); w.RRQ = b.take((size_t)s * s * es);
   w.Qn = b.take((size_t)s * s * es);
   w.Va = b.take((size_t)32 * s * es); w.Vb = b.take((size_t)32 * s * es);
+  w.RRRQ = b.take((size_t)s * s * es);
   w.total = b.off;
 }
 
@@ -808,6 +811,125 @@ int psgd_gemm(psgd_handle_t h, int path, int in_dtype, int out_dtype, int trans_
   int rc = launch_gemm(ctx, g, st);
   ctx->gemm_path = saved;
   return rc;
+}
+
+}  // extern "C"
+
+// ------------------------------------------- the other geometries / Newton pairs -------------------------------------------
+namespace psgd {
+// procrustes_step3 (psgd.py:127-155) on it.Qn -> writes it.q
+static int run_procrustes3(Ctx* ctx, int dt, DenseItem& it, void* RRRQ, float max_step, cudaStream_t st) {
+  const int s = it.s;
+  dim3 grid((s + 63) / 64, (s + 63) / 64);
+  DISPATCH_T(dt, (k_skew<T><<<grid, 256, 0, st>>>((const T*)it.Qn, (T*)it.T, s, it.f->r_abs_max, it.f->r_row_sumsq)));
+  LAUNCH_CHECK(ctx, "k_skew");
+  BoundJob jb{it.T, s, it.v_skh, it.f->r_row_sumsq, it.f->r_abs_max, &it.f->b_skh, it.Va, it.Vb};
+  BoundFinish fin{1, 0.f, 0.f, 0.f, nullptr, it.f->fs};
+  int rc = run_bounds(ctx, dt, &jb, 1, &fin, st); if (rc) return rc;
+  const void* src[3] = {it.Qn, it.RQ, it.RRQ};
+  void* dst[3] = {it.RQ, it.RRQ, RRRQ};
+  const int tr[3] = {FS_TR1, FS_TR2, FS_TR3};
+  for (int j = 0; j < 3; ++j) {   // RQ = R Q / |R|, RRQ = R RQ / |R|, RRRQ = R RRQ / |R|
+    GemmDesc g = gemm_desc(dt, it.T, s, 0, src[j], s, 0, s, s, s, dst[j], s);
+    g.epi.alpha_ptr = it.f->fs + FS_INV_SR; g.epi.trace = it.f->fs + tr[j];
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  }
+  const size_t numel = (size_t)s * s;
+  DISPATCH_T(dt, (k_procrustes3_finish<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)it.Qn, (const T*)it.RQ, (const T*)it.RRQ, (const T*)RRRQ,
+                                                                                  (T*)it.q, numel, it.f->fs, max_step)));
+  LAUNCH_CHECK(ctx, "k_procrustes3_finish");
+  return PSGD_OK;
+}
+}  // namespace psgd
+
+extern "C" {
+
+size_t psgd_kron_update_workspace_bytes(psgd_handle_t, const psgd_kron_t* k, int dq) {
+  if (validate_kron(k) || dq < 0 || dq > PSGD_DQ_PRO4P) return 0;
+  GeomWs g;
+  layout_geom(k, dq, nullptr, g);
+  return g.total;
+}
+
+int psgd_kron_update(psgd_handle_t h, const psgd_kron_t* k, int dq, const void* X, const void* V, float lr, float betaL, float damping,
+                     const psgd_kron_noise_t* noise, int stages, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !noise || dq < 0 || dq > PSGD_DQ_PRO4P) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_kron(k); if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GeomWs g;
+  layout_geom(k, dq, workspace, g);
+  if (!workspace || workspace_bytes < g.total) return PSGD_ERR_WORKSPACE;
+  if (stages & PSGD_STAGE_PREPARE) {
+    if (!X || (!noise->N && !V)) return PSGD_ERR_INVALID_ARG;
+    rc = geom_prepare(ctx, k, dq, X, V, damping, noise, g, st); if (rc) return rc;
+  }
+  // `newton` must be told to the factor stages too: a staged caller passes V (any non-null pointer) to every stage
+  const bool newton = V != nullptr;
+  if (stages & PSGD_STAGE_FACTOR_L) { rc = geom_factor(ctx, k, dq, newton, 0, lr, betaL, noise, g, st); if (rc) return rc; }
+  if ((stages & PSGD_STAGE_FACTOR_R) && k->has_r) { rc = geom_factor(ctx, k, dq, newton, 1, lr, betaL, noise, g, st); if (rc) return rc; }
+  if (stages & PSGD_STAGE_BALANCE) { rc = run_balance(ctx, k, g.k, st); if (rc) return rc; }
+  return PSGD_OK;
+}
+
+int psgd_kron_apply_factors(psgd_handle_t h, const psgd_kron_t* k, const void* X, void* out, float* sumsq_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !X || !out) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_kron(k); if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GeomWs g;
+  layout_geom(k, PSGD_DQ_QUAD4P, workspace, g);
+  if (!workspace || workspace_bytes < g.total) return PSGD_ERR_WORKSPACE;
+  if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4, st), "memset"); if (rc) return rc; }
+  return run_apply_factors(ctx, k, g, X, out, nullptr, nullptr, sumsq_out, st);
+}
+
+int psgd_kron_solve_factors(psgd_handle_t h, const psgd_kron_t* k, const void* V, void* out, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !V || !out) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_kron(k); if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GeomWs g;
+  layout_geom(k, PSGD_DQ_EQ, workspace, g);
+  if (!workspace || workspace_bytes < g.total) return PSGD_ERR_WORKSPACE;
+  if (k->kind_l == PSGD_DENSE) { rc = run_tri_inverse(ctx, k->dtype, k->QL, k->m, g.tri[0], st); if (rc) return rc; }
+  if (k->has_r && k->kind_r == PSGD_DENSE) { rc = run_tri_inverse(ctx, k->dtype, k->QR, k->n, g.tri[1], st); if (rc) return rc; }
+  return run_inverse_apply(ctx, k, g, V, out, nullptr, nullptr, st);
+}
+
+int psgd_procrustes_step3(psgd_handle_t h, int dt, void* Q, int s, const void* V0, float max_step_size, void* workspace, size_t wsb,
+                          void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !Q || !V0 || s < 1) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HelperWs w;
+  layout_helper(s, dt, workspace, w);
+  if (!workspace || wsb < w.total) return PSGD_ERR_WORKSPACE;
+  int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+  rc = check_cuda(ctx, cudaMemcpyAsync(w.Qn, Q, (size_t)s * s * dtype_size(dt), cudaMemcpyDeviceToDevice, st), "memcpy"); if (rc) return rc;
+  DenseItem it;
+  it.s = s; it.q = Q; it.L = nullptr; it.t2 = 0.f; it.T = w.R; it.Qn = w.Qn; it.RQ = w.RQ; it.RRQ = w.RRQ; it.Va = w.Va; it.Vb = w.Vb;
+  it.v_spd = nullptr; it.v_skh = V0; it.f = &w.f;
+  return run_procrustes3(ctx, dt, it, w.RRRQ, max_step_size, st);
+}
+
+int psgd_symmetry_gap(psgd_handle_t h, int dt, const void* Q, int s, float* out2, void* workspace, size_t wsb, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !Q || !out2 || s < 1) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HelperWs w;
+  layout_helper(s, dt, workspace, w);
+  if (!workspace || wsb < w.total) return PSGD_ERR_WORKSPACE;
+  int rc = check_cuda(ctx, cudaMemsetAsync(out2, 0, 8, st), "memset"); if (rc) return rc;
+  dim3 grid((s + 63) / 64, (s + 63) / 64);
+  DISPATCH_T(dt, (k_skew<T><<<grid, 256, 0, st>>>((const T*)Q, (T*)w.R, s, out2, nullptr)));
+  LAUNCH_CHECK(ctx, "k_skew");
+  const size_t numel = (size_t)s * s;
+  DISPATCH_T(dt, (k_absmax<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)Q, numel, out2 + 1)));
+  LAUNCH_CHECK(ctx, "k_absmax");
+  return PSGD_OK;
 }
 
 }  // extern "C"

@@ -9,7 +9,7 @@ namespace psgd {
 // slots of the per-bound scalar block (floats)
 enum { SC_INV_NF = 0, SC_NF = 1, SC_J = 2, SC_BOUND = 3, SC_COUNT = 8 };
 // slots of the per-factor update scalars
-enum { FS_ALPHA = 0, FS_BETA = 1, FS_INV_SR = 2, FS_TR1 = 3, FS_TR2 = 4, FS_COUNT = 8 };
+enum { FS_ALPHA = 0, FS_BETA = 1, FS_INV_SR = 2, FS_TR1 = 3, FS_TR2 = 4, FS_TR3 = 5, FS_COUNT = 8 };
 
 // 8 bf16 <-> 8 floats through one 16-byte access
 __device__ __forceinline__ void ld8(const bf16* p, float* x) {
@@ -74,7 +74,7 @@ __global__ void k_scale2d(const T* __restrict__ X, T* __restrict__ out, int m, i
     int r = (int)(i / n), c = (int)(i % n);
     float v = to_f<T>(X[i]) * (rs ? rs[r] : 1.f) * (cs ? cs[c] : 1.f);
     T o = from_f<T>(v);
-    out[i] = o;
+    if (out) out[i] = o;     // out == nullptr: reductions only (sums of squares of X itself)
     float f = to_f<T>(o);
     tot += f * f;
     if (row_sumsq) atomicAdd(&row_sumsq[r], f * f);
@@ -423,6 +423,174 @@ __global__ void k_kwns4_tail(TP* __restrict__ p, TQ* __restrict__ h, size_t nume
     v = fminf(fmaxf(v, -max_elem_amp), max_elem_amp);
     h[i] = from_f<TQ>(v);
     p[i] = from_f<TP>(to_f<TP>(p[i]) - lr_params * v);
+  }
+}
+
+// ------------------------------ the other Kron geometries (psgd.py:278-391, 422-513, 657-829) ------------------------------
+// out[i] = float(q[i]) (op 0) or 1 / float(q[i]) (op 1): fp32 row / column factors for the GEMM epilogue (exprA with a diagonal factor,
+// psgd.py:248-249; conjB / q, psgd.py:300)
+template <typename T>
+__global__ void k_vec_to_f32(const T* __restrict__ q, float* __restrict__ out, int n, int op) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float v = to_f<T>(q[i]); out[i] = op == 1 ? 1.f / v : v; }
+}
+
+// S = T1 + T2 (rounded; row sums of squares and max diagonal fused: the inputs of norm_lower_bound_spd(term1 + term2), psgd.py:315 / 363 /
+// 688 ...) and E = T1 - T2 (rounded; upper triangle only when triu: psgd.py:316).  S overwrites T1 and E overwrites T2.
+// grid.x = s (one row per block)
+template <typename T>
+__global__ void __launch_bounds__(256) k_combine_terms(T* __restrict__ T1, T* __restrict__ T2, int s, int triu, float* row_sumsq, float* diag_max) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < s; j += blockDim.x) {
+    const size_t idx = (size_t)i * s + j;
+    const float a = to_f<T>(T1[idx]), b = to_f<T>(T2[idx]);
+    const T sm = from_f<T>(a + b);
+    const float f = to_f<T>(sm);
+    T1[idx] = sm;
+    T2[idx] = (triu && j < i) ? from_f<T>(0.f) : from_f<T>(a - b);
+    ss = fmaf(f, f, ss);
+    if (j == i && diag_max) atomic_max_nonneg(diag_max, f);
+  }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0 && row_sumsq) row_sumsq[i] = ss;
+}
+
+// Q = (P + P^T) / 2    psgd.py:479 / 509 / 794 / 824.  grid (ceil(s/32), ceil(s/32)), block (32, 8)
+template <typename T>
+__global__ void k_symmetrize(const T* __restrict__ P, T* __restrict__ Q, int s) {
+  __shared__ float tA[32][33];   // P[i0 + y][j0 + x]
+  __shared__ float tB[32][33];   // P[j0 + y][i0 + x]
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int x = threadIdx.x;
+    tA[y][x] = (i0 + y < s && j0 + x < s) ? to_f<T>(P[(size_t)(i0 + y) * s + j0 + x]) : 0.f;
+    tB[y][x] = (j0 + y < s && i0 + x < s) ? to_f<T>(P[(size_t)(j0 + y) * s + i0 + x]) : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int x = threadIdx.x;
+    if (i0 + y < s && j0 + x < s) Q[(size_t)(i0 + y) * s + j0 + x] = from_f<T>(to_f<T>(from_f<T>(tA[y][x] + tB[x][y])) * 0.5f);
+  }
+}
+
+// diagonal factor, every geometry: term1 = t1[i] * (t1_q2 ? q_i^2 : 1), term2 = (t2v ? t2v[i] : t2s) * (t2_q2 ? q_i^2 : 1);
+// ell = max(term1 + term2); L = max(betaL L + (1 - betaL) ell, ell); c = lr / L;
+// quad == 0: q *= 1 - c (term1 - term2)   (psgd.py:312, 359, 383, 410, 437 ...);  quad == 1: q *= (1 - c (term1 - term2))^2  (psgd.py:471, 501)
+template <typename T>
+__global__ void k_diag_update_gen(T* __restrict__ q, const float* __restrict__ t1, const float* __restrict__ t2v, float t2s, int t1_q2, int t2_q2,
+                                  int s, float lr, float betaL, float* L, int quad) {
+  __shared__ float red[32];
+  __shared__ float c_s;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) {
+    const float qv = to_f<T>(q[i]);
+    const float q2 = to_f<T>(from_f<T>(qv * qv));
+    const float a = to_f<T>(from_f<T>(t1[i] * (t1_q2 ? q2 : 1.f)));
+    const float b = to_f<T>(from_f<T>((t2v ? t2v[i] : t2s) * (t2_q2 ? q2 : 1.f)));
+    mx = fmaxf(mx, to_f<T>(from_f<T>(a + b)));
+  }
+  mx = block_max(mx, red);
+  if (threadIdx.x == 0) {
+    const float ell = mx;
+    const float Ln = fmaxf(betaL * (*L) + (1.f - betaL) * ell, ell);
+    *L = Ln;
+    c_s = lr / Ln;
+  }
+  __syncthreads();
+  const float c = c_s;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) {
+    const float qv = to_f<T>(q[i]);
+    const float q2 = to_f<T>(from_f<T>(qv * qv));
+    const float a = to_f<T>(from_f<T>(t1[i] * (t1_q2 ? q2 : 1.f)));
+    const float b = to_f<T>(from_f<T>((t2v ? t2v[i] : t2s) * (t2_q2 ? q2 : 1.f)));
+    const float gain = 1.f - c * (a - b);
+    q[i] = from_f<T>(qv * (quad ? gain * gain : gain));
+  }
+}
+
+// Inverse of the upper-triangular diagonal blocks of Q (leaf of the blocked inversion behind the triangular solves of psgd.py:288-303).
+// One CTA of TRI_NB threads per TRI_NB x TRI_NB block, in place in shared memory: rows are processed bottom-up, thread j owns column j:
+//   X[i][j] = (delta_ij - sum_{k=i+1..j} U[i][k] X[k][j]) / U[i][i].
+// Output: fp32 (Xf) or a bf16 hi/lo split (Xhi + Xlo carries ~16 mantissa bits), both s x s row-major, only the diagonal blocks written.
+constexpr int TRI_NB = 128;
+template <typename T>
+__global__ void __launch_bounds__(TRI_NB) k_tri_inv_leaf(const T* __restrict__ Q, int s, float* __restrict__ Xf, bf16* __restrict__ Xhi,
+                                                         bf16* __restrict__ Xlo) {
+  extern __shared__ float tri_sm[];
+  float* X = tri_sm;                              // TRI_NB x (TRI_NB + 1)
+  float* ur = tri_sm + TRI_NB * (TRI_NB + 1);     // current row of U
+  const int o = blockIdx.x * TRI_NB;
+  const int nb = min(TRI_NB, s - o);
+  const int j = threadIdx.x;
+  for (int i = nb - 1; i >= 0; --i) {
+    ur[j] = (j < nb && j >= i) ? to_f<T>(Q[(size_t)(o + i) * s + o + j]) : 0.f;
+    __syncthreads();
+    float a0 = (j == i) ? 1.f : 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (j > i && j < nb) {
+      int k = i + 1;
+      for (; k + 3 <= j; k += 4) {
+        a0 = fmaf(-ur[k], X[k * (TRI_NB + 1) + j], a0);
+        a1 = fmaf(-ur[k + 1], X[(k + 1) * (TRI_NB + 1) + j], a1);
+        a2 = fmaf(-ur[k + 2], X[(k + 2) * (TRI_NB + 1) + j], a2);
+        a3 = fmaf(-ur[k + 3], X[(k + 3) * (TRI_NB + 1) + j], a3);
+      }
+      for (; k <= j; ++k) a0 = fmaf(-ur[k], X[k * (TRI_NB + 1) + j], a0);
+    }
+    const float v = (j >= i && j < nb) ? ((a0 + a1) + (a2 + a3)) / ur[i] : 0.f;
+    X[i * (TRI_NB + 1) + j] = v;
+    __syncthreads();
+  }
+  for (int i = 0; i < nb; ++i) {
+    if (j < nb) {
+      const float v = X[i * (TRI_NB + 1) + j];
+      const size_t idx = (size_t)(o + i) * s + o + j;
+      if (Xf) Xf[idx] = v;
+      if (Xhi) {
+        const bf16 h = __float2bfloat16_rn(v);
+        Xhi[idx] = h;
+        Xlo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+// fp32 blocks -> bf16 hi / lo splits, batched over the pairs of one level of the blocked inversion.
+// pair p: src = src0 + p * src_stride (rows x cols(p), ld src_ld), dst = hi0/lo0 + p * dst_stride (ld dst_ld);
+// cols(p) = min(b, s - (2 p b + b)).  grid (ceil(rows*b / 256), pairs)
+__global__ void k_split_hilo(const float* __restrict__ src0, size_t src_stride, int src_ld, bf16* __restrict__ hi0, bf16* __restrict__ lo0,
+                             size_t dst_stride, int dst_ld, int rows, int b, int s) {
+  const int p = blockIdx.y;
+  const int cols = min(b, s - (2 * p * b + b));
+  const float* src = src0 + (size_t)p * src_stride;
+  bf16* hi = hi0 + (size_t)p * dst_stride;
+  bf16* lo = lo0 + (size_t)p * dst_stride;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = e / b, c = e % b;
+  if (r < rows && c < cols) {
+    const float v = src[(size_t)r * src_ld + c];
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[(size_t)r * dst_ld + c] = h;
+    lo[(size_t)r * dst_ld + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// procrustes_step3 finish (psgd.py:149-155): if tr_RQ > 0 and tr_RRRQ < 0:
+//   a = min((-tr2 - sqrt(tr2^2 - 1.5 tr1 tr3)) / (0.75 tr3), max_step);  Q = Qn + a (RQ + 0.5 a (RRQ + 0.25 a RRRQ));  else Q = Qn
+template <typename T>
+__global__ void k_procrustes3_finish(const T* __restrict__ Qn, const T* __restrict__ RQ, const T* __restrict__ RRQ, const T* __restrict__ RRRQ,
+                                     T* __restrict__ Q, size_t numel, const float* __restrict__ fs, float max_step) {
+  const float tr1 = fs[FS_TR1], tr2 = fs[FS_TR2], tr3 = fs[FS_TR3];
+  const bool go = tr1 > 0.f && tr3 < 0.f;
+  float a = 0.f;
+  if (go) a = fminf((-tr2 - sqrtf(tr2 * tr2 - 1.5f * tr1 * tr3)) / (0.75f * tr3), max_step);
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride) {
+    float v = to_f<T>(Qn[i]);
+    if (go) v += a * (to_f<T>(RQ[i]) + 0.5f * a * (to_f<T>(RRQ[i]) + 0.25f * a * to_f<T>(RRRQ[i])));
+    Q[i] = from_f<T>(v);
   }
 }
 

@@ -10,6 +10,9 @@ Same names, argument meaning, defaults, in-place state mutation and RNG consumpt
     procrustes_step2                        psgd.py:101-124   -> psgd_procrustes_step2
     balance_kron_precond                    psgd.py:266-275   -> psgd_kron_balance
     update_precond_lra / _lra_whiten        psgd.py:994-1072  -> psgd_lra_update / psgd_lra_whiten_update
+    update_precond_kron_whiten_{eq,qep,qeq,pro4p,quad,quad4p}            psgd.py:330-513  -> psgd_kron_update
+    update_precond_kron_eq, update_precond_kron_newton_{eq,...,quad4p}   psgd.py:278-319, 657-829 -> psgd_kron_update
+    procrustes_step3                        psgd.py:127-155   -> psgd_procrustes_step3
     precond_grad_lra                        psgd.py:1055-1063 -> psgd_lra_precond_grad
 
 All tensors must live on a B200 (sm_100a) device; there is no CPU / PyTorch fallback.  Random numbers are drawn
@@ -69,30 +72,76 @@ class _ExprG:
         return torch.sum(X * Y, dim=1 - self.i)
 
 
+class _ExprA:
+    """exprA(*Q, G) -> every factor applied once, Q_L G Q_R^T for a matrix (psgd.py:248-249). What KronWhiten / KronNewton use as the
+    preconditioning step when P is fitted directly (psgd.py:573, 908)."""
+
+    def __init__(self, order):
+        self.order = order
+
+    def __call__(self, *ops):
+        n = max(self.order, 1)
+        assert len(ops) == n + 1, "exprA expects (*Q, G)"
+        return _apply_factors(list(ops[:n]), ops[-1])
+
+
+class _ExprQ:
+    """exprQs[i](q, T): the i-th factor applied along dim i of T (psgd.py:225-226, 245-246)."""
+
+    def __init__(self, i, dense, order):
+        self.i, self.dense, self.order = i, dense, order
+
+    def __call__(self, q, T):
+        if not self.dense or self.order == 0:
+            shp = [1] * T.dim()
+            if T.dim() > 0:
+                shp[self.i] = -1
+            return T * q.reshape(shp)
+        if self.order == 1:
+            return gemm(q, T.reshape(-1, 1)).reshape(T.shape)
+        if self.order == 2:
+            return gemm(q, T) if self.i == 0 else gemm(T, q, trans_b=True)
+        return _mode_product(q, T, self.i, False)
+
+
 def init_kron(t, Scale=1.0, max_size=float("inf"), max_skew=1.0, dQ="Q0.5EQ1.5"):
     """psgd.py:161-263. Returns [[Q, L], exprs] with the reference's state layout: Q[i] = scale*eye(s) (dense) or
-    scale*ones(s) (diagonal, psgd.py:208) in t's dtype, L[i] = fp32 0-dim zeros, exprs = (exprP, exprGs)."""
-    if dQ not in ("Q0.5EQ1.5", "Q0p5EQ1p5"):
-        raise NotImplementedError(f"dQ={dQ!r}: only the Q0.5EQ1.5 geometry (what KWNS4 runs, ddp.py:84-86) is built; "
-                                  "the other geometries are SURVEY.md 8(f) items 1 and 3")
+    scale*ones(s) (diagonal, psgd.py:208) in t's dtype, L[i] = fp32 0-dim zeros, exprs as psgd.py:255-263 lists them per geometry."""
+    if dQ not in _lib.DQ_CODES:
+        raise AssertionError("Invalid choice for dQ")  # psgd.py:262
+    if dQ in ("QUAD4P", "PRO4P"):  # psgd.py:186-187: the two geometries that fit P directly
+        Scale = Scale ** 2
     shape = t.shape
     if len(shape) == 0:  # psgd.py:189-195
         Q = [Scale * torch.ones_like(t)]
         L = [lift2single(torch.zeros_like(t))]
-        return [[Q, L], (_ExprP(0), (_ExprG(0, False, 0),))]
+        return [[Q, L], _exprs_for(dQ, 0, (_ExprG(0, False, 0),), (_ExprQ(0, False, 0),))]
     if len(shape) > 26:
         raise ValueError(f"Got tensor with dim {len(t.shape)}; einsum runs out of letters; replace 26 with larger numbers.")
     scale = Scale ** (1 / len(shape))
-    Q, L, exprGs = [], [], []
+    Q, L, exprGs, exprQs = [], [], [], []
     for i, size in enumerate(shape):
         L.append(lift2single(torch.zeros([], dtype=t.dtype, device=t.device)))
         if size <= 1 or size > max_size or size ** 2 > max_skew * t.numel():
             Q.append(scale * torch.ones(size, dtype=t.dtype, device=t.device))
             exprGs.append(_ExprG(i, False, len(shape)))
+            exprQs.append(_ExprQ(i, False, len(shape)))
         else:
             Q.append(scale * torch.eye(size, dtype=t.dtype, device=t.device))
             exprGs.append(_ExprG(i, True, len(shape)))
-    return [[Q, L], (_ExprP(len(shape)), tuple(exprGs))]
+            exprQs.append(_ExprQ(i, True, len(shape)))
+    return [[Q, L], _exprs_for(dQ, len(shape), tuple(exprGs), tuple(exprQs))]
+
+
+def _exprs_for(dQ, order, exprGs, exprQs):
+    """psgd.py:255-263: which expressions each geometry carries."""
+    if dQ == "QEP":
+        return (_ExprP(order), exprGs, exprQs)
+    if dQ == "EQ":
+        return (_ExprP(order), exprGs, _ExprA(order))
+    if dQ in ("QUAD4P", "PRO4P"):
+        return (_ExprA(order), exprGs)
+    return (_ExprP(order), exprGs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -431,18 +480,205 @@ precond_grad_UVd = precond_grad_lra
 
 
 # ------------------------------------------------------------------------------------------------
-# names the reference exports that are outside this round's scope: fail loudly, never silently fall back
+# The other geometries and the Newton-pair updates -> psgd_kron_update
 # ------------------------------------------------------------------------------------------------
-def _not_built(name, row):
-    def f(*a, **k):
-        raise NotImplementedError(f"{name} is not built yet ({row}); only the Q0.5EQ1.5 whitening path is served by the engine")
-    f.__name__ = name
+class NoiseTape:
+    """Random draws of one update in the reference's draw order.  Default: drawn lazily from the torch generators exactly where the
+    reference draws (randn_like(G), randn(32, s) per norm bound, the CPU coin torch.rand([])); a list of pre-drawn items replays them
+    (parity tests feed the numbers the reference consumed)."""
+
+    def __init__(self, items=None, device=None):
+        self.replay = items is not None
+        self.items = list(items) if items is not None else []
+        self.pos = 0
+        self.device = device
+
+    def _next(self, make):
+        if self.replay:
+            v = self.items[self.pos]
+            self.pos += 1
+            if isinstance(v, torch.Tensor) and self.device is not None:
+                v = v.to(self.device)
+            return v
+        v = make()
+        self.items.append(v)
+        return v
+
+    def randn_like(self, x):
+        return self._next(lambda: torch.randn_like(x))
+
+    def randn(self, k, s, like):
+        return self._next(lambda: torch.randn(k, s, dtype=like.dtype, device=like.device))
+
+    def rand(self):
+        return self._next(lambda: float(torch.rand([])))
+
+
+def _as_tape(noise, device):
+    if isinstance(noise, NoiseTape):
+        return noise
+    return NoiseTape(noise, device=device)
+
+
+def _apply_factors(Q, G, sumsq_out=None):
+    """exprA(*Q, G) on the engine (psgd_kron_apply_factors)."""
+    if not G.is_cuda:
+        raise EngineError("psgd_torch_b200 runs on CUDA (sm_100a) tensors only")
+    G = G.contiguous()
+    if G.dim() > 2:
+        X = G
+        for i, q in enumerate(Q):
+            if q.dim() == 2:
+                X = _mode_product(q, X, i, False)
+            else:
+                shp = [1] * X.dim()
+                shp[i] = -1
+                X = X * q.reshape(shp)
+        return X.contiguous()
+    k = _kron_desc(Q, None, G)
+    d = _dummy(G.device)
+    k.LL, k.LR = d.data_ptr(), d.data_ptr() + 4
+    h = _lib.handle_for(G.device)
+    lib = _lib.load_library()
+    ws = _lib.workspace(G.device, lib.psgd_kron_update_workspace_bytes(h, C.byref(k), _lib.DQ_CODES["QUAD4P"]))
+    out = torch.empty_like(G)
+    rc = lib.psgd_kron_apply_factors(h, C.byref(k), _lib.ptr(G), _lib.ptr(out), _lib.ptr(sumsq_out), _lib.ptr(ws), ws.numel(),
+                                     _lib.stream_ptr(G.device))
+    _lib.check(h, rc, "psgd_kron_apply_factors")
+    return out
+
+
+def solve_kron_factors(Q, V):
+    """conjB of psgd.py:297-303 for real tensors: kron_i(Q_i^{-T}) V with upper-triangular dense factors (fp32-accurate blocked
+    triangular inverse on the engine) and divisions for diagonal factors.  Exposed for tests."""
+    V = V.contiguous()
+    if V.dim() > 2:
+        raise NotImplementedError("triangular solves for tensors of order >= 3 are not built")
+    k = _kron_desc(Q, None, V)
+    d = _dummy(V.device)
+    k.LL, k.LR = d.data_ptr(), d.data_ptr() + 4
+    h = _lib.handle_for(V.device)
+    lib = _lib.load_library()
+    ws = _lib.workspace(V.device, lib.psgd_kron_update_workspace_bytes(h, C.byref(k), _lib.DQ_CODES["EQ"]))
+    out = torch.empty_like(V)
+    rc = lib.psgd_kron_solve_factors(h, C.byref(k), _lib.ptr(V), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(V.device))
+    _lib.check(h, rc, "psgd_kron_solve_factors")
+    return out
+
+
+def procrustes_step3(Q, max_step_size=1 / 3, V0=None):
+    """psgd.py:127-155, in place on Q (the branch of line 149 is taken on the device)."""
+    if Q.dim() != 2 or Q.shape[0] != Q.shape[1] or not Q.is_cuda or not Q.is_contiguous():
+        raise EngineError("Q must be a contiguous square CUDA matrix")
+    s = Q.shape[0]
+    if V0 is None:
+        V0 = torch.randn(_K_PROBES, s, dtype=Q.dtype, device=Q.device)  # psgd.py:87 via 142
+    h = _lib.handle_for(Q.device)
+    lib = _lib.load_library()
+    dt = _lib.dtype_code(Q)
+    # its own scratch: a staged PRO4P update keeps the Grams of the next factor in the shared workspace
+    ws = torch.empty(lib.psgd_helper_workspace_bytes(h, s, dt), dtype=torch.uint8, device=Q.device)
+    rc = lib.psgd_procrustes_step3(h, dt, _lib.ptr(Q), s, _lib.ptr(V0.contiguous()), float(max_step_size), _lib.ptr(ws), ws.numel(),
+                                   _lib.stream_ptr(Q.device))
+    _lib.check(h, rc, "psgd_procrustes_step3")
+
+
+def _almost_symmetric(q):
+    """(q.H - q).abs().amax() < 0.001 * q.abs().amax()  (psgd.py:448): two device reductions, one host read like the reference."""
+    s = q.shape[0]
+    h = _lib.handle_for(q.device)
+    lib = _lib.load_library()
+    dt = _lib.dtype_code(q)
+    ws = torch.empty(lib.psgd_helper_workspace_bytes(h, s, dt), dtype=torch.uint8, device=q.device)
+    out = torch.empty(2, dtype=torch.float32, device=q.device)
+    rc = lib.psgd_symmetry_gap(h, dt, _lib.ptr(q), s, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(q.device))
+    _lib.check(h, rc, "psgd_symmetry_gap")
+    gap, amax = out.tolist()
+    return gap < 0.001 * amax
+
+
+def _kron_update(dQ, QL, X, V, lr, betaL, damping, noise, damp=True):
+    """One update through psgd_kron_update.  Draw order = the reference's: randn_like(X) (if damped), then per dense factor the
+    norm-bound probe randn(32, s) (psgd.py:62) followed by that factor's procrustes probes (Q0.5EQ1.5: one, psgd.py:87; PRO4P: one
+    per procrustes_step3 round), finally the balancing coin (none for QEP)."""
+    Q, L = QL
+    if not X.is_cuda:
+        raise EngineError("psgd_torch_b200 runs on CUDA (sm_100a) tensors only")
+    X = X.contiguous()
+    if X.dim() > 2:
+        raise NotImplementedError(f"dQ={dQ!r} for tensors of order >= 3 is not built (SURVEY.md 8f item 3); Q0.5EQ1.5 is")
+    if V is not None:
+        V = V.contiguous()
+        if V.shape != X.shape or V.dtype != X.dtype:
+            raise EngineError("V and Hvp must agree in shape and dtype")
+    tape = _as_tape(noise, X.device)
+    code = _lib.DQ_CODES[dQ]
+    k = _kron_desc(Q, L, X)
+    nz = KronNoiseT()
+    keep = []
+    if damp:
+        N = tape.randn_like(X)
+        keep.append(N)
+        nz.N = N.data_ptr()
+    h = _lib.handle_for(X.device)
+    lib = _lib.load_library()
+    ws = _lib.workspace(X.device, lib.psgd_kron_update_workspace_bytes(h, C.byref(k), code))
+
+    def call(stages):
+        rc = lib.psgd_kron_update(h, C.byref(k), code, _lib.ptr(X), _lib.ptr(V), float(lr), float(betaL), float(damping), C.byref(nz),
+                                  stages, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(X.device))
+        _lib.check(h, rc, "psgd_kron_update")
+
+    fields = (("V0_spd_l", "V0_skh_l", _lib.STAGE_FACTOR_L), ("V0_spd_r", "V0_skh_r", _lib.STAGE_FACTOR_R))
+    staged = dQ == "PRO4P"
+    stages = _lib.STAGE_PREPARE
+    for i, q in enumerate(Q):
+        spd_f, skh_f, bit = fields[i]
+        if q.dim() == 2:
+            p = tape.randn(_K_PROBES, q.shape[1], q)
+            keep.append(p)
+            setattr(nz, spd_f, p.data_ptr())
+            if code == 0:
+                p2 = tape.randn(_K_PROBES, q.shape[1], q)
+                keep.append(p2)
+                setattr(nz, skh_f, p2.data_ptr())
+        stages |= bit
+        if staged:  # psgd.py:444-449: rotate until the factor is almost symmetric; host-side branch like the reference
+            call(stages)
+            stages = 0
+            if q.dim() == 2:
+                for _ in range(10):
+                    procrustes_step3(q, V0=tape.randn(_K_PROBES, q.shape[1], q))
+                    if _almost_symmetric(q):
+                        break
+    if dQ != "QEP" and tape.rand() < 0.01:  # psgd.py:318, 390, 418 ...
+        stages |= _lib.STAGE_BALANCE
+    if stages:
+        call(stages)
+    del keep
+
+
+def update_precond_kron_eq(QL, exprs, V, Hvp, lr=0.1, betaL=0.9, noise=None):
+    """psgd.py:278-319: the raw dQ = E*Q update with the pair (V, Hvp); no damping."""
+    _kron_update("EQ", QL, Hvp, V, lr, betaL, 0.0, noise, damp=False)
+
+
+def _whiten(dQ):
+    def f(QL, exprs, G, lr=0.1, betaL=0.9, damping=1e-9, noise=None):
+        _kron_update(dQ, QL, G, None, lr, betaL, damping, noise)
     return f
 
 
-for _n in ("eq", "qep", "qeq", "pro4p", "quad", "quad4p"):
-    globals()[f"update_precond_kron_whiten_{_n}"] = _not_built(f"update_precond_kron_whiten_{_n}", "SURVEY.md 8a K8/K9")
-for _n in ("eq", "qep", "qeq", "q0p5eq1p5", "pro4p", "quad", "quad4p"):
-    globals()[f"update_precond_kron_newton_{_n}"] = _not_built(f"update_precond_kron_newton_{_n}", "SURVEY.md 8a K10")
-update_precond_kron_eq = _not_built("update_precond_kron_eq", "SURVEY.md 8a K8")
-procrustes_step3 = _not_built("procrustes_step3", "SURVEY.md 8a K9")
+def _newton(dQ):
+    def f(QL, exprs, V, Hvp, lr=0.1, betaL=0.9, damping=1e-9, noise=None):
+        _kron_update(dQ, QL, Hvp, V, lr, betaL, damping, noise)
+    return f
+
+
+for _n, _dq in (("eq", "EQ"), ("qep", "QEP"), ("qeq", "QEQ"), ("pro4p", "PRO4P"), ("quad", "QUAD"), ("quad4p", "QUAD4P")):
+    globals()[f"update_precond_kron_whiten_{_n}"] = _whiten(_dq)       # psgd.py:330-391, 422-513
+    globals()[f"update_precond_kron_whiten_{_n}"].__name__ = f"update_precond_kron_whiten_{_n}"
+for _n, _dq in (("eq", "EQ"), ("qep", "QEP"), ("qeq", "QEQ"), ("q0p5eq1p5", "Q0.5EQ1.5"), ("pro4p", "PRO4P"), ("quad", "QUAD"),
+                ("quad4p", "QUAD4P")):
+    globals()[f"update_precond_kron_newton_{_n}"] = _newton(_dq)       # psgd.py:657-829
+    globals()[f"update_precond_kron_newton_{_n}"].__name__ = f"update_precond_kron_newton_{_n}"
