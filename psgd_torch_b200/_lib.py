@@ -79,6 +79,7 @@ SYMBOLS = {
     "psgd_debug_set_flags": (_i, [_vp, _i]),
     "psgd_debug_set_tile_n": (_i, [_vp, _i]),
     "psgd_debug_set_mn_desc": (_i, [_vp, _i, _i]),
+    "psgd_debug_read_probe": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

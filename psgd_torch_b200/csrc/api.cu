@@ -894,8 +894,11 @@ int psgd_kron_solve_factors(psgd_handle_t h, const psgd_kron_t* k, const void* V
   GeomWs g;
   layout_geom(k, PSGD_DQ_EQ, workspace, g);
   if (!workspace || workspace_bytes < g.total) return PSGD_ERR_WORKSPACE;
-  if (k->kind_l == PSGD_DENSE) { rc = run_tri_inverse(ctx, k->dtype, k->QL, k->m, g.tri[0], st); if (rc) return rc; }
-  if (k->has_r && k->kind_r == PSGD_DENSE) { rc = run_tri_inverse(ctx, k->dtype, k->QR, k->n, g.tri[1], st); if (rc) return rc; }
+  TriJob jobs[2];
+  int nj = 0;
+  if (k->kind_l == PSGD_DENSE) jobs[nj++] = TriJob{k->QL, k->m, &g.tri[0]};
+  if (k->has_r && k->kind_r == PSGD_DENSE) jobs[nj++] = TriJob{k->QR, k->n, &g.tri[1]};
+  rc = run_tri_inverse(ctx, k->dtype, jobs, nj, st); if (rc) return rc;
   return run_inverse_apply(ctx, k, g, V, out, nullptr, nullptr, st);
 }
 
@@ -933,3 +936,41 @@ int psgd_symmetry_gap(psgd_handle_t h, int dt, const void* Q, int s, float* out2
 }
 
 }  // extern "C"
+
+// ------------------------------------------- measurement aid: pure-read HBM stream -------------------------------------------
+// What a read-only sweep can reach on this part, independent of the LRA kernels' own structure (tools/read_bw_probe.py).
+template <int UNROLL, bool NOALLOC>
+__global__ void __launch_bounds__(512) k_read_probe(const uint4* __restrict__ x, size_t nvec, unsigned* out) {
+  unsigned acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + (UNROLL - 1) * stride < nvec; i += UNROLL * stride) {
+    uint4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint4* p = x + i + u * stride;
+      if (NOALLOC) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(p));
+      else v[u] = *p;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+  }
+  for (; i < nvec; i += stride) { uint4 v = x[i]; acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+  if (acc == 0x12345678u) out[0] = acc;   // keeps the loads alive
+}
+
+extern "C" int psgd_debug_read_probe(psgd_handle_t h, const void* x, size_t bytes, int blocks, int threads, int unroll, int noalloc,
+                                     void* scratch, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !x || !scratch || blocks < 1 || threads < 32 || threads > 512) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nvec = bytes / 16;
+  const uint4* p = (const uint4*)x;
+  unsigned* o = (unsigned*)scratch;
+#define PROBE(U, NA) k_read_probe<U, NA><<<blocks, threads, 0, st>>>(p, nvec, o)
+  if (noalloc) { if (unroll == 16) PROBE(16, true); else if (unroll == 8) PROBE(8, true); else if (unroll == 4) PROBE(4, true); else PROBE(1, true); }
+  else { if (unroll == 16) PROBE(16, false); else if (unroll == 8) PROBE(8, false); else if (unroll == 4) PROBE(4, false); else PROBE(1, false); }
+#undef PROBE
+  LAUNCH_CHECK(ctx, "k_read_probe");
+  return PSGD_OK;
+}

@@ -13,7 +13,7 @@
 // workspace of one generic update: the KronWs of api.cu followed by the extras below
 // ---------------------------------------------------------------------------------------------
 struct TriWs {           // blocked inversion of one upper-triangular dense factor
-  float* Xf;             // fp32 path: inverse, s x s
+  float* Xf;             // the inverse in fp32, s x s (leaves and low levels; every level for fp32 factors)
   bf16* Xhi; bf16* Xlo;  // bf16 path: hi / lo split of the inverse, s x s each
   float* Wf;             // fp32 pair temporaries (slot p at p * b * b, ld b)
   bf16* Wt; bf16* Whi; bf16* Wlo; bf16* Z2;
@@ -59,9 +59,8 @@ static void layout_geom(const psgd_kron_t* k, int dq, void* base, GeomWs& g) {
       if (k->dtype == PSGD_BF16) {
         t.Xhi = (bf16*)b.take(sd * sd * 2); t.Xlo = (bf16*)b.take(sd * sd * 2);
         t.Wt = (bf16*)b.take(half * 2); t.Whi = (bf16*)b.take(half * 2); t.Wlo = (bf16*)b.take(half * 2); t.Z2 = (bf16*)b.take(half * 2);
-      } else {
-        t.Xf = (float*)b.take(sd * sd * 4);
       }
+      t.Xf = (float*)b.take(sd * sd * 4);
       t.Wf = (float*)b.take(half * 4);
     }
   }
@@ -110,95 +109,114 @@ static int run_apply_factors(Ctx* ctx, const psgd_kron_t* k, GeomWs& gw, const v
 }
 
 // ---------------------------------------------------------------------------------------------
-// Blocked inverse of an upper-triangular factor Q (s x s): leaves of TRI_NB inverted in shared memory, then level by level
-//   inv([[A11, A12], [0, A22]]) = [[X11, -X11 A12 X22], [0, X22]]
-// as GEMMs (grouped four pairs per launch).  fp32 factors: plain fp32 products.  bf16 factors: the inverse is carried as a hi + lo pair
-// of bf16 matrices (~16 mantissa bits) so that every product runs on the bf16 tensor cores yet the solve stays well below the bf16
-// rounding the reference applies to its fp32 solve (psgd.py:291):
-//   W  = A12 X22          = A12 Xhi22 + [A12 Xlo22]_bf16                         (fp32 out, split into Whi + Wlo)
-//   X12 = -X11 W          = -(Xhi11 Whi) - [Xhi11 Wlo + [Xlo11 Whi]_bf16]_bf16   (fp32 out, split into the hi / lo storage)
+// Blocked inverse of upper-triangular factors Q (s x s): leaves of TRI_NB inverted in shared memory (k_tri_inv_leaf), then level by level
+//   inv([[A11, A12], [0, A22]]) = [[X11, -X11 A12 X22], [0, X22]].
+// Levels below TRI_TC_MIN_B (and every level of fp32 factors) run in fp32 on CUDA cores, batched over the pairs (k_tri_pair_gemm): the
+// products are tiny there and a tcgen05 launch costs 12-16 us whatever its size.  From TRI_TC_MIN_B on, bf16 factors switch to the tensor
+// cores: the inverse is carried as a hi + lo pair of bf16 matrices (~16 mantissa bits), so every product is a bf16 GEMM yet the solve
+// stays well below the bf16 rounding the reference applies to its fp32 solve (psgd.py:291):
+//   W   = A12 X22  = A12 Xhi22 + [A12 Xlo22]_bf16                         (fp32 out, split into Whi + Wlo)
+//   X12 = -X11 W   = -(Xhi11 Whi) - [Xhi11 Wlo + [Xlo11 Whi]_bf16]_bf16   (fp32 out, split into the hi / lo storage)
+// The pairs of both factors of one update share the grouped launches (four problems per launch).
 // ---------------------------------------------------------------------------------------------
-static int run_tri_inverse(Ctx* ctx, int dt, const void* Q, int s, TriWs& t, cudaStream_t st) {
-  const size_t smem = (size_t)(TRI_NB * (TRI_NB + 1) + TRI_NB) * sizeof(float);
+constexpr int TRI_TC_MIN_B = 512;
+struct TriJob { const void* Q; int s; TriWs* t; };
+
+static int run_tri_inverse(Ctx* ctx, int dt, const TriJob* jobs, int nj, cudaStream_t st) {
   static bool attr_done[2] = {false, false};
   int rc;
-  if (dt == PSGD_BF16) {
-    rc = check_cuda(ctx, cudaMemsetAsync(t.Xhi, 0, (size_t)s * s * 2, st), "memset"); if (rc) return rc;
-    rc = check_cuda(ctx, cudaMemsetAsync(t.Xlo, 0, (size_t)s * s * 2, st), "memset"); if (rc) return rc;
-    if (!attr_done[0]) { cudaFuncSetAttribute(k_tri_inv_leaf<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[0] = true; }
-    k_tri_inv_leaf<bf16><<<(s + TRI_NB - 1) / TRI_NB, TRI_NB, smem, st>>>((const bf16*)Q, s, nullptr, t.Xhi, t.Xlo);
-  } else {
+  int smax = 0;
+  for (int jx = 0; jx < nj; ++jx) {
+    const TriJob& J = jobs[jx];
+    TriWs& t = *J.t;
+    const int s = J.s;
+    if (s > smax) smax = s;
     rc = check_cuda(ctx, cudaMemsetAsync(t.Xf, 0, (size_t)s * s * 4, st), "memset"); if (rc) return rc;
-    if (!attr_done[1]) { cudaFuncSetAttribute(k_tri_inv_leaf<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[1] = true; }
-    k_tri_inv_leaf<float><<<(s + TRI_NB - 1) / TRI_NB, TRI_NB, smem, st>>>((const float*)Q, s, t.Xf, nullptr, nullptr);
+    const int ai = dt == PSGD_BF16 ? 0 : 1;
+    if (!attr_done[ai]) {
+      if (dt == PSGD_BF16) cudaFuncSetAttribute(k_tri_inv_leaf<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_LEAF_SMEM);
+      else cudaFuncSetAttribute(k_tri_inv_leaf<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_LEAF_SMEM);
+      attr_done[ai] = true;
+    }
+    DISPATCH_T(dt, (k_tri_inv_leaf<T><<<(s + TRI_NB - 1) / TRI_NB, 256, TRI_LEAF_SMEM, st>>>((const T*)J.Q, s, t.Xf)));
+    LAUNCH_CHECK(ctx, "k_tri_inv_leaf");
+    for (int b = TRI_NB; b < s && (dt == PSGD_F32 || b < TRI_TC_MIN_B); b *= 2) {
+      int pairs = 0;
+      while (2 * pairs * b + b < s) ++pairs;
+      dim3 grid((b + 63) / 64, (b + 63) / 64, pairs);
+      DISPATCH_T(dt, (k_tri_pair_gemm<T, 1><<<grid, 256, 0, st>>>((const T*)J.Q, t.Xf, t.Wf, s, b)));
+      LAUNCH_CHECK(ctx, "k_tri_pair_gemm");
+      DISPATCH_T(dt, (k_tri_pair_gemm<T, 2><<<grid, 256, 0, st>>>((const T*)J.Q, t.Xf, t.Wf, s, b)));
+      LAUNCH_CHECK(ctx, "k_tri_pair_gemm");
+    }
   }
-  LAUNCH_CHECK(ctx, "k_tri_inv_leaf");
-  const int es = dtype_size(dt);
-  const char* Qc = reinterpret_cast<const char*>(Q);
-  for (int b = TRI_NB; b < s; b *= 2) {
-    int pairs = 0;
-    while (2 * pairs * b + b < s) ++pairs;
+  if (dt == PSGD_F32) return PSGD_OK;
+  for (int jx = 0; jx < nj; ++jx) {
+    const size_t numel = (size_t)jobs[jx].s * jobs[jx].s;
+    k_split_full<<<ew_blocks(ctx, numel / 4 + 1), 256, 0, st>>>(jobs[jx].t->Xf, jobs[jx].t->Xhi, jobs[jx].t->Xlo, numel);
+    LAUNCH_CHECK(ctx, "k_split_full");
+  }
+  // ---- tensor-core levels: hi / lo products, the pairs of all factors grouped ----
+  for (int b = TRI_TC_MIN_B; b < smax; b *= 2) {
+    struct Item { const char* Q; int s; TriWs* t; int p; };
+    Item items[64];
+    int ni = 0;
+    int pairs_of[2] = {0, 0};
+    for (int jx = 0; jx < nj; ++jx) {
+      int pairs = 0;
+      while (2 * pairs * b + b < jobs[jx].s) ++pairs;
+      pairs_of[jx] = pairs;
+      for (int p = 0; p < pairs && ni < 64; ++p) items[ni++] = Item{reinterpret_cast<const char*>(jobs[jx].Q), jobs[jx].s, jobs[jx].t, p};
+    }
     const size_t slot = (size_t)b * b;
-    auto b2_of = [&](int p) { int c = s - (2 * p * b + b); return c < b ? c : b; };
-    // one "stage" = the same product for every pair of the level, four pairs per grouped launch
-    auto for_pairs = [&](auto&& make) -> int {
+    auto for_items = [&](auto&& make) -> int {
       GemmDesc gs[4];
       int ng = 0;
-      for (int p = 0; p < pairs; ++p) {
-        gs[ng++] = make(p);
-        if (ng == 4 || p + 1 == pairs) { int r = launch_gemm_group(ctx, gs, ng, st); if (r) return r; ng = 0; }
+      for (int it = 0; it < ni; ++it) {
+        gs[ng++] = make(items[it]);
+        if (ng == 4 || it + 1 == ni) { int r = launch_gemm_group(ctx, gs, ng, st); if (r) return r; ng = 0; }
       }
       return PSGD_OK;
     };
-    if (dt == PSGD_F32) {
-      rc = for_pairs([&](int p) {
-        const size_t r1 = (size_t)2 * p * b, c2 = r1 + b; const int b2 = b2_of(p);
-        GemmDesc g = gemm_desc(dt, Qc + (r1 * s + c2) * es, s, 0, t.Xf + c2 * s + c2, s, 0, b, b2, b2, t.Wf + p * slot, b);
-        return g; });
-      if (rc) return rc;
-      rc = for_pairs([&](int p) {
-        const size_t r1 = (size_t)2 * p * b, c2 = r1 + b; const int b2 = b2_of(p);
-        GemmDesc g = gemm_desc(dt, t.Xf + r1 * s + r1, s, 0, t.Wf + p * slot, b, 0, b, b2, b, t.Xf + r1 * s + c2, s);
-        g.epi.alpha = -1.f;
-        return g; });
-      if (rc) return rc;
-      continue;
-    }
-    // ---- bf16 factors: hi / lo products ----
-    rc = for_pairs([&](int p) {   // Wt = A12 Xlo22
-      const size_t r1 = (size_t)2 * p * b, c2 = r1 + b; const int b2 = b2_of(p);
-      return gemm_desc(dt, Qc + (r1 * s + c2) * es, s, 0, t.Xlo + c2 * s + c2, s, 0, b, b2, b2, t.Wt + p * slot, b); });
+    auto b2_of = [&](const Item& I) { int c = I.s - (2 * I.p * b + b); return c < b ? c : b; };
+    rc = for_items([&](const Item& I) {   // Wt = A12 Xlo22
+      const size_t s = I.s, r1 = (size_t)2 * I.p * b, c2 = r1 + b; const int b2 = b2_of(I); TriWs& t = *I.t;
+      return gemm_desc(dt, I.Q + (r1 * s + c2) * 2, I.s, 0, t.Xlo + c2 * s + c2, I.s, 0, b, b2, b2, t.Wt + I.p * slot, b); });
     if (rc) return rc;
-    rc = for_pairs([&](int p) {   // Wf = A12 Xhi22 + Wt   (fp32 out)
-      const size_t r1 = (size_t)2 * p * b, c2 = r1 + b; const int b2 = b2_of(p);
-      GemmDesc g = gemm_desc(dt, Qc + (r1 * s + c2) * es, s, 0, t.Xhi + c2 * s + c2, s, 0, b, b2, b2, t.Wf + p * slot, b);
-      g.epi.out_dtype = PSGD_F32; g.epi.D = t.Wt + p * slot; g.epi.ldd = b; g.epi.d_dtype = PSGD_BF16; g.epi.beta = 1.f;
+    rc = for_items([&](const Item& I) {   // Wf = A12 Xhi22 + Wt   (fp32 out)
+      const size_t s = I.s, r1 = (size_t)2 * I.p * b, c2 = r1 + b; const int b2 = b2_of(I); TriWs& t = *I.t;
+      GemmDesc g = gemm_desc(dt, I.Q + (r1 * s + c2) * 2, I.s, 0, t.Xhi + c2 * s + c2, I.s, 0, b, b2, b2, t.Wf + I.p * slot, b);
+      g.epi.out_dtype = PSGD_F32; g.epi.D = t.Wt + I.p * slot; g.epi.ldd = b; g.epi.d_dtype = PSGD_BF16; g.epi.beta = 1.f;
       return g; });
     if (rc) return rc;
-    {
-      dim3 grid((unsigned)((slot + 255) / 256), pairs);
-      k_split_hilo<<<grid, 256, 0, st>>>(t.Wf, slot, b, t.Whi, t.Wlo, slot, b, b, b, s);
+    for (int jx = 0; jx < nj; ++jx) {
+      if (!pairs_of[jx]) continue;
+      TriWs& t = *jobs[jx].t;
+      dim3 grid((unsigned)((slot + 255) / 256), pairs_of[jx]);
+      k_split_hilo<<<grid, 256, 0, st>>>(t.Wf, slot, b, t.Whi, t.Wlo, slot, b, b, b, jobs[jx].s);
       LAUNCH_CHECK(ctx, "k_split_hilo");
     }
-    rc = for_pairs([&](int p) {   // Wt = Xlo11 Whi
-      const size_t r1 = (size_t)2 * p * b; const int b2 = b2_of(p);
-      return gemm_desc(dt, t.Xlo + r1 * s + r1, s, 0, t.Whi + p * slot, b, 0, b, b2, b, t.Wt + p * slot, b); });
+    rc = for_items([&](const Item& I) {   // Wt = Xlo11 Whi
+      const size_t s = I.s, r1 = (size_t)2 * I.p * b; const int b2 = b2_of(I); TriWs& t = *I.t;
+      return gemm_desc(dt, t.Xlo + r1 * s + r1, I.s, 0, t.Whi + I.p * slot, b, 0, b, b2, b, t.Wt + I.p * slot, b); });
     if (rc) return rc;
-    rc = for_pairs([&](int p) {   // Z2 = Xhi11 Wlo + Wt
-      const size_t r1 = (size_t)2 * p * b; const int b2 = b2_of(p);
-      GemmDesc g = gemm_desc(dt, t.Xhi + r1 * s + r1, s, 0, t.Wlo + p * slot, b, 0, b, b2, b, t.Z2 + p * slot, b);
-      g.epi.D = t.Wt + p * slot; g.epi.ldd = b; g.epi.d_dtype = PSGD_BF16; g.epi.beta = 1.f;
+    rc = for_items([&](const Item& I) {   // Z2 = Xhi11 Wlo + Wt
+      const size_t s = I.s, r1 = (size_t)2 * I.p * b; const int b2 = b2_of(I); TriWs& t = *I.t;
+      GemmDesc g = gemm_desc(dt, t.Xhi + r1 * s + r1, I.s, 0, t.Wlo + I.p * slot, b, 0, b, b2, b, t.Z2 + I.p * slot, b);
+      g.epi.D = t.Wt + I.p * slot; g.epi.ldd = b; g.epi.d_dtype = PSGD_BF16; g.epi.beta = 1.f;
       return g; });
     if (rc) return rc;
-    rc = for_pairs([&](int p) {   // Wf = -Xhi11 Whi - Z2   (fp32 out)
-      const size_t r1 = (size_t)2 * p * b; const int b2 = b2_of(p);
-      GemmDesc g = gemm_desc(dt, t.Xhi + r1 * s + r1, s, 0, t.Whi + p * slot, b, 0, b, b2, b, t.Wf + p * slot, b);
-      g.epi.out_dtype = PSGD_F32; g.epi.alpha = -1.f; g.epi.D = t.Z2 + p * slot; g.epi.ldd = b; g.epi.d_dtype = PSGD_BF16; g.epi.beta = -1.f;
+    rc = for_items([&](const Item& I) {   // Wf = -Xhi11 Whi - Z2   (fp32 out)
+      const size_t s = I.s, r1 = (size_t)2 * I.p * b; const int b2 = b2_of(I); TriWs& t = *I.t;
+      GemmDesc g = gemm_desc(dt, t.Xhi + r1 * s + r1, I.s, 0, t.Whi + I.p * slot, b, 0, b, b2, b, t.Wf + I.p * slot, b);
+      g.epi.out_dtype = PSGD_F32; g.epi.alpha = -1.f; g.epi.D = t.Z2 + I.p * slot; g.epi.ldd = b; g.epi.d_dtype = PSGD_BF16; g.epi.beta = -1.f;
       return g; });
     if (rc) return rc;
-    {
-      dim3 grid((unsigned)((slot + 255) / 256), pairs);
-      k_split_hilo<<<grid, 256, 0, st>>>(t.Wf, slot, b, t.Xhi + b, t.Xlo + b, (size_t)2 * b * s + 2 * b, s, b, b, s);
+    for (int jx = 0; jx < nj; ++jx) {
+      if (!pairs_of[jx]) continue;
+      TriWs& t = *jobs[jx].t;
+      dim3 grid((unsigned)((slot + 255) / 256), pairs_of[jx]);
+      k_split_hilo<<<grid, 256, 0, st>>>(t.Wf, slot, b, t.Xhi + b, t.Xlo + b, (size_t)2 * b * jobs[jx].s + 2 * b, jobs[jx].s, b, b, jobs[jx].s);
       LAUNCH_CHECK(ctx, "k_split_hilo");
     }
   }
@@ -324,8 +342,11 @@ static int geom_prepare(Ctx* ctx, const psgd_kron_t* k, int dq, const void* X, c
   // ---- term2 ----
   const float t2s[2] = {(float)((double)numel / (double)m), (float)((double)numel / (double)n)};
   if (dq == PSGD_DQ_EQ) {
+    TriJob jobs[2];
+    int nj = 0;
     for (int i = 0; i < nf; ++i)
-      if (dense[i]) { rc = run_tri_inverse(ctx, dt, i == 0 ? k->QL : k->QR, i == 0 ? m : n, gw.tri[i], st); if (rc) return rc; }
+      if (dense[i]) jobs[nj++] = TriJob{i == 0 ? k->QL : k->QR, i == 0 ? m : n, &gw.tri[i]};
+    rc = run_tri_inverse(ctx, dt, jobs, nj, st); if (rc) return rc;
     rc = run_inverse_apply(ctx, k, gw, V, gw.C1, dense[0] ? nullptr : gw.t2vec[0], (k->has_r && !dense[1]) ? gw.t2vec[1] : nullptr, st);
     if (rc) return rc;
     for (int i = 0; i < nf; ++i)
@@ -362,7 +383,12 @@ static int geom_prepare(Ctx* ctx, const psgd_kron_t* k, int dq, const void* X, c
   for (int i = 0; i < nf; ++i) {
     if (!dense[i]) continue;
     const int s = i == 0 ? m : n;
-    DISPATCH_T(dt, (k_combine_terms<T><<<s, 256, 0, st>>>((T*)w.S[i][0], (T*)gw.T2[i], s, dq == PSGD_DQ_EQ ? 1 : 0, w.f[i].row_sumsq, w.f[i].diag_max)));
+    const int triu = dq == PSGD_DQ_EQ ? 1 : 0;
+    if (dt == PSGD_BF16 && s % 8 == 0 && ((reinterpret_cast<uintptr_t>(w.S[i][0]) | reinterpret_cast<uintptr_t>(gw.T2[i])) & 15u) == 0) {
+      k_combine_terms_bf16x8<<<s, 256, 0, st>>>((bf16*)w.S[i][0], (bf16*)gw.T2[i], s, triu, w.f[i].row_sumsq, w.f[i].diag_max);
+    } else {
+      DISPATCH_T(dt, (k_combine_terms<T><<<s, 256, 0, st>>>((T*)w.S[i][0], (T*)gw.T2[i], s, triu, w.f[i].row_sumsq, w.f[i].diag_max)));
+    }
     LAUNCH_CHECK(ctx, "k_combine_terms");
   }
   return PSGD_OK;

@@ -457,6 +457,29 @@ __global__ void __launch_bounds__(256) k_combine_terms(T* __restrict__ T1, T* __
   if (threadIdx.x == 0 && row_sumsq) row_sumsq[i] = ss;
 }
 
+// bf16, s % 8 == 0, 16-byte aligned: the same with 16-byte accesses
+__global__ void __launch_bounds__(256) k_combine_terms_bf16x8(bf16* __restrict__ T1, bf16* __restrict__ T2, int s, int triu, float* row_sumsq,
+                                                              float* diag_max) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  float ss = 0.f;
+  for (int j0 = threadIdx.x * 8; j0 < s; j0 += blockDim.x * 8) {
+    const size_t idx = (size_t)i * s + j0;
+    float a[8], b[8], sm[8], e[8];
+    ld8(T1 + idx, a); ld8(T2 + idx, b);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      sm[t] = rbf(a[t] + b[t]);
+      e[t] = (triu && j0 + t < i) ? 0.f : a[t] - b[t];
+      ss = fmaf(sm[t], sm[t], ss);
+      if (j0 + t == i && diag_max) atomic_max_nonneg(diag_max, sm[t]);
+    }
+    st8(T1 + idx, sm); st8(T2 + idx, e);
+  }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0 && row_sumsq) row_sumsq[i] = ss;
+}
+
 // Q = (P + P^T) / 2    psgd.py:479 / 509 / 794 / 824.  grid (ceil(s/32), ceil(s/32)), block (32, 8)
 template <typename T>
 __global__ void k_symmetrize(const T* __restrict__ P, T* __restrict__ Q, int s) {
@@ -511,49 +534,169 @@ __global__ void k_diag_update_gen(T* __restrict__ q, const float* __restrict__ t
 }
 
 // Inverse of the upper-triangular diagonal blocks of Q (leaf of the blocked inversion behind the triangular solves of psgd.py:288-303).
-// One CTA of TRI_NB threads per TRI_NB x TRI_NB block, in place in shared memory: rows are processed bottom-up, thread j owns column j:
-//   X[i][j] = (delta_ij - sum_{k=i+1..j} U[i][k] X[k][j]) / U[i][i].
-// Output: fp32 (Xf) or a bf16 hi/lo split (Xhi + Xlo carries ~16 mantissa bits), both s x s row-major, only the diagonal blocks written.
+// One CTA of 256 threads per TRI_NB x TRI_NB block, everything in shared memory (fp32):
+//   level 0: the eight 16 x 16 diagonal micro-blocks by back substitution, one thread per column (columns are independent: no barriers);
+//   levels b = 16, 32, 64: inv([[A11, A12], [0, A22]]) = [[X11, -X11 (A12 X22)], [0, X22]] as two small products per pair, all threads,
+//            1 x 4 register tiles, the k ranges trimmed to the triangles.
+// Output: Xf (fp32, s x s row-major), only the diagonal blocks are written.
 constexpr int TRI_NB = 128;
+constexpr int TRI_P = TRI_NB + 4;   // smem pitch (floats): rows stay 16-byte aligned
+constexpr size_t TRI_LEAF_SMEM = (size_t)(2 * TRI_NB + TRI_NB / 2) * TRI_P * sizeof(float);
 template <typename T>
-__global__ void __launch_bounds__(TRI_NB) k_tri_inv_leaf(const T* __restrict__ Q, int s, float* __restrict__ Xf, bf16* __restrict__ Xhi,
-                                                         bf16* __restrict__ Xlo) {
-  extern __shared__ float tri_sm[];
-  float* X = tri_sm;                              // TRI_NB x (TRI_NB + 1)
-  float* ur = tri_sm + TRI_NB * (TRI_NB + 1);     // current row of U
+__global__ void __launch_bounds__(256) k_tri_inv_leaf(const T* __restrict__ Q, int s, float* __restrict__ Xf) {
+  extern __shared__ __align__(16) float tri_sm[];
+  float* U = tri_sm;                     // TRI_NB x TRI_P: the block's upper triangle (identity beyond the matrix edge)
+  float* X = U + TRI_NB * TRI_P;         // its inverse
+  float* Tm = X + TRI_NB * TRI_P;        // TRI_NB/2 x TRI_P: A12 X22 of every pair of the current level
   const int o = blockIdx.x * TRI_NB;
-  const int nb = min(TRI_NB, s - o);
-  const int j = threadIdx.x;
-  for (int i = nb - 1; i >= 0; --i) {
-    ur[j] = (j < nb && j >= i) ? to_f<T>(Q[(size_t)(o + i) * s + o + j]) : 0.f;
-    __syncthreads();
-    float a0 = (j == i) ? 1.f : 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (j > i && j < nb) {
-      int k = i + 1;
-      for (; k + 3 <= j; k += 4) {
-        a0 = fmaf(-ur[k], X[k * (TRI_NB + 1) + j], a0);
-        a1 = fmaf(-ur[k + 1], X[(k + 1) * (TRI_NB + 1) + j], a1);
-        a2 = fmaf(-ur[k + 2], X[(k + 2) * (TRI_NB + 1) + j], a2);
-        a3 = fmaf(-ur[k + 3], X[(k + 3) * (TRI_NB + 1) + j], a3);
-      }
-      for (; k <= j; ++k) a0 = fmaf(-ur[k], X[k * (TRI_NB + 1) + j], a0);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < TRI_NB * TRI_NB; e += 256) {
+    const int r = e / TRI_NB, c = e % TRI_NB;
+    float v = (r == c) ? 1.f : 0.f;
+    if (o + r < s && o + c < s) v = (c >= r) ? to_f<T>(Q[(size_t)(o + r) * s + o + c]) : 0.f;
+    U[r * TRI_P + c] = v;
+    X[r * TRI_P + c] = 0.f;
+  }
+  __syncthreads();
+  if (tid < TRI_NB) {   // level 0: column jj of micro-block blk
+    const int base = (tid >> 4) * 16, jj = tid & 15;
+    float x[16];
+#pragma unroll
+    for (int i = 15; i >= 0; --i) {
+      float acc = (i == jj) ? 1.f : 0.f;
+#pragma unroll
+      for (int k = i + 1; k < 16; ++k) acc = fmaf(-U[(base + i) * TRI_P + base + k], x[k], acc);
+      x[i] = (i <= jj) ? acc / U[(base + i) * TRI_P + base + i] : 0.f;
     }
-    const float v = (j >= i && j < nb) ? ((a0 + a1) + (a2 + a3)) / ur[i] : 0.f;
-    X[i * (TRI_NB + 1) + j] = v;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) X[(base + i) * TRI_P + base + jj] = x[i];
+  }
+  __syncthreads();
+  for (int b = 16; b < TRI_NB; b *= 2) {
+    const int tpr = b / 4;                 // 1 x 4 tiles per row
+    const int ntiles = (TRI_NB / 2) * tpr; // pairs * b rows = TRI_NB / 2
+    for (int tile = tid; tile < ntiles; tile += 256) {      // Tm = A12 X22   (X22 upper triangular: k <= c)
+      const int row = tile / tpr, c0 = (tile % tpr) * 4;
+      const int p = row / b, r = row % b, r1 = 2 * p * b, c2 = r1 + b;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const int kend = min(c0 + 3, b - 1);
+      for (int k = 0; k <= kend; ++k) {
+        const float a = U[(r1 + r) * TRI_P + c2 + k];
+        const float4 xv = *reinterpret_cast<const float4*>(&X[(c2 + k) * TRI_P + c2 + c0]);
+        a0 = fmaf(a, xv.x, a0); a1 = fmaf(a, xv.y, a1); a2 = fmaf(a, xv.z, a2); a3 = fmaf(a, xv.w, a3);
+      }
+      *reinterpret_cast<float4*>(&Tm[row * TRI_P + c0]) = make_float4(a0, a1, a2, a3);
+    }
+    __syncthreads();
+    for (int tile = tid; tile < ntiles; tile += 256) {      // X12 = -X11 Tm   (X11 upper triangular: k >= r)
+      const int row = tile / tpr, c0 = (tile % tpr) * 4;
+      const int p = row / b, r = row % b, r1 = 2 * p * b, c2 = r1 + b;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int k = r; k < b; ++k) {
+        const float a = X[(r1 + r) * TRI_P + r1 + k];
+        const float4 tv = *reinterpret_cast<const float4*>(&Tm[(p * b + k) * TRI_P + c0]);
+        a0 = fmaf(a, tv.x, a0); a1 = fmaf(a, tv.y, a1); a2 = fmaf(a, tv.z, a2); a3 = fmaf(a, tv.w, a3);
+      }
+      *reinterpret_cast<float4*>(&X[(r1 + r) * TRI_P + c2 + c0]) = make_float4(-a0, -a1, -a2, -a3);
+    }
     __syncthreads();
   }
-  for (int i = 0; i < nb; ++i) {
-    if (j < nb) {
-      const float v = X[i * (TRI_NB + 1) + j];
-      const size_t idx = (size_t)(o + i) * s + o + j;
-      if (Xf) Xf[idx] = v;
-      if (Xhi) {
-        const bf16 h = __float2bfloat16_rn(v);
-        Xhi[idx] = h;
-        Xlo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+  for (int e = tid; e < TRI_NB * TRI_NB; e += 256) {
+    const int r = e / TRI_NB, c = e % TRI_NB;
+    if (o + r < s && o + c < s) Xf[(size_t)(o + r) * s + o + c] = X[r * TRI_P + c];
+  }
+}
+
+// One level of the blocked inversion in fp32 on CUDA cores, batched over the pairs (blockIdx.z = pair): C = alpha * A * B with
+//   STAGE 1: A = A12 (a block of Q, dtype T), B = X22 (fp32, upper triangular: k < n0 + 64 suffices), C = Tm  (slot p, ld b)
+//   STAGE 2: A = X11 (fp32, upper triangular: k >= m0), B = Tm, C = X12 (into the inverse), alpha = -1
+// 64 x 64 tiles, 256 threads, 4 x 4 per thread.  Used for the low levels (b < TRI_TC_MIN_B: the tcgen05 kernel's launch latency dominates
+// there) and for every level of fp32 factors.
+template <typename T, int STAGE>
+__global__ void __launch_bounds__(256) k_tri_pair_gemm(const T* __restrict__ Q, float* __restrict__ Xf, float* __restrict__ Tm, int s, int b) {
+  __shared__ float As[16][68];
+  __shared__ float Bs[16][68];
+  const int p = blockIdx.z;
+  const size_t r1 = (size_t)2 * p * b, c2 = r1 + b;
+  const int b2 = min(b, s - (int)c2);                 // columns of this pair's off-diagonal block
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (n0 >= b2) return;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float* Tp = Tm + (size_t)p * b * b;
+  const int K = STAGE == 1 ? b2 : b;
+  const int kbeg = STAGE == 1 ? 0 : (m0 / 16) * 16;
+  const int kend = STAGE == 1 ? min(K, n0 + 64) : K;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int idx = tid + t * 256;
+      {  // A tile: 64 rows x 16 k
+        const int mi = idx >> 4, ki = idx & 15;
+        const int gm = m0 + mi, gk = k0 + ki;
+        float v = 0.f;
+        if (gm < b && gk < K) v = STAGE == 1 ? to_f<T>(Q[(r1 + gm) * s + c2 + gk]) : Xf[(r1 + gm) * s + r1 + gk];
+        As[ki][mi] = v;
+      }
+      {  // B tile: 16 k x 64 cols
+        const int ki = idx >> 6, ni = idx & 63;
+        const int gk = k0 + ki, gn = n0 + ni;
+        float v = 0.f;
+        if (gk < K && gn < b2) v = STAGE == 1 ? Xf[(c2 + gk) * s + c2 + gn] : Tp[(size_t)gk * b + gn];
+        Bs[ki][ni] = v;
       }
     }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= b) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= b2) continue;
+      if (STAGE == 1) Tp[(size_t)gm * b + gn] = acc[i][j];
+      else Xf[(r1 + gm) * s + c2 + gn] = -acc[i][j];
+    }
+  }
+}
+
+// fp32 inverse -> bf16 hi + lo (the whole s x s matrix, zeros included).  8 elements per thread.
+__global__ void k_split_full(const float* __restrict__ Xf, bf16* __restrict__ hi, bf16* __restrict__ lo, size_t numel) {
+  size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < numel; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(Xf + i);
+    const bf16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
+    __nv_bfloat162 la = __floats2bfloat162_rn(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+    __nv_bfloat162 lb = __floats2bfloat162_rn(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+    *reinterpret_cast<uint2*>(hi + i) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+    *reinterpret_cast<uint2*>(lo + i) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t t = numel & ~size_t(3); t < numel; ++t) {
+      const bf16 h = __float2bfloat16_rn(Xf[t]);
+      hi[t] = h; lo[t] = __float2bfloat16_rn(Xf[t] - __bfloat162float(h));
+    }
 }
 
 // fp32 blocks -> bf16 hi / lo splits, batched over the pairs of one level of the blocked inversion.

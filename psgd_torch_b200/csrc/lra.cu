@@ -749,8 +749,8 @@ int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
       const float* pin = mode == 0 ? nullptr : (mode == 1 ? w.p1 : w.p2);
       float* pout = mode == 0 ? w.p1 : (mode == 1 ? w.p2 : nullptr);
       if (n_full > 0) {
-        if (r == 32) k_lra_apply_tma<32><<<gridt, 288, 8 * tile_bytes, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n_full, mode, pin, pout, sumsq_out);
-        else k_lra_apply_tma<16><<<gridt, 288, 8 * tile_bytes, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n_full, mode, pin, pout, sumsq_out);
+        if (r == 32) k_lra_apply_tma<32><<<gridt, 32 * (LRA_APPLY_CW + 1), 8 * tile_bytes, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n_full, mode, pin, pout, sumsq_out);
+        else k_lra_apply_tma<16><<<gridt, 32 * (LRA_APPLY_CW + 1), 8 * tile_bytes, st>>>(Mx, (const bf16*)l->d, (const bf16*)g, w.dd, (bf16*)out, n_full, mode, pin, pout, sumsq_out);
         ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply_tma"); if (rc) return rc;
       }
       if (n_rem > 0) {

@@ -711,8 +711,10 @@ __device__ __forceinline__ void lra_bulk_g2s(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+constexpr int LRA_APPLY_CW = 16;   // consumer warps of k_lra_apply_tma: a pure-read sweep needs >= 16 resident warps per SM to cover the
+                                   // dot-product latency chains (8 warps top out near 4 TB/s on this part, tools/read_bw_probe.py)
 template <int RP>
-__global__ void __launch_bounds__(288, 1) k_lra_apply_tma(const bf16* __restrict__ Mtx, const bf16* __restrict__ d, const bf16* __restrict__ g,
+__global__ void __launch_bounds__(32 * (LRA_APPLY_CW + 1), 1) k_lra_apply_tma(const bf16* __restrict__ Mtx, const bf16* __restrict__ d, const bf16* __restrict__ g,
                                                           float* __restrict__ g2, bf16* __restrict__ out, long long n_full, int mode,
                                                           const float* __restrict__ pin, float* __restrict__ pout, float* sumsq) {
   constexpr int ROWS = 256;
@@ -721,7 +723,10 @@ __global__ void __launch_bounds__(288, 1) k_lra_apply_tma(const bf16* __restrict
   constexpr int OFF_D = MAT_BYTES, OFF_G = OFF_D + ROWS * 2, OFF_G2 = OFF_G + ROWS * 2;
   constexpr int TILE = OFF_G2 + ROWS * 4;
   constexpr int STAGES = 8;
-  constexpr int NP = 32 * PPR / 32;   // 16-byte pieces per lane for a warp's 32 rows
+  constexpr int NCW = LRA_APPLY_CW;
+  constexpr int RPW = ROWS / NCW;     // rows per consumer warp and stage
+  constexpr int NP = RPW * PPR / 32;  // 16-byte pieces per lane for a warp's rows
+  static_assert(NP >= 1 && RPW * PPR == NP * 32, "consumer warp tiling");
   extern __shared__ __align__(128) uint8_t smem_lra[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES];
   __shared__ float pacc[RP];
@@ -729,7 +734,7 @@ __global__ void __launch_bounds__(288, 1) k_lra_apply_tma(const bf16* __restrict
   const uint32_t sbase = smem_u32_generic(smem_lra);
   const uint32_t bbase = smem_u32_generic(bars);
   if (threadIdx.x == 0) {
-    for (int s0 = 0; s0 < STAGES; ++s0) { lra_mbar_init(bbase + 8 * s0, 1); lra_mbar_init(bbase + 8 * (STAGES + s0), 8); }
+    for (int s0 = 0; s0 < STAGES; ++s0) { lra_mbar_init(bbase + 8 * s0, 1); lra_mbar_init(bbase + 8 * (STAGES + s0), NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < RP) pacc[threadIdx.x] = 0.f;
@@ -751,7 +756,7 @@ __global__ void __launch_bounds__(288, 1) k_lra_apply_tma(const bf16* __restrict
       }
     }
   } else {
-    const int cw = warp - 1;             // consumer warp 0..7 -> rows [32 cw, 32 cw + 32) of the stage
+    const int cw = warp - 1;             // consumer warp -> rows [RPW cw, RPW cw + RPW) of the stage
     const int piece = lane % PPR;
     float pv[8], acc[8];
 #pragma unroll
@@ -768,7 +773,7 @@ __global__ void __launch_bounds__(288, 1) k_lra_apply_tma(const bf16* __restrict
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         const int p = lane + 32 * i;
-        const int lrow = cw * 32 + p / PPR;
+        const int lrow = cw * RPW + p / PPR;
         const uint4 raw = *reinterpret_cast<const uint4*>(tile + (size_t)lrow * RP * 2 + (p % PPR) * 16);
         float x[8];
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
