@@ -369,7 +369,11 @@ def run_engine(args):
         sampler.start()
     lib.psgd_timing_enable(h, 1)
     l0 = lib.psgd_launch_count(h)
+    if args.profile_range:   # ncu --profile-from-start off: only the timed region of the `value` leg is captured
+        torch.cuda.cudart().cudaProfilerStart()
     ms_value = timed(lambda: step_resident(units, psgd), args.steps, dev, dist, world)
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = lib.psgd_launch_count(h) - l0
     n_l, t_ms, fl = C.c_int(), C.c_double(), C.c_double()
     lib.psgd_timing_read(h, C.byref(n_l), C.byref(t_ms), C.byref(fl))
@@ -393,7 +397,8 @@ def run_engine(args):
         peaks, peak_src = load_peaks()
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         achieved_tf = (fl.value / (t_ms.value * 1e-3) / 1e12) if t_ms.value > 0 else None
-        roof = {"bound": "tensor", "kernel": "psgd::gemm_tc_kernel<256> (tcgen05 128x256x64 grouped GEMM, fused PSGD epilogue)",
+        roof = {"bound": "tensor", "kernel": "psgd::gemm_tc2_kernel / gemm_tc_kernel<BN> (tcgen05 grouped GEMM with the fused PSGD epilogue: cta_group::2 256x256 pair "
+                          "tiles where whole waves fit, else 128xBN tiles with split-K units)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved_tf / peak_tf) if achieved_tf else None,
                 "peak_source": peak_src + ", sustained cuBLAS bf16 figure (kernel timed inside a long step)",
@@ -472,6 +477,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

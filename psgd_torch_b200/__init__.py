@@ -12,5 +12,6 @@ from ._lib import EngineError, load_library, launch_count  # noqa: F401
 try:  # wrappers are pure Python on top of .psgd
     from .kwns4 import KWNS4  # noqa: F401
     from .lra_optim import LRAWhitenOptimizer  # noqa: F401
+    from .closure_optim import KronNewton, KronWhiten, LRANewton, LRAWhiten  # noqa: F401
 except ImportError:  # pragma: no cover - during bring-up
     pass

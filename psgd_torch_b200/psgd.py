@@ -682,3 +682,12 @@ for _n, _dq in (("eq", "EQ"), ("qep", "QEP"), ("qeq", "QEQ"), ("q0p5eq1p5", "Q0.
                 ("quad4p", "QUAD4P")):
     globals()[f"update_precond_kron_newton_{_n}"] = _newton(_dq)       # psgd.py:657-829
     globals()[f"update_precond_kron_newton_{_n}"].__name__ = f"update_precond_kron_newton_{_n}"
+
+
+# closure-style optimizer classes of the reference (psgd.py:516-654, 832-978, 1075-1190, 1201-1330): re-authored host-side glue on top of
+# the functions above (psgd_torch_b200/closure_optim.py); resolved lazily to keep this module importable on its own
+def __getattr__(name):
+    if name in ("KronWhiten", "KronNewton", "LRAWhiten", "LRANewton"):
+        from . import closure_optim
+        return getattr(closure_optim, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
