@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace psgd {
@@ -735,9 +736,10 @@ __device__ __forceinline__ void locate_tile2(const TcGroup& g, int t, int& pi, i
   tn = in_g / gsz;
 }
 
+template <int BN_>
 struct Tc2Cfg {
-  static constexpr int BN = TC2_BN;
-  static constexpr int STAGES = 6;
+  static constexpr int BN = BN_;                           // 256, or 128 for launches whose last 256-wide wave would be mostly empty
+  static constexpr int STAGES = BN_ == 256 ? 6 : 8;
   static constexpr int A_BYTES = 128 * TC_BK * 2;          // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;     // this CTA's half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB
@@ -746,9 +748,9 @@ struct Tc2Cfg {
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TcGroup g) {
-  using Cfg = Tc2Cfg;
-  constexpr int BN = Cfg::BN;
+  using Cfg = Tc2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1086,34 +1088,52 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
 // 2-CTA launch (256 x 256 pair tiles, B split between the two SMs: 64 B/clk/SM of operand traffic instead of 96).  Measured on B200 the
 // same work costs a 1-CTA wave ~1.2x a pair wave, but the 1-CTA kernel has finer tiles (half-width tail wave, split-K), so the choice is
 // made on modelled waves: pair waves are whole, 1-CTA waves round up to the next half.
-static bool tc2_worthwhile(const Ctx* ctx, const GemmDesc* gs, int n) {
-  if (ctx->debug_flags & 8) return false;
+// Returns 0 (use the 1-CTA kernel), 256 or 128 (pair-tile width of the 2-CTA kernel).  128-wide pair tiles halve the wave granularity (a
+// 4096^3 product is 256 tiles of 256 x 256 = 3.46 waves of 74 pairs -> 4 waves, but 512 tiles of 256 x 128 = 6.92 -> 7 half-size waves), yet
+// measured on B200 a 256 x 128 wave costs 0.70 of a 256 x 256 wave, not 0.5 (4096^3: 122 us against 100 us, profiles/r01_gemm_tile_n128.log):
+// the relative cost PSGD_B200_TC2_N128_PCT defaults to 140, which keeps the narrow tile for launches that would otherwise waste most
+// of their last wave only.
+static int tc2_choice(const Ctx* ctx, const GemmDesc* gs, int n) {
+  if (ctx->debug_flags & 8) return 0;
   const int pairs = ctx->num_sms / 2;
-  long t2 = 0, t1 = 0;
+  long t2 = 0, t2n = 0, t1 = 0;
+  bool any_sym = false;
   for (int i = 0; i < n; ++i) {
     const GemmDesc& g = gs[i];
-    if (g.M < 256 || g.N <= 128) return false;
+    if (g.M < 256 || g.N <= 128) return 0;
     const bool sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis);
     const long pm = (g.M + TC2_BM - 1) / TC2_BM, pn = (g.N + TC2_BN - 1) / TC2_BN;
     const long tm = (g.M + TC_BM - 1) / TC_BM;
     if (sym) {
+      any_sym = true;
       for (long r = 0; r < pm; ++r) t2 += pn - r;
       for (long r = 0; r < tm; ++r) t1 += pn - (r * TC_BM) / 256;
     } else {
       t2 += pm * pn;
+      t2n += pm * ((g.N + 127) / 128);
       t1 += tm * pn;
     }
   }
-  if (t2 < pairs) return false;                 // under-filled: the 1-CTA kernel's narrow tiles / split-K fill the machine better
+  if (t2 < pairs) return 0;                     // under-filled: the 1-CTA kernel's narrow tiles / split-K fill the machine better
   const double w2 = (double)((t2 + pairs - 1) / pairs);
   const long full = t1 / ctx->num_sms, frac = t1 % ctx->num_sms;
   const double w1 = (double)full + (frac == 0 ? 0.0 : (frac * 2 <= ctx->num_sms ? 0.5 : 1.0));
   const int pct = (ctx->debug_flags >> 8) & 0xff;     // experiment knob: relative cost of a 1-CTA wave in percent (default 118)
-  return w2 <= w1 * (pct ? pct * 0.01 : 1.18);
+  const double c1 = w1 * (pct ? pct * 0.01 : 1.18);
+  double c2 = w2;
+  int bn = 256;
+  if (!any_sym && !(ctx->debug_flags & 128)) {
+    static int n128_pct = -1;
+    if (n128_pct < 0) { const char* e = getenv("PSGD_B200_TC2_N128_PCT"); n128_pct = e ? atoi(e) : 140; if (n128_pct < 50) n128_pct = 140; }
+    const double c2n = (double)((t2n + pairs - 1) / pairs) * 0.5 * (n128_pct * 0.01);
+    if (c2n < c2 || (ctx->debug_flags & 65536)) { c2 = c2n; bn = 128; }
+  }
+  return c2 <= c1 ? bn : 0;
 }
 
+template <int BN>
 static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStream_t st) {
-  using Cfg = Tc2Cfg;
+  using Cfg = Tc2Cfg<BN>;
   int tiles = 0;
   double exec_flops = 0.0;
   for (int i = 0; i < n; ++i) {
@@ -1148,9 +1168,9 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
   grp.mn_lbo = ctx->mn_lbo;
   grp.mn_sbo = ctx->mn_sbo;
   grp.error_flag = nullptr;
-  static bool attr_set = false;
+  static bool attr_set = false;   // one flag per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(gemm_tc2)");
     attr_set = true;
   }
@@ -1158,7 +1178,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   const bool timed = ctx->timing_on && ctx->timing_count < ctx->ev_capacity;
   if (timed) cudaEventRecord(ctx->ev_begin[ctx->timing_count], st);
-  gemm_tc2_kernel<<<2 * pairs, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
+  gemm_tc2_kernel<BN><<<2 * pairs, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
   if (timed) {
     cudaEventRecord(ctx->ev_end[ctx->timing_count], st);
     ctx->timing_count++;
@@ -1178,7 +1198,11 @@ int launch_gemm_tc_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
   }
   TcGroup grp;
   memset(&grp, 0, sizeof(grp));
-  if (ctx->force_bn == 0 && tc2_worthwhile(ctx, gs, n)) return launch_tc2(ctx, grp, gs, n, st);
+  if (ctx->force_bn == 0) {
+    const int bn2 = tc2_choice(ctx, gs, n);
+    if (bn2 == 256) return launch_tc2<256>(ctx, grp, gs, n, st);
+    if (bn2 == 128) return launch_tc2<128>(ctx, grp, gs, n, st);
+  }
   if (ctx->force_bn == 128) return launch_tc<128>(ctx, grp, gs, n, st);
   if (ctx->force_bn == 256) return launch_tc<256>(ctx, grp, gs, n, st);
   if (max_n > 128) return launch_tc<256>(ctx, grp, gs, n, st);

@@ -117,7 +117,8 @@ def test_kron_engine_matches_oracle_midsize(shape, dtype, path):
 
 
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("shape", [(256, 512, 192), (384, 640, 1000), (136, 136, 72), (1000, 520, 264), (2048, 768, 512), (2048, 2560, 1024)])
+@pytest.mark.parametrize("shape", [(256, 512, 192), (384, 640, 1000), (136, 136, 72), (1000, 520, 264), (2048, 768, 512), (2048, 2560, 1024),
+                                   (2304, 2440, 320)])   # the last two take the 2-CTA kernel with 128-wide pair tiles (ragged N in the last)
 def test_tcgen05_gemm_matches_fp64(ta, tb, shape):
     from psgd_torch_b200 import psgd
     dev = _dev()

@@ -20,7 +20,7 @@ for (M, N, K, ta, tb) in ((4096, 4096, 4096, 0, 0), (4096, 4096, 4096, 1, 0), (4
     A = torch.randn((K, M) if ta else (M, K), device=dev).bfloat16()
     B = torch.randn((N, K) if tb else (K, N), device=dev).bfloat16()
     res = []
-    for name, fl in (("default", 0), ("no3d", 32), ("2cta", 8)):
+    for name, fl in (("default", 0), ("2cta-256 only", 128), ("2cta-128 forced", 65536), ("1cta", 8)):
         lib.psgd_debug_set_flags(h, fl)
         try:
             ms = t(lambda: psgd.gemm(A, B, trans_a=bool(ta), trans_b=bool(tb), path=2))
