@@ -118,10 +118,22 @@ def test_kron_engine_matches_oracle_midsize(shape, dtype, path):
 
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("shape", [(256, 512, 192), (384, 640, 1000), (136, 136, 72), (1000, 520, 264), (2048, 768, 512), (2048, 2560, 1024),
-                                   (2304, 2440, 320)])   # the last two take the 2-CTA kernel with 128-wide pair tiles (ragged N in the last)
-def test_tcgen05_gemm_matches_fp64(ta, tb, shape):
-    from psgd_torch_b200 import psgd
+                                   (2304, 2440, 320)])   # the last two take the 2-CTA (cta_group::2) kernel (ragged N in the last)
+@pytest.mark.parametrize("flags", [0, 65536])            # 65536: force the 128-wide pair tile of the 2-CTA kernel where that kernel runs
+def test_tcgen05_gemm_matches_fp64(ta, tb, shape, flags):
+    from psgd_torch_b200 import psgd, _lib
     dev = _dev()
+    if flags and shape[0] < 2048:
+        pytest.skip("the 2-CTA kernel only takes launches that fill the machine")
+    lib = _lib.load_library()
+    lib.psgd_debug_set_flags(_lib.handle_for(dev), flags)
+    try:
+        _gemm_check(psgd, dev, ta, tb, shape)
+    finally:
+        lib.psgd_debug_set_flags(_lib.handle_for(dev), 0)
+
+
+def _gemm_check(psgd, dev, ta, tb, shape):
     M, N, K = shape
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn((K, M) if ta else (M, K), generator=g).bfloat16().to(dev)
