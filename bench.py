@@ -15,8 +15,9 @@ bf16 preconditioners, wrapper-default hyper-parameters, synthetic N(0, 0.01^2) g
   e2e   : the same pass through the public API with HOST gradients: per unit pinned-host -> device copy, update + apply, device ->
           pinned-host copy of the preconditioned gradient, all inside the timed region (copies on side streams, pipelined 3 units
           ahead, shape buckets interleaved so that both PCIe directions stay busy under the compute)
-  N > 1 : owner-computes partition of the 291 independent units (psgd_torch_b200/partition.py), no data-path collective; the total
-          work is fixed, so scaling is "strong".
+  N > 1 : owner-computes partition of the 290 independent Kron units (psgd_torch_b200/partition.py, no data-path collective) + the LRA
+          unit row-sharded over all ranks (psgd_torch_b200/lra_sharded.py: the r x r Grams / projections are all-reduced over NCCL, 13 KB
+          per update); the total work is fixed, so scaling is "strong".
   --impl reference : the reference's own CPU arithmetic (oracle port of psgd.py in torch-CPU ops, all host threads) on a bounded
           sample of the same workload, extrapolated per shape bucket.
 """
@@ -47,6 +48,11 @@ LLAMA3_8B_SET = [
     ("lm_head", 1, (128256, 4096), "kron"),
     ("embed_tokens_lra32", 1, (128256 * 4096,), "lra"),
 ]
+
+
+# measured update + apply time per unit on one B200 (ms; profiles/r01_bucket_times_v2.log, v3): the weights of the LPT partition
+UNIT_MS = {"q_o_proj": 1.68, "k_v_proj": 0.40, "gate_up_proj": 1.86, "down_proj": 1.89, "rmsnorm": 0.05, "lm_head": 10.5,
+           "embed_tokens_lra32": 69.0}
 
 
 def unit_list():
@@ -176,29 +182,32 @@ def cpu_baseline_sample(threads=None, lra_sample_n=1 << 22, verbose=False):
 # engine arm
 # ----------------------------------------------------------------------------------------------------------------
 class Unit:
-    __slots__ = ("name", "shape", "kind", "G", "QL", "exprs", "UVd", "Luvd", "numel")
+    __slots__ = ("name", "shape", "kind", "G", "QL", "exprs", "UVd", "Luvd", "numel", "sharded")
 
 
-def build_units(my_units, dev):
+def build_units(my_units, dev, lra_rows=None, group=None):
+    """lra_rows = (lo, hi): this rank's row shard of the LRA unit (N > 1: the one unit too big to hand to a single rank, it is row-sharded
+    over all ranks, psgd_torch_b200/lra_sharded.py); None: the whole unit."""
     from psgd_torch_b200 import psgd
     out = []
     gen = torch.Generator(device=dev).manual_seed(1234)
     for name, shape, kind in my_units:
         u = Unit()
-        u.name, u.shape, u.kind = name, shape, kind
+        u.name, u.shape, u.kind, u.sharded = name, shape, kind, None
         if kind == "kron":
             u.G = (0.01 * torch.randn(*shape, device=dev, generator=gen)).bfloat16()
             u.QL, u.exprs = psgd.init_kron(u.G)
             u.numel = u.G.numel()
         else:
-            n = shape[0]
+            n_total = shape[0]
+            n = n_total if lra_rows is None else lra_rows[1] - lra_rows[0]
             u.G = torch.empty(n, 1, device=dev, dtype=torch.bfloat16)
             chunk = 1 << 26
             for o in range(0, n, chunk):  # chunked init keeps the fp32 temporaries small
                 u.G[o:o + chunk] = (0.01 * torch.randn(min(chunk, n - o), 1, device=dev, generator=gen)).bfloat16()
             U = torch.empty(n, LRA_RANK, device=dev, dtype=torch.bfloat16)
             V = torch.empty(n, LRA_RANK, device=dev, dtype=torch.bfloat16)
-            sc = (0.1 / (n * LRA_RANK)) ** 0.5  # psgd.py:1115-1118: ||U||_F = ||V||_F = sqrt(0.1)
+            sc = (0.1 / (n_total * LRA_RANK)) ** 0.5  # psgd.py:1115-1118: ||U||_F = ||V||_F = sqrt(0.1)
             for o in range(0, n, chunk):
                 m_ = min(chunk, n - o)
                 U[o:o + m_] = (sc * torch.randn(m_, LRA_RANK, device=dev, generator=gen)).bfloat16()
@@ -207,6 +216,9 @@ def build_units(my_units, dev):
             u.UVd = [U, V, d]
             u.Luvd = [torch.zeros([], dtype=torch.float32, device=dev) for _ in range(3)]
             u.numel = n
+            if lra_rows is not None:
+                from psgd_torch_b200.lra_sharded import ShardedLRA
+                u.sharded = ShardedLRA(u.UVd, u.Luvd, group=group)
         out.append(u)
     return out
 
@@ -216,6 +228,9 @@ def run_unit(u, G, psgd):
     if u.kind == "kron":
         psgd.update_precond_kron_whiten_q0p5eq1p5(u.QL, u.exprs, G, lr=0.1, betaL=0.9, damping=1e-9)
         return psgd.precond_grad_kron(u.QL, u.exprs, G)
+    if u.sharded is not None:   # row shard of the LRA unit: same kernels, five small all-reduces (NCCL) between the sweeps
+        u.sharded.update_precond_lra_whiten(G, lr=0.1, betaL=0.9, damping=1e-9)
+        return u.sharded.precond_grad_lra(G)
     psgd.update_precond_lra_whiten(u.UVd, u.Luvd, G, lr=0.1, betaL=0.9, damping=1e-9)
     return psgd.precond_grad_lra(u.UVd, G)
 
@@ -260,6 +275,8 @@ class HostPipeline:
             seen[key] = j + 1
             pos.append(((j + 0.5) / count[key], idx))
         self.order = [idx for _, idx in sorted(pos)]
+        coll = [i for i in self.order if units[i].sharded is not None]   # units with collectives go first on every rank: the ranks meet there
+        self.order = coll + [i for i in self.order if units[i].sharded is None]
         self.slot = {k: 0 for k in self.host_in}
         self.in_free = {k: [None] * len(v) for k, v in self.stage_in.items()}   # event: compute finished reading stage_in[k][i]
         self.out_done = {k: None for k in self.host_in}                         # event: last D2H into host_out[k] finished
@@ -345,18 +362,17 @@ def run_engine(args):
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
 
     all_units = unit_list()
-    costs = []
-    for name, shape, kind in all_units:
-        if kind == "lra":
-            costs.append(partition.lra_unit_cost(shape[0], LRA_RANK))
-        elif len(shape) == 1:
-            costs.append(partition.kron_unit_cost(shape[0], 1, False, False))
-        else:
-            dl, dr = dense_flags(shape)
-            costs.append(partition.kron_unit_cost(shape[0], shape[1], dl, dr))
-    parts = partition.lpt_partition(costs, world)
-    mine = [all_units[i] for i in parts[rank]]
-    units = build_units(mine, dev)
+    if world == 1:
+        units = build_units(all_units, dev)
+    else:
+        # Kron units: owner-computes LPT partition on the measured unit times; the LRA unit (17 % of the step, indivisible by ownership) is
+        # row-sharded over all ranks and comes first in every rank's list so that its all-reduces meet
+        kron = [u for u in all_units if u[2] != "lra"]
+        lra = [u for u in all_units if u[2] == "lra"]
+        lra_ms = sum(UNIT_MS[u[0]] for u in lra) / world
+        parts = partition.lpt_partition([UNIT_MS[u[0]] for u in kron], world, initial_loads=[lra_ms] * world)
+        mine = lra + [kron[i] for i in parts[rank]]
+        units = build_units(mine, dev, lra_rows=partition.row_shard(lra[0][1][0], world, rank) if lra else None)
     torch.cuda.synchronize(dev)
     h = _lib.handle_for(dev)
     lib = _lib.load_library()
@@ -427,7 +443,8 @@ def run_engine(args):
                                    "(dense x dense) + 64 k/v 1024x4096 + 64 gate/up 14336x4096 + 32 down 4096x14336 + 65 RMSNorm "
                                    "4096 + lm_head 128256x4096 as Kron(diag,dense) + embed_tokens 128256x4096 as LRA r=32",
                        "preconditioner_dtype": "bf16", "geometry": "Q0.5EQ1.5 (dense Q, the path KWNS4 runs)",
-                       "partition": "single GPU" if world == 1 else f"owner-computes LPT partition over {world} GPUs, no collective",
+                       "partition": "single GPU" if world == 1 else f"Kron units: owner-computes LPT partition over {world} GPUs, no collective; "
+                                    "the LRA unit is row-sharded over all ranks (5 all-reduces of <= 13 KB per update + apply, NCCL)",
                        "cache": "per-step working set (>16 GB of gradients + 7 GB of Q) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": n_units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,

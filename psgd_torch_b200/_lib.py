@@ -72,6 +72,9 @@ SYMBOLS = {
     "psgd_lra_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _i, _vp, _sz, _vp]),
     "psgd_lra_whiten_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _f, _i, _vp, _sz, _vp]),
     "psgd_lra_precond_grad": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "psgd_lra_workspace_offsets": (_i, [_vp, C.POINTER(LraT), C.POINTER(_sz), C.POINTER(_sz)]),
+    "psgd_lra_update_staged": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _f, _i, _i, _i, _vp, _sz, _vp]),
+    "psgd_lra_precond_grad_staged": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "psgd_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _f, _vp, _i, _f, _vp]),
     "psgd_timing_enable": (_i, [_vp, _i]),
     "psgd_timing_read": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

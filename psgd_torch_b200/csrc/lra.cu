@@ -610,16 +610,23 @@ static int validate_lra(const psgd_lra_t* l) {
   return PSGD_OK;
 }
 
+// stages of one update: a row-sharded preconditioner (rows of U, V, d spread over ranks) all-reduces the sweep-1 sums between SWEEP1 and
+// SWEEP2 and the two maxima of the d update between SWEEP2 and FINISH (psgd_torch_b200/lra_sharded.py); a single GPU runs all three
+enum { LRA_ST_SWEEP1 = 1, LRA_ST_SWEEP2 = 2, LRA_ST_FINISH = 4, LRA_ST_ALL = 7 };
+
 static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const void* hv, float lr, float betaL, int update_U, LraWs& w,
-                           cudaStream_t st) {
+                           cudaStream_t st, int stages = LRA_ST_ALL, bool zeroed = false) {
   const int dt = l->dtype, RP = w.RP, r = l->r;
   const long long n = l->n;
-  int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+  int rc;
+  if ((stages & LRA_ST_SWEEP1) && !zeroed) { rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc; }
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   // tensor-core sweeps: bf16, rank exactly 16 or 32 (rows are whole 16-byte pieces); everything else takes the CUDA-core sweeps
   const bool mma_path = dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && al16(l->d) && al16(hv) && al16(v) && ctx->gemm_path != 1;
   const int smem_mma = 8 * LRA_STAGES * (r == 32 ? LraTile<32>::BYTES : LraTile<16>::BYTES);
-  if (mma_path) {
+  if (!(stages & LRA_ST_SWEEP1)) {
+    // sums of sweep 1 already in w.acc (all-reduced by the caller)
+  } else if (mma_path) {
     long long chunks = (n + 15) / 16;
     int grid1 = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
     static bool attr_g = false;
@@ -639,6 +646,8 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
     LRA_DISPATCH(dt, RP, (k_lra_sweep1<T, R_><<<grid1, 256, 0, st>>>((const T*)l->U, (const T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.acc)));
     ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep1"); if (rc) return rc;
   }
+  float* scal = w.par + lra_par_scal_off(RP);
+  if (stages & LRA_ST_SWEEP2) {
   size_t smem_small = ((size_t)8 * RP * RP + 24 * RP) * 4;
   static bool small_attr = false;
   if (!small_attr) { cudaFuncSetAttribute(k_lra_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); small_attr = true; }
@@ -647,7 +656,6 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   long long rows_blocks = (n + 127) / 128;
   int grid2 = (int)(rows_blocks < (long long)ctx->num_sms * 8 ? rows_blocks : (long long)ctx->num_sms * 8);
   size_t smem2 = ((size_t)2 * RP * RP + LV_NVEC * RP) * 4;
-  float* scal = w.par + lra_par_scal_off(RP);
   if (mma_path) {
     long long chunks = (n + 15) / 16;
     int gridr = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
@@ -659,6 +667,8 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
     k_lra_sweep2<T, R_><<<grid2, 128, smem2, st>>>((T*)l->U, (T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.par, update_U, w.dd, scal);
   });
   ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep2"); if (rc) return rc;
+  }
+  if (!(stages & LRA_ST_FINISH)) return PSGD_OK;
   k_lra_Ld<<<1, 32, 0, st>>>(scal, lr, betaL, l->Ld, dt);
   ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_Ld"); if (rc) return rc;
   int gridd = (int)(((n + 255) / 256) < (long long)ctx->num_sms * 8 ? ((n + 255) / 256) : (long long)ctx->num_sms * 8);
@@ -710,8 +720,24 @@ int psgd_lra_whiten_update(psgd_handle_t h, const psgd_lra_t* l, const void* g, 
   return lra_update_impl(ctx, l, v, w.hbuf, lr, betaL, update_U, w, st);
 }
 
+static int lra_apply_impl(psgd_handle_t h, const psgd_lra_t* l, const void* g, void* out, float* sumsq_out, void* workspace,
+                          size_t workspace_bytes, void* stream, int modes);
+
 int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, void* out, float* sumsq_out, void* workspace,
                           size_t workspace_bytes, void* stream) {
+  return lra_apply_impl(h, l, g, out, sumsq_out, workspace, workspace_bytes, stream, 7);
+}
+
+// modes: bit 0 = V^T (d g) (zeroes the projections first), bit 1 = y = d g + U p1 and U^T y, bit 2 = out = d (y + V p2).  A row-sharded
+// preconditioner all-reduces the projection after bit 0 and after bit 1 (psgd_lra_workspace_offsets [2], [3]) and sumsq_out at the end.
+int psgd_lra_precond_grad_staged(psgd_handle_t h, const psgd_lra_t* l, const void* g, void* out, float* sumsq_out, int modes, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!(modes & 7)) return PSGD_ERR_INVALID_ARG;
+  return lra_apply_impl(h, l, g, out, sumsq_out, workspace, workspace_bytes, stream, modes);
+}
+
+static int lra_apply_impl(psgd_handle_t h, const psgd_lra_t* l, const void* g, void* out, float* sumsq_out, void* workspace,
+                          size_t workspace_bytes, void* stream, int modes) {
   Ctx* ctx = reinterpret_cast<Ctx*>(h);
   if (!ctx || !g || !out) return PSGD_ERR_INVALID_ARG;
   int rc = validate_lra(l); if (rc) return rc;
@@ -721,9 +747,11 @@ int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int dt = l->dtype, RP = w.RP, r = l->r;
   const long long n = l->n;
-  rc = check_cuda(ctx, cudaMemsetAsync(w.p1, 0, 64 * 4, st), "memset"); if (rc) return rc;
-  rc = check_cuda(ctx, cudaMemsetAsync(w.p2, 0, 64 * 4, st), "memset"); if (rc) return rc;
-  if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4, st), "memset"); if (rc) return rc; }
+  if (modes & 1) {
+    rc = check_cuda(ctx, cudaMemsetAsync(w.p1, 0, 64 * 4, st), "memset"); if (rc) return rc;
+    rc = check_cuda(ctx, cudaMemsetAsync(w.p2, 0, 64 * 4, st), "memset"); if (rc) return rc;
+    if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4, st), "memset"); if (rc) return rc; }
+  }
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   if (dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && ctx->gemm_path != 1) {
     const int rpi = r == 32 ? 8 : 16;   // rows per warp instruction
@@ -745,6 +773,7 @@ int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
     long long need_r = ((n_rem + rpi - 1) / rpi + 4 * 8 - 1) / (4 * 8);
     int gridrem = (int)(need_r < 1 ? 1 : need_r);
     for (int mode = 0; mode < 3; ++mode) {
+      if (!(modes & (1 << mode))) continue;
       const bf16* Mx = (const bf16*)(mode == 1 ? l->U : l->V);
       const float* pin = mode == 0 ? nullptr : (mode == 1 ? w.p1 : w.p2);
       float* pout = mode == 0 ? w.p1 : (mode == 1 ? w.p2 : nullptr);
@@ -764,12 +793,64 @@ int psgd_lra_precond_grad(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
   }
   long long rb = (n + 127) / 128;
   int grid = (int)(rb < (long long)ctx->num_sms * 8 ? rb : (long long)ctx->num_sms * 8);
-  LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->V, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 0, nullptr, w.p1, nullptr)));
-  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply0"); if (rc) return rc;
-  LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->U, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 1, w.p1, w.p2, nullptr)));
-  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply1"); if (rc) return rc;
-  LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->V, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 2, w.p2, nullptr, sumsq_out)));
-  ctx->launches++; return check_cuda(ctx, cudaGetLastError(), "k_lra_apply2");
+  if (modes & 1) {
+    LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->V, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 0, nullptr, w.p1, nullptr)));
+    ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply0"); if (rc) return rc;
+  }
+  if (modes & 2) {
+    LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->U, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 1, w.p1, w.p2, nullptr)));
+    ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply1"); if (rc) return rc;
+  }
+  if (modes & 4) {
+    LRA_DISPATCH(dt, RP, (k_lra_apply<T, R_><<<grid, 128, 0, st>>>((const T*)l->V, (const T*)l->d, (const T*)g, w.dd, (T*)out, n, r, 2, w.p2, nullptr, sumsq_out)));
+    ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_apply2"); if (rc) return rc;
+  }
+  return PSGD_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Row-sharded LRA (rows of U, V, d, g spread over the GPUs of a box): the same kernels, issued stage by stage so that the host can
+// all-reduce the few cross-row quantities in between (NCCL over NVLink; psgd_torch_b200/lra_sharded.py).
+//   offsets (bytes into the workspace) / counts (floats): [0] sweep-1 sums (SUM), [1] the two maxima of the d update (MAX),
+//   [2] apply projection after mode 0 (SUM), [3] apply projection after mode 1 (SUM)
+// ------------------------------------------------------------------------------------------------
+int psgd_lra_workspace_offsets(psgd_handle_t, const psgd_lra_t* l, size_t* offsets, size_t* counts) {
+  if (validate_lra(l) || !offsets || !counts) return PSGD_ERR_INVALID_ARG;
+  LraWs w;
+  layout_lra(l, nullptr, w);
+  auto off = [](const void* p) { return (size_t)(reinterpret_cast<uintptr_t>(p) - 256); };   // sizing mode hands out offset + 256
+  offsets[0] = off(w.acc); counts[0] = lra_acc_floats(w.RP);
+  offsets[1] = off(w.par + lra_par_scal_off(w.RP) + LS_MAX_PHH); counts[1] = 2;
+  offsets[2] = off(w.p1); counts[2] = 64;
+  offsets[3] = off(w.p2); counts[3] = 64;
+  return PSGD_OK;
+}
+
+// stages: 1 = (damping, if whiten) + sweep 1, 2 = r x r algebra + sweep 2, 4 = Ld + d update.  gh = g (whiten != 0: h = g + (damping + eps|g|) v is
+// formed here) or h itself.
+int psgd_lra_update_staged(psgd_handle_t h, const psgd_lra_t* l, const void* gh, const void* v, float lr, float betaL, float damping,
+                           int whiten, int update_U, int stages, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !v || !gh || !(stages & LRA_ST_ALL)) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_lra(l); if (rc) return rc;
+  if (!l->Lu || !l->Lv || !l->Ld) return PSGD_ERR_INVALID_ARG;
+  LraWs w;
+  layout_lra(l, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = l->n;
+  const void* hv = gh;
+  if (whiten) {
+    hv = w.hbuf;
+    if (stages & LRA_ST_SWEEP1) {
+      int grid = (int)(((n + 255) / 256) < (long long)ctx->num_sms * 8 ? ((n + 255) / 256) : (long long)ctx->num_sms * 8);
+      if (l->dtype == PSGD_BF16) k_lra_damp<bf16><<<grid, 256, 0, st>>>((const bf16*)gh, (const bf16*)v, (bf16*)w.hbuf, n, damping, dtype_eps(PSGD_BF16));
+      else k_lra_damp<float><<<grid, 256, 0, st>>>((const float*)gh, (const float*)v, (float*)w.hbuf, n, damping, dtype_eps(PSGD_F32));
+      ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_damp"); if (rc) return rc;
+    }
+  }
+  return lra_update_impl(ctx, l, v, hv, lr, betaL, update_U, w, st, stages);
 }
 
 }  // extern "C"

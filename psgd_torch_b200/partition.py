@@ -29,10 +29,12 @@ def lra_unit_cost(n: int, r: int, elem_bytes: int = 2) -> float:
     return (10.0 * n * r * elem_bytes + 12.0 * n * elem_bytes) * 250.0 + 14.0 * n * r * r
 
 
-def lpt_partition(costs: Sequence[float], world_size: int) -> List[List[int]]:
-    """Greedy LPT: returns, per rank, the (sorted) list of unit indices it owns. Deterministic on every rank."""
+def lpt_partition(costs: Sequence[float], world_size: int, initial_loads: Sequence[float] | None = None) -> List[List[int]]:
+    """Greedy LPT: returns, per rank, the (sorted) list of unit indices it owns. Deterministic on every rank.
+    `initial_loads`: work every rank already carries (e.g. its row shard of a sharded LRA preconditioner)."""
     order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
-    loads = [0.0] * world_size
+    loads = list(initial_loads) if initial_loads is not None else [0.0] * world_size
+    assert len(loads) == world_size
     owned: List[List[int]] = [[] for _ in range(world_size)]
     for i in order:
         r = min(range(world_size), key=lambda k: (loads[k], k))
@@ -53,3 +55,13 @@ def imbalance(costs: Sequence[float], parts: List[List[int]]) -> Tuple[float, fl
     loads = [sum(costs[i] for i in p) for p in parts]
     mean = sum(loads) / len(loads)
     return max(loads) / mean if mean > 0 else 1.0, mean
+
+
+def row_shard(n: int, world_size: int, rank: int, align: int = 256) -> Tuple[int, int]:
+    """Rows [lo, hi) of an n-row LRA preconditioner owned by `rank`: contiguous, sizes multiples of `align` (whole bulk-copy blocks of the
+    sweep kernels) except for the last rank, which takes the remainder."""
+    per = -(-n // world_size)
+    per = -(-per // align) * align
+    lo = min(n, rank * per)
+    hi = min(n, lo + per) if rank < world_size - 1 else n
+    return lo, max(lo, hi)

@@ -102,3 +102,29 @@ def test_world_size_2_gloo_rng_sync_and_partition():
         assert same_state, "private RNG states must be identical across ranks after construction (ddp.py:88-96)"
         assert ext_restored, "step() must restore the caller's RNG state (ddp.py:172-176)"
         assert drew and same_parts
+
+
+def test_row_shard_covers_all_rows_in_aligned_blocks():
+    from psgd_torch_b200 import partition
+    for n in (525336576, 1000, 70000, 255):
+        for world in (1, 2, 4, 8):
+            spans = [partition.row_shard(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(spans, spans[1:]):
+                assert hi == lo2 and lo <= hi
+            for lo, hi in spans[:-1]:
+                assert (hi - lo) % 256 == 0 or hi == n    # whole bulk-copy blocks, except where the rows run out
+
+
+def test_bench_multi_gpu_partition_is_balanced():
+    """bench.py at N > 1: Kron units by LPT on the measured unit times with the LRA row shard as every rank's initial load."""
+    import bench
+    from psgd_torch_b200 import partition
+    units = bench.unit_list()
+    kron = [u for u in units if u[2] != "lra"]
+    lra_ms = bench.UNIT_MS["embed_tokens_lra32"]
+    for world in (2, 4, 8):
+        parts = partition.lpt_partition([bench.UNIT_MS[u[0]] for u in kron], world, initial_loads=[lra_ms / world] * world)
+        assert sorted(i for p in parts for i in p) == list(range(len(kron)))
+        loads = [lra_ms / world + sum(bench.UNIT_MS[kron[i][0]] for i in p) for p in parts]
+        assert max(loads) / (sum(loads) / world) < 1.03, loads
