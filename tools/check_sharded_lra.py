@@ -33,7 +33,7 @@ for step in range(3):
         psgd.update_precond_lra_whiten(whole, Lw, g, lr=0.1, noise={"v": v, "update_U": step % 2 == 0})
         ssq_w = torch.zeros(1, device=dev)
         want = psgd.precond_grad_lra(whole, g, sumsq_out=ssq_w)
-        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
         errs = [rel(sh.UVd[k], whole[k][lo:hi]) for k in range(3)] + [rel(out, want[lo:hi]), rel(ssq, ssq_w)] + [rel(a, b) for a, b in zip(sh.Luvd, Lw)]
         worst = max(worst, max(errs))
         print(f"step {step}: rel err U,V,d,out,sumsq,Lu,Lv,Ld = " + " ".join(f"{e:.2e}" for e in errs), flush=True)
