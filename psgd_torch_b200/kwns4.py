@@ -46,6 +46,7 @@ class KWNS4(torch.optim.Optimizer):
             preconditioner_dtype: torch.dtype | None = torch.bfloat16,
             update_preconditioner_first=True,
             resync_every=1000_000,
+            shard_preconditioners=False,
     ):
         # ddp.py:45-62, verbatim
         assert whiten_grad in (False, True)
@@ -87,6 +88,12 @@ class KWNS4(torch.optim.Optimizer):
         }
         super().__init__(params, defaults)
 
+        # Not in the reference (which replicates all of the optimizer work on every rank, ddp.py:88-96): owner-computes sharding of the
+        # per-parameter preconditioners (BASELINE configs[3], SURVEY.md 8e "training-correct mode").  Every parameter is owned by one rank,
+        # which alone keeps its (Q, L, ema) and runs its update + apply; the updated parameter is then broadcast to the other ranks
+        # (NCCL).  Off by default so that the class stays a drop-in with the reference's replicated semantics.
+        self.shard_preconditioners = bool(shard_preconditioners)
+        self._owner = None
         self.dQ = "Q0.5EQ1.5"  # ddp.py:84-86
         self.update_precond = psgd.update_precond_kron_whiten_q0p5eq1p5
         self.precond_grad = psgd.precond_grad_kron
@@ -112,6 +119,34 @@ class KWNS4(torch.optim.Optimizer):
                 self.cuda_rng_state = state.cpu()
             else:
                 self.cuda_rng_state = None
+
+    # ---- owner-computes sharding (shard_preconditioners=True) ----
+    def _sharding_active(self):
+        return self.shard_preconditioners and self.is_distributed and torch.distributed.get_world_size() > 1
+
+    def _assign_owners(self):
+        """LPT partition of all parameters on the cost model of SURVEY.md 8d; identical on every rank (shapes only)."""
+        from . import partition
+        plist, costs = [], []
+        for group in self.param_groups:
+            for p in group["params"]:
+                shp = tuple(self._local(p).squeeze().shape)
+                numel = 1
+                for s_ in shp:
+                    numel *= s_
+                dense = [not (s_ <= 1 or s_ > group["preconditioner_max_size"] or s_ * s_ > group["preconditioner_max_skew"] * numel) for s_ in shp]
+                if len(shp) == 2:
+                    c = partition.kron_unit_cost(shp[0], shp[1], dense[0], dense[1])
+                else:   # 0/1-D and order >= 3: a pass-count estimate is enough for balancing
+                    c = 40.0 * numel * 2 * 250.0 + sum(8.0 * s_ ** 3 + 6.0 * s_ * numel for s_, dn in zip(shp, dense) if dn)
+                plist.append(p)
+                costs.append(c)
+        owners = partition.owner_of(costs, torch.distributed.get_world_size())
+        self._owner = {id(p): r for p, r in zip(plist, owners)}
+        # the only draws every rank must agree on are the per-group update coins (ddp.py:110): a dedicated generator seeded from the
+        # synchronised private state, because each rank now consumes a different amount of the main streams
+        seed = int(torch.frombuffer(bytearray(self.cpu_rng_state[:8].numpy().tobytes()), dtype=torch.int64)[0]) & 0x7FFFFFFF
+        self._coin_gen = torch.Generator().manual_seed(seed)
 
     # ---- hooks overridden by the DTensor variant ----
     def _local(self, t):
@@ -161,16 +196,27 @@ class KWNS4(torch.optim.Optimizer):
                 torch.cuda.set_rng_state(self.cuda_rng_state)
 
         lib = _lib.load_library()
+        sharded = self._sharding_active()
+        if sharded and self._owner is None:
+            self._assign_owners()
+        my_rank = torch.distributed.get_rank() if sharded else 0
+        pending = []
         for group in self.param_groups:
             momentum = group["momentum"]
             max_avg_amp, max_element_amp = group["grad_clip_max_amps"]
+            coin = torch.rand([], generator=self._coin_gen) if sharded else torch.rand([])
             updateP_first, updateP_last = ((group["update_preconditioner_first"], not group["update_preconditioner_first"])
-                                           if torch.rand([]) < group["preconditioner_update_probability"] else (False, False))
+                                           if coin < group["preconditioner_update_probability"] else (False, False))
             wd, lr_params = group["weight_decay"], group["lr_params"]
             for p in group["params"]:
                 grad = p.grad
                 if grad is None:
                     continue
+                if sharded:
+                    owner = self._owner[id(p)]
+                    if owner != my_rank:   # the owner computes; this rank only receives the updated parameter
+                        pending.append(torch.distributed.broadcast(self._local(p), src=owner, async_op=True))
+                        continue
                 grad = self._local(grad)
                 if grad.numel() == 0:  # dtensor.py:124-125
                     continue
@@ -229,7 +275,12 @@ class KWNS4(torch.optim.Optimizer):
                     self.update_precond(state["QL"], state["exprs"], to_be_whitened,
                                         lr=group["lr_preconditioner"], betaL=group["betaL"], damping=group["damping"])
 
-                self._resync(p, state, group, momentum)
+                if sharded:
+                    pending.append(torch.distributed.broadcast(local_p, src=my_rank, async_op=True))
+                else:
+                    self._resync(p, state, group, momentum)
+        for w in pending:
+            w.wait()
 
         if self.is_distributed:  # ddp.py:172-176
             self.cpu_rng_state = torch.get_rng_state()

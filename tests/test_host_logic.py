@@ -128,3 +128,21 @@ def test_bench_multi_gpu_partition_is_balanced():
         assert sorted(i for p in parts for i in p) == list(range(len(kron)))
         loads = [lra_ms / world + sum(bench.UNIT_MS[kron[i][0]] for i in p) for p in parts]
         assert max(loads) / (sum(loads) / world) < 1.03, loads
+
+
+def test_kwns4_owner_assignment_is_a_partition(monkeypatch):
+    """shard_preconditioners=True: the owner map is computed from shapes only (identical on every rank), covers every parameter once."""
+    import torch
+    from psgd_torch_b200 import kwns4
+    ps = [torch.nn.Parameter(torch.zeros(*s)) for s in [(64, 96), (96,), (32, 512), (1, 8, 1, 12), (48, 48)]]
+    opt = kwns4.KWNS4(ps, shard_preconditioners=True)
+    opt.cpu_rng_state = torch.get_rng_state()
+    monkeypatch.setattr(torch.distributed, "get_world_size", lambda *a, **k: 2)
+    opt._assign_owners()
+    owners = [opt._owner[id(p)] for p in ps]
+    assert set(owners) == {0, 1} and len(owners) == len(ps)
+    opt2 = kwns4.KWNS4(ps, shard_preconditioners=True)
+    opt2.cpu_rng_state = opt.cpu_rng_state
+    opt2._assign_owners()
+    assert [opt2._owner[id(p)] for p in ps] == owners
+    assert float(torch.rand([], generator=opt._coin_gen)) == float(torch.rand([], generator=opt2._coin_gen))
