@@ -7,7 +7,7 @@ Host code is Python/PyTorch (device memory, streams, torch.distributed); all ari
 behind the C-ABI of include/psgd_b200.h (libpsgd_b200.so, built in-tree by `python -m psgd_torch_b200.build`).
 """
 from . import psgd  # noqa: F401
-from ._lib import EngineError, load_library, launch_count  # noqa: F401
+from ._lib import EngineError, load_library, launch_count, set_fp32_tensor_cores  # noqa: F401
 
 try:  # wrappers are pure Python on top of .psgd
     from .kwns4 import KWNS4  # noqa: F401

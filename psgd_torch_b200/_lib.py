@@ -51,6 +51,7 @@ SYMBOLS = {
     "psgd_destroy": (None, [_vp]),
     "psgd_set_gemm_path": (_i, [_vp, _i]),
     "psgd_launch_count": (_i64, [_vp]),
+    "psgd_set_fp32_tensor_cores": (_i, [_vp, _i]),
     "psgd_kron_workspace_bytes": (_sz, [_vp, C.POINTER(KronT)]),
     "psgd_kron_whiten_q0p5eq1p5_update": (_i, [_vp, C.POINTER(KronT), _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),
     "psgd_kron_precond_grad": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -175,6 +176,13 @@ def stream_ptr(device):
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     return C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+def set_fp32_tensor_cores(on, device=None):
+    """Opt-in: big fp32 products on the tensor cores as bf16 triples (include/psgd_b200.h: psgd_set_fp32_tensor_cores)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    h = handle_for(dev)
+    check(h, load_library().psgd_set_fp32_tensor_cores(h, int(bool(on))), "psgd_set_fp32_tensor_cores")
 
 
 def launch_count(device=None):

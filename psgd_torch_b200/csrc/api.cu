@@ -11,16 +11,64 @@
 
 namespace psgd {
 
+static inline int ew_blocks_n(Ctx* ctx, size_t numel) {
+  size_t b = (numel + 255) / 256, cap = (size_t)ctx->num_sms * 8;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
 int check_cuda(Ctx* ctx, cudaError_t e, const char* what) {
   if (e == cudaSuccess) return PSGD_OK;
   if (ctx) snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", what, cudaGetErrorString(e));
   return PSGD_ERR_CUDA;
 }
 
+// fp32 product on the tensor cores: both operands re-expressed as bf16 triples concatenated along K (k_split3), one tcgen05 GEMM of depth
+// 6K with the caller's epilogue: 7.6x the CUDA-core kernel at 4096^3 (0.77 vs 5.8 ms), a whole 4096^2 fp32 update 77 -> 16 ms.
+// The splits are exact and the dropped piece products are <= 2^-24, but the tensor core accumulates in fp32 with truncation, which
+// biases long sums: measured 4e-6 per 4096-deep product on random data and 9e-6 through the chain of an apply at 2048^2, against 4e-7
+// for the CUDA-core kernel.  That sits at north_star's 1e-5 for fp32 and grows with the depth, so -- like TF32 in torch -- it is OPT-IN
+// (psgd_set_fp32_tensor_cores); the default fp32 path stays on the CUDA cores.  Returns PSGD_ERR_UNSUPPORTED when not applicable.
+static int launch_gemm_f32x3(Ctx* ctx, const GemmDesc& g, cudaStream_t st) {
+  if (g.in_dtype != PSGD_F32 || !ctx->fp32_tensor) return PSGD_ERR_UNSUPPORTED;
+  if (g.M < 512 || g.N < 256 || g.K < 256 || (g.K % 8) || (g.M % 8) || (g.N % 8)) return PSGD_ERR_UNSUPPORTED;
+  if ((double)g.M * g.N * g.K < 512.0 * 512.0 * 512.0) return PSGD_ERR_UNSUPPORTED;
+  const int K6 = 6 * g.K;
+  const size_t need[2] = {(size_t)g.M * K6 * 2, (size_t)g.N * K6 * 2};
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->x3_cap[i] >= need[i]) continue;
+    if (ctx->x3_buf[i]) { cudaStreamSynchronize(st); cudaFree(ctx->x3_buf[i]); ctx->x3_buf[i] = nullptr; ctx->x3_cap[i] = 0; }
+    const size_t cap = need[i] + need[i] / 4;
+    if (cudaMalloc(&ctx->x3_buf[i], cap) != cudaSuccess) { cudaGetLastError(); return PSGD_ERR_UNSUPPORTED; }
+    ctx->x3_cap[i] = cap;
+  }
+  GemmDesc t = g;
+  t.in_dtype = PSGD_BF16;
+  t.K = K6;
+  t.A = ctx->x3_buf[0]; t.B = ctx->x3_buf[1];
+  t.lda = g.ta ? g.M : K6;     // ta: A stored K x M -> six copies stacked (6K x M); else M x K -> side by side (M x 6K)
+  t.ldb = g.tb ? K6 : g.N;     // tb: B stored N x K -> side by side (N x 6K); else K x N -> stacked (6K x N)
+  if (!tc_eligible(t)) return PSGD_ERR_UNSUPPORTED;
+  // small terms first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
+  const Split3Seq sa = {{2, 0, 1, 1, 0, 0}}, sb = {{0, 2, 1, 0, 1, 0}};
+  const int a_rows = g.ta ? g.K : g.M, a_cols = g.ta ? g.M : g.K;
+  const int b_rows = g.tb ? g.N : g.K, b_cols = g.tb ? g.K : g.N;
+  k_split3<<<ew_blocks_n(ctx, (size_t)a_rows * a_cols), 256, 0, st>>>((const float*)g.A, a_rows, a_cols, g.lda, (bf16*)ctx->x3_buf[0], t.lda, g.ta ? 0 : 1, sa);
+  ctx->launches++;
+  k_split3<<<ew_blocks_n(ctx, (size_t)b_rows * b_cols), 256, 0, st>>>((const float*)g.B, b_rows, b_cols, g.ldb, (bf16*)ctx->x3_buf[1], t.ldb, g.tb ? 1 : 0, sb);
+  ctx->launches++;
+  int rc = check_cuda(ctx, cudaGetLastError(), "k_split3"); if (rc) return rc;
+  return launch_gemm_tc_group(ctx, &t, 1, st);
+}
+
 int launch_gemm(Ctx* ctx, const GemmDesc& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return PSGD_OK;
   if (ctx->gemm_path == 1) return launch_gemm_simt(ctx, g, st);
   if (tc_eligible(g)) return launch_gemm_tc_group(ctx, &g, 1, st);
+  {
+    const int rc = launch_gemm_f32x3(ctx, g, st);
+    if (rc != PSGD_ERR_UNSUPPORTED) return rc;
+  }
   if (ctx->gemm_path == 2) return PSGD_ERR_UNSUPPORTED;
   return launch_gemm_simt(ctx, g, st);
 }
@@ -329,8 +377,10 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
   };
   // P-first (P = Q^T Q is symmetric: the tensor-core path computes its upper 128-blocks only, ~1.06 s^3 instead of 2 s^3) costs
   // 1.06 m^3 + 2 m^2 n on the left against 4 m^2 n for the chain Q_L^T (Q_L X): take it whenever m < 1.88 n (same on the right).
-  const bool pl = dl && (double)m < 1.88 * (double)n && !(ctx->debug_flags & 2);
-  const bool pr = dr && (double)n < 1.88 * (double)m && !(ctx->debug_flags & 2);
+  // bf16 only: P = Q^T Q in fp32 has no exact-diagonal correction and nothing to gain (the fp32 kernels compute symmetric products in
+  // full), while forming P squares Q's dynamic range -- measured 2e-5 instead of 2e-6 on the apply at s = 2048 while Q is still ~ c I
+  const bool pl = dl && (double)m < 1.88 * (double)n && !(ctx->debug_flags & 2) && dt == PSGD_BF16;
+  const bool pr = dr && (double)n < 1.88 * (double)m && !(ctx->debug_flags & 2) && dt == PSGD_BF16;
   {
     GemmDesc sy[2];
     int ns = 0;
@@ -472,6 +522,7 @@ void psgd_destroy(psgd_handle_t h) {
   if (!ctx) return;
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws_count) cudaFree(ctx->ws_count);
+  for (int i = 0; i < 2; ++i) if (ctx->x3_buf[i]) cudaFree(ctx->x3_buf[i]);
   delete ctx;
 }
 
@@ -482,6 +533,12 @@ int psgd_set_gemm_path(psgd_handle_t h, int p) {
 }
 
 int64_t psgd_launch_count(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->launches : 0; }
+
+int psgd_set_fp32_tensor_cores(psgd_handle_t h, int on) {
+  if (!h) return PSGD_ERR_INVALID_ARG;
+  reinterpret_cast<Ctx*>(h)->fp32_tensor = on ? 1 : 0;
+  return PSGD_OK;
+}
 
 int psgd_timing_enable(psgd_handle_t h, int on) {
   Ctx* ctx = reinterpret_cast<Ctx*>(h);

@@ -163,6 +163,10 @@ struct Ctx {
   float* ws;
   int* ws_count;
   int ws_slots;
+  // operands of an fp32 product re-expressed as bf16 triples (hi + mid + lo, concatenated along K) for the tensor cores; grown on demand
+  void* x3_buf[2];
+  size_t x3_cap[2];
+  int fp32_tensor;   // opt-in (psgd_set_fp32_tensor_cores): big fp32 products as bf16 triples on the tensor cores
 };
 
 // one GEMM problem: C = epi(op(A) op(B)), op(A) M x K, op(B) K x N

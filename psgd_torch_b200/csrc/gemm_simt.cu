@@ -44,6 +44,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
       Bs[ki][ni] = v;
     }
     __syncthreads();
+    // blocked summation: the 16 products of a k tile are summed on their own and then added to the running sum.  One long fp32 FMA
+    // chain swamps small terms once a large one has entered the accumulator (Q ~ c I + tiny, early in training: Q^T Q lost 1e-5 at
+    // s = 2048), which an MKL / cuBLAS-style blocked sum does not.
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < SM_K; ++kk) {
       float a[4], b[4];
@@ -54,8 +62,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 

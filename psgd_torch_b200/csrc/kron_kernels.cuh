@@ -426,6 +426,33 @@ __global__ void k_kwns4_tail(TP* __restrict__ p, TQ* __restrict__ h, size_t nume
   }
 }
 
+// ------------------------------ fp32 products on the bf16 tensor cores ------------------------------
+// x = hi + mid + lo with three bf16 pieces is exact for an fp32 mantissa (3 x 8 bits).  A product A B is then the sum of the six piece
+// products that matter (hi hi, hi mid, mid hi, hi lo, mid mid, lo hi: the dropped ones are <= 2^-24 relative), i.e. ONE bf16 GEMM over a
+// six times longer K axis: A' = [A_s0 | A_s1 | ... | A_s5], B' = [B_t0; ...; B_t5] with fp32 accumulation in TMEM.  This kernel writes one
+// operand: out holds six copies of the rows x cols matrix X, copy c being piece seq[c] of X, laid side by side (axis 1: rows x 6 cols)
+// or stacked (axis 0: 6 rows x cols).
+struct Split3Seq { int s[6]; };
+__global__ void k_split3(const float* __restrict__ X, int rows, int cols, int ld, bf16* __restrict__ out, int out_ld, int axis, Split3Seq seq) {
+  const size_t numel = (size_t)rows * cols;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < numel; i += stride) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float x = X[(size_t)r * ld + c];
+    bf16 p[3];
+    p[0] = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(p[0]);
+    p[1] = __float2bfloat16_rn(r1);
+    p[2] = __float2bfloat16_rn(r1 - __bfloat162float(p[1]));
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      const size_t o = axis == 1 ? (size_t)r * out_ld + (size_t)t * cols + c : ((size_t)t * rows + r) * out_ld + c;
+      out[o] = p[seq.s[t]];
+    }
+  }
+}
+
 // ------------------------------ the other Kron geometries (psgd.py:278-391, 422-513, 657-829) ------------------------------
 // out[i] = float(q[i]) (op 0) or 1 / float(q[i]) (op 1): fp32 row / column factors for the GEMM epilogue (exprA with a diagonal factor,
 // psgd.py:248-249; conjB / q, psgd.py:300)

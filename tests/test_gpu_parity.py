@@ -72,6 +72,7 @@ def _structured(m, n, seed, dtype):
     ((128, 2048), torch.bfloat16, 0),  # dense x diag (k_proj-like)
     ((2048, 128), torch.bfloat16, 0),  # diag x dense (gate_proj-like)
     ((200, 264), torch.float32, 0),    # fp32 (SIMT) dense x dense
+    ((640, 896), torch.float32, 0),    # fp32, CUDA cores by default whatever the size
 ])
 def test_kron_engine_matches_oracle_midsize(shape, dtype, path):
     from psgd_torch_b200 import psgd, _lib
@@ -145,6 +146,73 @@ def _gemm_check(psgd, dev, ta, tb, shape):
     assert relerr(C_simt, ref) < 5e-3
     C32 = psgd.gemm(A, B, trans_a=ta, trans_b=tb, path=2, out_dtype=torch.float32)
     assert relerr(C32, ref) < 2e-5       # fp32 accumulation of exact bf16 products
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_fp32_gemm_on_tensor_cores_matches_fp64(ta, tb):
+    """fp32 operands as bf16 triples (hi + mid + lo, exact) concatenated along K, one tcgen05 GEMM with fp32 accumulation: as accurate
+    as the CUDA-core fp32 kernel to well below the 1e-5 fp32 tolerance of north_star."""
+    from psgd_torch_b200 import psgd, _lib
+    dev = _dev()
+    M, N, K = 1024, 768, 520
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn((K, M) if ta else (M, K), generator=g).to(dev)
+    B = torch.randn((N, K) if tb else (K, N), generator=g).to(dev)
+    D = torch.randn(M, N, generator=g).to(dev)
+    ref = (A.double().T if ta else A.double()) @ (B.double().T if tb else B.double())
+    _lib.set_fp32_tensor_cores(True, dev)
+    try:
+        l0 = _lib.launch_count(dev)
+        C_x3 = psgd.gemm(A, B, trans_a=ta, trans_b=tb, path=2)          # path 2 = tensor cores or error
+        assert _lib.launch_count(dev) - l0 == 3                           # two operand splits + one GEMM
+        C_simt = psgd.gemm(A, B, trans_a=ta, trans_b=tb, path=1)
+        e_x3, e_simt = relerr(C_x3, ref), relerr(C_simt, ref)
+        assert e_x3 < 2e-6 and e_x3 < 4 * e_simt + 5e-7, (e_x3, e_simt)
+        C2 = psgd.gemm(A, B, trans_a=ta, trans_b=tb, alpha=-0.5, D=D, beta=2.0, path=2)
+        assert relerr(C2, -0.5 * ref + 2.0 * D.double()) < 2e-6
+    finally:
+        _lib.set_fp32_tensor_cores(False, dev)
+    with pytest.raises(_lib.EngineError):
+        psgd.gemm(A, B, trans_a=ta, trans_b=tb, path=2)                   # default: fp32 never goes to the tensor cores
+
+
+@pytest.mark.parametrize("tensor_cores,tol", [(False, 1e-5), (True, 1e-4)])
+def test_fp32_full_size_step_matches_oracle(tensor_cores, tol):
+    """Two fp32 updates + applies on a 2048 x 2048 weight against the CPU oracle on the same noise.  Default (CUDA cores): the fp32 tolerance of
+    north_star, 1e-5, holds through the whole chain of a step (measured 4e-7 on the apply, better than the CPU reference arithmetic's 7e-7).
+    Opt-in tensor cores (bf16 triples): 1e-4 allowed, measured 9e-6 (the tensor core's truncating fp32 accumulation biases long sums)."""
+    from psgd_torch_b200 import psgd, _lib
+    from oracle import psgd_oracle as orc
+    dev = _dev()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    _lib.set_fp32_tensor_cores(tensor_cores, dev)
+    try:
+        _fp32_full_size(psgd, orc, dev, tol)
+    finally:
+        _lib.set_fp32_tensor_cores(False, dev)
+
+
+def _fp32_full_size(psgd, orc, dev, tol):
+    m = n = 2048
+    G = _structured(m, n, 77, torch.float32)
+    QLo = orc.init_kron(torch.zeros(m, n))
+    QLe, exprs = psgd.init_kron(torch.zeros(m, n, device=dev))
+    for step in range(2):
+        torch.manual_seed(50 + step)
+        noise = orc.draw_kron_noise(G, QLo[0])
+        Qo = [q.detach().cpu().clone() for q in QLe[0]]
+        Lo = [l.detach().cpu().clone() for l in QLe[1]]
+        orc.update_precond_kron_whiten_q0p5eq1p5([Qo, Lo], G, noise, lr=0.5)
+        psgd.update_precond_kron_whiten_q0p5eq1p5(QLe, exprs, G.to(dev), lr=0.5, noise=_noise_to(noise, dev))
+        errs = [relerr(qe, qo) for qe, qo in zip(QLe[0], Qo)] + [relerr(le, lo) for le, lo in zip(QLe[1], Lo)]
+        assert all(e < tol for e in errs), (step, errs)
+        # the apply is judged against an fp64 evaluation like bf16 is: two valid fp32 evaluation orders already differ by ~2e-6 here
+        Pe = psgd.precond_grad_kron(QLe, exprs, G.to(dev))
+        Qc = [q.detach().cpu() for q in QLe[0]]
+        P64 = orc.precond_grad_kron([q.detach().double() for q in QLe[0]], G.double().to(dev))   # fp64 yardstick, evaluated on the GPU
+        e_eng, e_ref = relerr(Pe, P64), relerr(orc.precond_grad_kron(Qc, G), P64)
+        assert e_eng < max(tol, 1.5 * e_ref + 2e-6), (step, e_eng, e_ref)
+        print(f"fp32 2048^2 step {step}: apply error vs fp64: engine {e_eng:.2e}, reference arithmetic {e_ref:.2e}")
 
 
 def test_helpers_match_oracle():
