@@ -1,4 +1,4 @@
-"""cuBLAS vs 1-CTA vs 2-CTA tcgen05 GEMM at 4096^3 inside cudaProfilerStart/Stop (for ncu --set full)."""
+"""cuBLAS vs 2-CTA (default) vs 1-CTA tcgen05 GEMM at 4096^3 inside cudaProfilerStart/Stop (for ncu --set full)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,8 +11,8 @@ lib.psgd_debug_set_flags(h, 8); psgd.gemm(A, B, path=2); lib.psgd_debug_set_flag
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 C0 = A @ B
-lib.psgd_debug_set_flags(h, 16); C1 = psgd.gemm(A, B, path=2)
-lib.psgd_debug_set_flags(h, 8); C2 = psgd.gemm(A, B, path=2)
+C1 = psgd.gemm(A, B, path=2)                                     # default: the 2-CTA kernel (gemm_tc2_kernel<256>)
+lib.psgd_debug_set_flags(h, 8); C2 = psgd.gemm(A, B, path=2)     # bit 3: 1-CTA kernel (gemm_tc_kernel<256>)
 lib.psgd_debug_set_flags(h, 0)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
