@@ -60,6 +60,7 @@ SYMBOLS = {
     "psgd_kron_update": (_i, [_vp, C.POINTER(KronT), _i, _vp, _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),
     "psgd_kron_apply_factors": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _vp, _sz, _vp]),
     "psgd_kron_solve_factors": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _sz, _vp]),
+    "psgd_kron_factor_step": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "psgd_procrustes_step3": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _sz, _vp]),
     "psgd_symmetry_gap": (_i, [_vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "psgd_helper_workspace_bytes": (_sz, [_vp, _i, _i]),

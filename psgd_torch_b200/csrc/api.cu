@@ -959,6 +959,42 @@ int psgd_kron_solve_factors(psgd_handle_t h, const psgd_kron_t* k, const void* V
   return run_inverse_apply(ctx, k, g, V, out, nullptr, nullptr, st);
 }
 
+// One factor's bound + Lipschitz update + step for any geometry, given its contractions (the building block of the host-side composition
+// for tensors of order >= 3; the fused psgd_kron_update forms the same quantities itself for order <= 2).
+//   kind = PSGD_DENSE: term1 (s x s, dtype), term2 (s x s, dtype) or NULL (then term2 = t2 * I);
+//   kind = PSGD_DIAG : term1 (fp32, length s), term2 (fp32, length s) or NULL (then term2 = t2).
+int psgd_kron_factor_step(psgd_handle_t h, int dt, int dq, int kind, int s, void* q, float* L, const void* term1, const void* term2, float t2,
+                          float lr, float betaL, const void* V0_spd, const void* V0_skh, void* workspace, size_t wsb, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !q || !L || !term1 || s < 1 || dq < 0 || dq > PSGD_DQ_PRO4P) return PSGD_ERR_INVALID_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool quad = dq == PSGD_DQ_QUAD || dq == PSGD_DQ_QUAD4P;
+  if (kind == PSGD_DIAG) {
+    DISPATCH_T(dt, (k_diag_update_gen<T><<<1, 1024, 0, st>>>((T*)q, (const float*)term1, (const float*)term2, t2, 0, 0, s,
+                                                            dq == PSGD_DQ_QUAD ? 0.5f * lr : lr, betaL, L, quad ? 1 : 0)));
+    LAUNCH_CHECK(ctx, "k_diag_update_gen");
+    return PSGD_OK;
+  }
+  HelperWs w;
+  layout_helper(s, dt, workspace, w);
+  if (!workspace || wsb < w.total) return PSGD_ERR_WORKSPACE;
+  const size_t bytes = (size_t)s * s * dtype_size(dt);
+  int rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+  rc = check_cuda(ctx, cudaMemcpyAsync(w.R, term1, bytes, cudaMemcpyDeviceToDevice, st), "memcpy"); if (rc) return rc;
+  if (term2) {
+    rc = check_cuda(ctx, cudaMemcpyAsync(w.RRRQ, term2, bytes, cudaMemcpyDeviceToDevice, st), "memcpy"); if (rc) return rc;
+    DISPATCH_T(dt, (k_combine_terms<T><<<s, 256, 0, st>>>((T*)w.R, (T*)w.RRRQ, s, dq == PSGD_DQ_EQ ? 1 : 0, w.row_sumsq, w.nf)));
+    LAUNCH_CHECK(ctx, "k_combine_terms");
+  } else {
+    DISPATCH_T(dt, (k_rowstats<T><<<s, 256, 0, st>>>((const T*)w.R, s, w.row_sumsq, w.nf, nullptr)));
+    LAUNCH_CHECK(ctx, "k_rowstats");
+  }
+  DenseStep d;
+  d.s = s; d.q = q; d.L = L; d.t2 = t2; d.S = w.R; d.E = term2 ? w.RRRQ : nullptr; d.Qn = w.Qn; d.RQ = w.RQ; d.RRQ = w.RRQ; d.Va = w.Va; d.Vb = w.Vb;
+  d.v_spd = V0_spd; d.v_skh = V0_skh; d.f = &w.f;
+  return geom_dense_step(ctx, dt, dq, d, lr, betaL, st);
+}
+
 int psgd_procrustes_step3(psgd_handle_t h, int dt, void* Q, int s, const void* V0, float max_step_size, void* workspace, size_t wsb,
                           void* stream) {
   Ctx* ctx = reinterpret_cast<Ctx*>(h);

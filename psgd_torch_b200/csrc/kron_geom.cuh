@@ -397,6 +397,51 @@ static int geom_prepare(Ctx* ctx, const psgd_kron_t* k, int dq, const void* X, c
 // ---------------------------------------------------------------------------------------------
 // one factor's bound, Lipschitz update and step
 // ---------------------------------------------------------------------------------------------
+struct DenseStep {          // one dense factor entering its step: S = term1 (scalar term2) or term1 + term2, E = term1 - term2 (or null)
+  int s; void* q; float* L; float t2;
+  void* S; void* E; void* Qn; void* RQ; void* RRQ; void* Va; void* Vb;
+  const void* v_spd; const void* v_skh;
+  FactorWs* f;              // row_sumsq / diag_max of S already reduced
+};
+
+// norm bound of S, Lipschitz update, then the geometry's step on q (psgd.py:315-316, 362-364, 386-388, 413-416, 440-449, 474-479 ...)
+static int geom_dense_step(Ctx* ctx, int dt, int dq, const DenseStep& d, float lr, float betaL, cudaStream_t st) {
+  const int s = d.s;
+  FactorWs& f = *d.f;
+  const bool matrix_t2 = d.E != nullptr;
+  const bool quad = dq == PSGD_DQ_QUAD || dq == PSGD_DQ_QUAD4P;
+  const float lr_eff = dq == PSGD_DQ_QUAD ? 0.5f * lr : lr;   // psgd.py:470 / 476: lr/2/L
+  if (!d.v_spd) return PSGD_ERR_INVALID_ARG;
+  BoundJob jb{d.S, s, d.v_spd, f.row_sumsq, f.diag_max, &f.b_spd, d.Va, d.Vb};
+  BoundFinish fin{0, matrix_t2 ? 0.f : d.t2, lr_eff, betaL, d.L, f.fs};
+  int rc = run_bounds(ctx, dt, &jb, 1, &fin, st); if (rc) return rc;
+  // fs[FS_ALPHA] = -c, fs[FS_BETA] = 1 + c t2 (1 when term2 is a matrix): one product gives beta * q + alpha * (M q) = q - c (term1 - term2) q
+  const void* M = matrix_t2 ? d.E : d.S;
+  auto step_desc = [&](const void* src, void* dst, bool left) {
+    GemmDesc g = left ? gemm_desc(dt, M, s, 0, src, s, 0, s, s, s, dst, s) : gemm_desc(dt, src, s, 0, M, s, 0, s, s, s, dst, s);
+    g.epi.alpha_ptr = f.fs + FS_ALPHA; g.epi.D = src; g.epi.ldd = s; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.beta_ptr = f.fs + FS_BETA;
+    return g;
+  };
+  GemmDesc g = step_desc(d.q, d.Qn, dq != PSGD_DQ_QEQ);   // QEQ: q - c q (term1 - term2)   psgd.py:388 / 713
+  rc = launch_gemm(ctx, g, st); if (rc) return rc;
+  if (dq == PSGD_DQ_Q0P5EQ1P5) {                         // psgd.py:416 / 738
+    if (!d.v_skh) return PSGD_ERR_INVALID_ARG;
+    DenseItem it;
+    it.s = s; it.q = d.q; it.L = d.L; it.t2 = d.t2; it.T = d.S; it.Qn = d.Qn; it.RQ = d.RQ; it.RRQ = d.RRQ; it.Va = d.Va; it.Vb = d.Vb;
+    it.v_spd = d.v_spd; it.v_skh = d.v_skh; it.f = &f;
+    return run_procrustes(ctx, dt, &it, 1, 0.125f, st);
+  }
+  if (quad) {                                            // p = p - c p (term1 - term2); q = (p + p^T)/2   psgd.py:477-479 / 792-794
+    g = step_desc(d.Qn, d.RQ, false);
+    rc = launch_gemm(ctx, g, st); if (rc) return rc;
+    dim3 grid((s + 31) / 32, (s + 31) / 32), block(32, 8);
+    DISPATCH_T(dt, (k_symmetrize<T><<<grid, block, 0, st>>>((const T*)d.RQ, (T*)d.q, s)));
+    LAUNCH_CHECK(ctx, "k_symmetrize");
+    return PSGD_OK;
+  }
+  return check_cuda(ctx, cudaMemcpyAsync(d.q, d.Qn, (size_t)s * s * dtype_size(dt), cudaMemcpyDeviceToDevice, st), "memcpy");
+}
+
 static int geom_factor(Ctx* ctx, const psgd_kron_t* k, int dq, bool newton, int i, float lr, float betaL, const psgd_kron_noise_t* noise,
                        GeomWs& gw, cudaStream_t st) {
   KronWs& w = gw.k;
@@ -421,36 +466,10 @@ static int geom_factor(Ctx* ctx, const psgd_kron_t* k, int dq, bool newton, int 
     LAUNCH_CHECK(ctx, "k_diag_update_gen");
     return PSGD_OK;
   }
-  const void* v_spd = i == 0 ? noise->V0_spd_l : noise->V0_spd_r;
-  const void* v_skh = i == 0 ? noise->V0_skh_l : noise->V0_skh_r;
-  if (!v_spd) return PSGD_ERR_INVALID_ARG;
-  BoundJob jb{w.S[i][0], s, v_spd, f.row_sumsq, f.diag_max, &f.b_spd, w.Va[i], w.Vb[i]};
-  BoundFinish fin{0, matrix_t2 ? 0.f : t2, lr_eff, betaL, L, f.fs};
-  rc = run_bounds(ctx, dt, &jb, 1, &fin, st); if (rc) return rc;
-  // fs[FS_ALPHA] = -c, fs[FS_BETA] = 1 + c t2 (1 when term2 is a matrix): one product gives beta * q + alpha * (M q) = q - c (term1 - term2) q
-  const void* M = matrix_t2 ? gw.T2[i] : w.S[i][0];
-  void* Qn = w.S[i][1];
-  auto step_desc = [&](const void* src, void* dst, bool left) {
-    GemmDesc g = left ? gemm_desc(dt, M, s, 0, src, s, 0, s, s, s, dst, s) : gemm_desc(dt, src, s, 0, M, s, 0, s, s, s, dst, s);
-    g.epi.alpha_ptr = f.fs + FS_ALPHA; g.epi.D = src; g.epi.ldd = s; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.beta_ptr = f.fs + FS_BETA;
-    return g;
-  };
-  GemmDesc g = step_desc(q, Qn, dq != PSGD_DQ_QEQ);      // QEQ: q - c q (term1 - term2)   psgd.py:388 / 713
-  rc = launch_gemm(ctx, g, st); if (rc) return rc;
-  if (dq == PSGD_DQ_Q0P5EQ1P5) {                         // psgd.py:416 / 738
-    if (!v_skh) return PSGD_ERR_INVALID_ARG;
-    DenseItem it;
-    it.s = s; it.q = q; it.L = L; it.t2 = t2; it.T = w.S[i][0]; it.Qn = Qn; it.RQ = w.S[i][2]; it.RRQ = w.S[i][3]; it.Va = w.Va[i]; it.Vb = w.Vb[i];
-    it.v_spd = v_spd; it.v_skh = v_skh; it.f = &f;
-    return run_procrustes(ctx, dt, &it, 1, 0.125f, st);
-  }
-  if (quad) {                                            // p = p - c p (term1 - term2); q = (p + p^T)/2   psgd.py:477-479 / 792-794
-    g = step_desc(Qn, w.S[i][2], false);
-    rc = launch_gemm(ctx, g, st); if (rc) return rc;
-    dim3 grid((s + 31) / 32, (s + 31) / 32), block(32, 8);
-    DISPATCH_T(dt, (k_symmetrize<T><<<grid, block, 0, st>>>((const T*)w.S[i][2], (T*)q, s)));
-    LAUNCH_CHECK(ctx, "k_symmetrize");
-    return PSGD_OK;
-  }
-  return check_cuda(ctx, cudaMemcpyAsync(q, Qn, (size_t)s * s * dtype_size(dt), cudaMemcpyDeviceToDevice, st), "memcpy");
+  DenseStep d;
+  d.s = s; d.q = q; d.L = L; d.t2 = t2; d.S = w.S[i][0]; d.E = matrix_t2 ? gw.T2[i] : nullptr; d.Qn = w.S[i][1]; d.RQ = w.S[i][2]; d.RRQ = w.S[i][3];
+  d.Va = w.Va[i]; d.Vb = w.Vb[i]; d.f = &f;
+  d.v_spd = i == 0 ? noise->V0_spd_l : noise->V0_spd_r;
+  d.v_skh = i == 0 ? noise->V0_skh_l : noise->V0_skh_r;
+  return geom_dense_step(ctx, dt, dq, d, lr, betaL, st);
 }

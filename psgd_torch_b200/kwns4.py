@@ -169,10 +169,26 @@ class KWNS4(torch.optim.Optimizer):
             self._sumsq[device] = b
         return b
 
+    def state_dict(self):
+        """The reference's state_dict plus, under the extra key "psgd_rng", the private CPU / CUDA generator states of a distributed run
+        (ddp.py:92,96 keep them as attributes and forget them in checkpoints, so a resumed reference run draws different numbers than an
+        uninterrupted one).  A checkpoint written by the reference (no such key) loads unchanged."""
+        sd = super().state_dict()
+        if getattr(self, "is_distributed", False):
+            sd["psgd_rng"] = {"cpu": self.cpu_rng_state.clone(),
+                              "cuda": None if self.cuda_rng_state is None else self.cuda_rng_state.clone()}
+        return sd
+
     def load_state_dict(self, state_dict):
         """torch.optim.Optimizer.load_state_dict casts every floating state tensor to the PARAMETER's dtype, which would silently turn a
         bf16 preconditioner (and its momentum buffer) into fp32 on resume -- the reference has the same quirk.  Restore the group's
         preconditioner_dtype for Q and ema (L stays fp32, psgd.py:96-98) so that a resumed run continues on the same arithmetic."""
+        state_dict = dict(state_dict)
+        rng = state_dict.pop("psgd_rng", None)
+        if rng is not None and getattr(self, "is_distributed", False):
+            self.cpu_rng_state = rng["cpu"].clone().cpu()
+            if rng.get("cuda") is not None and self.cuda_rng_state is not None:
+                self.cuda_rng_state = rng["cuda"].clone().cpu()
         super().load_state_dict(state_dict)
         for group in self.param_groups:
             pd = group["preconditioner_dtype"]

@@ -605,13 +605,13 @@ def _kron_update(dQ, QL, X, V, lr, betaL, damping, noise, damp=True):
     if not X.is_cuda:
         raise EngineError("psgd_torch_b200 runs on CUDA (sm_100a) tensors only")
     X = X.contiguous()
-    if X.dim() > 2:
-        raise NotImplementedError(f"dQ={dQ!r} for tensors of order >= 3 is not built (SURVEY.md 8f item 3); Q0.5EQ1.5 is")
     if V is not None:
         V = V.contiguous()
         if V.shape != X.shape or V.dtype != X.dtype:
             raise EngineError("V and Hvp must agree in shape and dtype")
     tape = _as_tape(noise, X.device)
+    if X.dim() > 2:
+        return _kron_update_nd(dQ, QL, X, V, lr, betaL, damping, tape, damp)
     code = _lib.DQ_CODES[dQ]
     k = _kron_desc(Q, L, X)
     nz = KronNoiseT()
@@ -656,6 +656,96 @@ def _kron_update(dQ, QL, X, V, lr, betaL, damping, noise, damp=True):
     if stages:
         call(stages)
     del keep
+
+
+def _unfold(T, i):
+    return T.movedim(i, 0).reshape(T.shape[i], -1).contiguous()
+
+
+def _factor_on_mode(q, T, i):
+    """exprQs[i](q, T): psgd.py:225-226 / 245-246"""
+    if q.dim() == 2:
+        return _mode_product(q, T, i, False)
+    shp = [1] * T.dim()
+    shp[i] = -1
+    return T * q.reshape(shp)
+
+
+def _solve_factors_nd(Q, V):
+    """conjB of psgd.py:297-303 for order >= 3: one engine triangular solve per dense mode (on the mode-i unfolding), divisions for the rest."""
+    X = V
+    for i, q in enumerate(Q):
+        if q.dim() == 2:
+            Xi = X.movedim(i, 0)
+            shp = Xi.shape
+            M = Xi.reshape(shp[0], -1).contiguous()
+            ones = torch.ones(M.shape[1], dtype=M.dtype, device=M.device)
+            X = solve_kron_factors([q, ones], M).reshape(shp).movedim(0, i)
+        else:
+            shp = [1] * X.dim()
+            shp[i] = -1
+            X = X / q.reshape(shp)
+    return X.contiguous()
+
+
+def _kron_update_nd(dQ, QL, X, V, lr, betaL, damping, tape, damp):
+    """Any geometry, whitening or Newton pair, for tensors of order >= 3: host-side composition -- the contractions
+    are engine GEMMs on mode unfoldings (permutes / elementwise glue by torch), each factor's bound + Lipschitz update + step is one
+    engine call (psgd_kron_factor_step).  Same draw order as the order <= 2 path."""
+    Q, L = QL
+    lib = _lib.load_library()
+    h = _lib.handle_for(X.device)
+    dt = _lib.dtype_code(X)
+    code = _lib.DQ_CODES[dQ]
+    newton = V is not None
+    H = X
+    if damp:
+        N = tape.randn_like(X)
+        H = X + (damping + torch.finfo(X.dtype).eps * X.abs()) * N
+        if dQ == "EQ" and not newton:
+            V = N                                   # psgd.py:334: the probe is the damping noise
+    if dQ == "QEP":
+        balance_kron_precond(Q)                     # psgd.py:347 / 674
+    Pg = _apply_factors(Q, H) if dQ in ("EQ", "QUAD4P", "PRO4P") else _apply_kron_nd(Q, H)
+    conjB = _solve_factors_nd(Q, V) if dQ == "EQ" else None
+    numel = X.numel()
+    for i, q in enumerate(Q):
+        s, dense = q.shape[0], q.dim() == 2
+        t2 = float(numel / s)
+        src1 = _factor_on_mode(q, Pg, i) if dQ == "QEP" else Pg
+        src2 = conjB if dQ == "EQ" else ((_factor_on_mode(q, V, i) if dQ == "QEP" else V) if newton else None)
+        M1 = _unfold(src1, i)
+        if dense:
+            term1 = gemm(M1, M1, trans_b=True)
+            if src2 is not None:
+                M2 = _unfold(src2, i)
+                term2 = gemm(M2, M2, trans_b=True)
+            else:
+                term2 = gemm(q, q, trans_b=True, alpha=t2) if dQ == "QEP" else None   # psgd.py:361
+            spd = tape.randn(_K_PROBES, s, q)
+            skh = tape.randn(_K_PROBES, s, q) if code == 0 else None
+            ws = torch.empty(lib.psgd_helper_workspace_bytes(h, s, dt), dtype=torch.uint8, device=X.device)
+            rc = lib.psgd_kron_factor_step(h, dt, code, _lib.PSGD_DENSE, s, _lib.ptr(q), _lib.ptr(L[i]), _lib.ptr(term1), _lib.ptr(term2), t2,
+                                           float(lr), float(betaL), _lib.ptr(spd), _lib.ptr(skh), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr(X.device))
+            _lib.check(h, rc, "psgd_kron_factor_step")
+            if dQ == "PRO4P":                        # psgd.py:444-449
+                for _ in range(10):
+                    procrustes_step3(q, V0=tape.randn(_K_PROBES, s, q))
+                    if _almost_symmetric(q):
+                        break
+        else:
+            term1 = torch.sum(M1.float() * M1.float(), dim=1).contiguous()
+            if src2 is not None:
+                M2 = _unfold(src2, i)
+                term2 = torch.sum(M2.float() * M2.float(), dim=1).contiguous()
+            else:
+                term2 = (t2 * q.float() * q.float()).contiguous() if dQ == "QEP" else None   # psgd.py:357
+            rc = lib.psgd_kron_factor_step(h, dt, code, _lib.PSGD_DIAG, s, _lib.ptr(q), _lib.ptr(L[i]), _lib.ptr(term1), _lib.ptr(term2), t2,
+                                           float(lr), float(betaL), None, None, None, 0, _lib.stream_ptr(X.device))
+            _lib.check(h, rc, "psgd_kron_factor_step")
+    if dQ != "QEP" and tape.rand() < 0.01:
+        balance_kron_precond(Q)
 
 
 def update_precond_kron_eq(QL, exprs, V, Hvp, lr=0.1, betaL=0.9, noise=None):

@@ -175,6 +175,9 @@ def geom_cases(dq):
     fn = DQ_FUNCS[dq]
     specs = [("whiten", (24, 40), f32, 3), ("whiten", (8, 300), f32, 3), ("whiten", (300, 8), f32, 2), ("whiten", (50,), f32, 3),
              ("whiten", (136, 200), f32, 2), ("newton", (24, 40), f32, 3), ("newton", (8, 300), f32, 2)]
+    specs += [("whiten", (5, 6, 7), f32, 2)]                                   # order 3: all dense
+    if dq != "PRO4P":   # (PRO4P's data-dependent procrustes_step3 loop makes this one chaotic: two contraction orders differ by 5e-4)
+        specs += [("newton", (3, 4, 30), f32, 2)]                              # order 3: dense, dense, diagonal
     if dq not in ("PRO4P",):
         specs += [("whiten", (24, 40), bf16, 3), ("whiten", (136, 200), bf16, 2), ("newton", (24, 40), bf16, 2)]
     if dq == "Q0.5EQ1.5":

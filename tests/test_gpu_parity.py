@@ -453,11 +453,10 @@ def test_kwns4_state_dict_roundtrip_and_dtensor_variant():
             for i, g in enumerate(grads):
                 if resume_at is not None and i == resume_at:
                     buf = io.BytesIO(); torch.save(opt.state_dict(), buf); buf.seek(0)
-                    rng = (opt.cpu_rng_state.clone(), opt.cuda_rng_state.clone())
                     p2 = torch.nn.Parameter(p.detach().clone())
+                    torch.manual_seed(12345); torch.cuda.manual_seed(12345)   # a resumed process starts from unrelated generator states
                     opt2 = cls([p2], lr_params=1e-2)
-                    opt2.load_state_dict(torch.load(buf, weights_only=False))
-                    opt2.cpu_rng_state, opt2.cuda_rng_state = rng   # the reference does not checkpoint its private RNG states either
+                    opt2.load_state_dict(torch.load(buf, weights_only=False))   # ... the checkpoint carries the private ones ("psgd_rng")
                     p, opt = p2, opt2
                 p.grad = g.to(dev)
                 opt.step()

@@ -146,3 +146,24 @@ def test_kwns4_owner_assignment_is_a_partition(monkeypatch):
     opt2._assign_owners()
     assert [opt2._owner[id(p)] for p in ps] == owners
     assert float(torch.rand([], generator=opt._coin_gen)) == float(torch.rand([], generator=opt2._coin_gen))
+
+
+def test_kwns4_checkpoint_carries_private_rng_states():
+    """state_dict() of a distributed KWNS4 carries the private generator states the reference forgets (ddp.py:92,96); a reference-style
+    checkpoint without them still loads."""
+    import io
+    import torch
+    from psgd_torch_b200 import kwns4
+    p = torch.nn.Parameter(torch.zeros(6, 5))
+    opt = kwns4.KWNS4([p])
+    assert "psgd_rng" not in opt.state_dict()          # single process: no private states, exactly the reference's keys
+    opt.is_distributed, opt.cpu_rng_state, opt.cuda_rng_state = True, torch.get_rng_state(), None
+    sd = opt.state_dict()
+    buf = io.BytesIO(); torch.save(sd, buf); buf.seek(0)
+    torch.manual_seed(987)
+    opt2 = kwns4.KWNS4([torch.nn.Parameter(torch.zeros(6, 5))])
+    opt2.is_distributed, opt2.cpu_rng_state, opt2.cuda_rng_state = True, torch.get_rng_state(), None
+    opt2.load_state_dict(torch.load(buf, weights_only=False))
+    assert torch.equal(opt2.cpu_rng_state, opt.cpu_rng_state)
+    ref_style = {k: v for k, v in sd.items() if k != "psgd_rng"}
+    opt2.load_state_dict(ref_style)
