@@ -172,6 +172,62 @@ __global__ void __launch_bounds__(256) k_lra_sweep1(const T* __restrict__ U, con
   }
 }
 
+// sweep 1 for ranks <= 4 (BASELINE configs[4] sweeps r = 4): the three 4 x 4 Grams, the four projections and the two norms are 66 sums --
+// they fit in one thread's registers, so every thread streams whole rows (8 or 16 bytes each, coalesced across the warp) and the block
+// reduces once at the end.  The tiled kernel above leaves 253 of its 256 threads idle at this rank (3 tiles of 4 x 4): 2.76 ms per 2^24
+// rows against 0.37 GB of compulsory traffic.
+template <typename T>
+__global__ void __launch_bounds__(256) k_lra_sweep1_r4(const T* __restrict__ U, const T* __restrict__ V, const T* __restrict__ d,
+                                                       const T* __restrict__ hvec, const T* __restrict__ vvec, long long n, int r,
+                                                       float* __restrict__ acc_out) {
+  constexpr int RP = 4, NS = 3 * RP * RP + 4 * RP + 2;
+  __shared__ float red[NS];
+  float a[NS];
+#pragma unroll
+  for (int e = 0; e < NS; ++e) a[e] = 0.f;
+  for (int e = threadIdx.x; e < NS; e += blockDim.x) red[e] = 0.f;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < n; row += stride) {
+    float u[RP], w[RP];
+    if (r == RP && sizeof(T) == 2) {   // 8-byte rows
+      const uint2 pu = *reinterpret_cast<const uint2*>(U + row * RP), pw = *reinterpret_cast<const uint2*>(V + row * RP);
+      const T* eu = reinterpret_cast<const T*>(&pu);
+      const T* ew = reinterpret_cast<const T*>(&pw);
+#pragma unroll
+      for (int c = 0; c < RP; ++c) { u[c] = to_f<T>(eu[c]); w[c] = to_f<T>(ew[c]); }
+    } else {
+      load_row<T, RP>(U, row, r, u);
+      load_row<T, RP>(V, row, r, w);
+    }
+    const float dd = to_f<T>(d[row]);
+    const float x1 = to_f<T>(from_f<T>(dd * to_f<T>(hvec[row])));   // d*h   psgd.py:1017
+    const float x2 = to_f<T>(from_f<T>(to_f<T>(vvec[row]) / dd));   // v/d   psgd.py:1022
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+#pragma unroll
+      for (int j = 0; j < RP; ++j) {
+        a[i * RP + j] = fmaf(u[i], u[j], a[i * RP + j]);                       // U^T U
+        a[RP * RP + i * RP + j] = fmaf(w[i], w[j], a[RP * RP + i * RP + j]);   // V^T V
+        a[2 * RP * RP + i * RP + j] = fmaf(w[i], u[j], a[2 * RP * RP + i * RP + j]);   // V^T U
+      }
+      a[3 * RP * RP + i] = fmaf(u[i], x1, a[3 * RP * RP + i]);                 // U^T x1, V^T x1, U^T x2, V^T x2
+      a[3 * RP * RP + RP + i] = fmaf(w[i], x1, a[3 * RP * RP + RP + i]);
+      a[3 * RP * RP + 2 * RP + i] = fmaf(u[i], x2, a[3 * RP * RP + 2 * RP + i]);
+      a[3 * RP * RP + 3 * RP + i] = fmaf(w[i], x2, a[3 * RP * RP + 3 * RP + i]);
+    }
+    a[NS - 2] = fmaf(x1, x1, a[NS - 2]);
+    a[NS - 1] = fmaf(x2, x2, a[NS - 1]);
+  }
+#pragma unroll
+  for (int e = 0; e < NS; ++e) {
+    const float v = warp_sum(a[e]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[e], v);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NS; e += blockDim.x) atomicAdd(&acc_out[e], red[e]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // small kernel: one CTA, all r x r / r-vector algebra in fp32 in shared memory  (psgd.py:1006-1052)
 // ------------------------------------------------------------------------------------------------
@@ -643,6 +699,12 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   } else {
     long long tiles = (n + 63) / 64;
     int grid1 = (int)(tiles < (long long)ctx->num_sms * 2 ? tiles : (long long)ctx->num_sms * 2);
+    if (RP == 4) {   // thread-per-row kernel: everything fits in registers at this rank
+      long long nb = (n + 255) / 256;
+      int gridr = (int)(nb < (long long)ctx->num_sms * 8 ? nb : (long long)ctx->num_sms * 8);
+      if (dt == PSGD_BF16) k_lra_sweep1_r4<bf16><<<gridr, 256, 0, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, r, w.acc);
+      else k_lra_sweep1_r4<float><<<gridr, 256, 0, st>>>((const float*)l->U, (const float*)l->V, (const float*)l->d, (const float*)hv, (const float*)v, n, r, w.acc);
+    } else
     LRA_DISPATCH(dt, RP, (k_lra_sweep1<T, R_><<<grid1, 256, 0, st>>>((const T*)l->U, (const T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.acc)));
     ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep1"); if (rc) return rc;
   }
