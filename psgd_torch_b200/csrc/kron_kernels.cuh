@@ -252,21 +252,6 @@ __global__ void __launch_bounds__(1024) k_probe_init(const T* __restrict__ A, in
   }
 }
 
-// sc[p] = inv_nf / (sqrt(rn[p]) + tiny): normalisation of psgd.py:66 folded with the /nf of the next product
-__global__ void k_rowscale(const float* __restrict__ rn, const float* __restrict__ scal, float tiny, float* sc, int k) {
-  int p = threadIdx.x;
-  // rn == 0 means the whole probe row is exactly zero (e.g. R = Q^T - Q = 0 while Q is still symmetric): the reference
-  // computes 0/(0+tiny) = 0 there; keep the folded factor finite so that 0 * factor stays 0 instead of 0 * inf = NaN
-  if (p < k) sc[p] = fminf(scal[SC_INV_NF] / (sqrtf(rn[p]) + tiny), 3.0e38f);
-}
-
-// bound = nf * max_p sqrt(rn[p])   psgd.py:68.  mode 0: just store.  One warp.
-__global__ void k_bound_final(const float* __restrict__ rn, int k, float* scal, int dtype) {
-  float v = threadIdx.x < k ? rn[threadIdx.x] : 0.f;
-  v = warp_max(v);
-  if (threadIdx.x == 0) scal[SC_BOUND] = round_to(dtype, scal[SC_NF] * round_to(dtype, sqrtf(v)));
-}
-
 // bound = nf * max_p sqrt(rn[p]) (psgd.py:68) fused with its consumer:
 //   mode 0: dense-factor L update + step size (psgd.py:412-415): fs[FS_ALPHA] = -lr/L, fs[FS_BETA] = 1 + lr/L*t2
 //   mode 1: procrustes normaliser (psgd.py:118): fs[FS_INV_SR] = 1 / (bound + tiny)
@@ -288,26 +273,6 @@ __global__ void k_bound_finish(const float* __restrict__ rn, int k, float* scal,
       fs[FS_INV_SR] = 1.f / (bound + tiny);
     }
   }
-}
-
-// dense factor: ell = bound + t2; L = max(betaL*L + (1-betaL)*ell, ell); c = lr/L   psgd.py:412-415
-//   fs[FS_ALPHA] = -c, fs[FS_BETA] = 1 + c*t2   so that  Q' = beta*Q + alpha*(term1 @ Q)
-__global__ void k_dense_L_update(const float* __restrict__ bound_scal, float t2, float lr, float betaL, float* L, float* fs,
-                                 int dtype) {
-  if (threadIdx.x == 0) {
-    float ell = round_to(dtype, bound_scal[SC_BOUND] + t2);
-    float Lo = *L;
-    float Ln = fmaxf(betaL * Lo + (1.f - betaL) * ell, ell);
-    *L = Ln;
-    float c = lr / Ln;
-    fs[FS_ALPHA] = -c;
-    fs[FS_BETA] = 1.f + c * t2;
-  }
-}
-
-// inv_sR = 1 / (bound(R) + tiny)    psgd.py:118
-__global__ void k_procrustes_scal(const float* __restrict__ bound_scal, float tiny, float* fs) {
-  if (threadIdx.x == 0) fs[FS_INV_SR] = 1.f / (bound_scal[SC_BOUND] + tiny);
 }
 
 // a = tr_RRQ < 0 ? min(-tr_RQ/tr_RRQ, max_step) : max_step;  Q = Qn + a*(RQ + 0.5*a*RRQ)   psgd.py:121-124

@@ -551,142 +551,6 @@ __global__ void __launch_bounds__(256) k_lra_apply_bf16(const bf16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// apply sweeps through a cp.async ring (same math as k_lra_apply_bf16; the direct-load version leaves too few bytes in flight per SM:
-// 3.2-3.8 TB/s in profiles/r01_launches_lra_*.csv).  Each warp streams 32-row chunks of ONE factor (rows are contiguous: a chunk is a
-// single 32*RP*2-byte block) plus the chunk's d and g (or fp32 g2) values; 8 stages x 8 warps keep > 100 KB in flight per SM.
-// ------------------------------------------------------------------------------------------------
-template <int RP>
-__global__ void __launch_bounds__(256, 1) k_lra_apply_ring(const bf16* __restrict__ Mtx, const bf16* __restrict__ d, const bf16* __restrict__ g,
-                                                           float* __restrict__ g2, bf16* __restrict__ out, long long n, int mode,
-                                                           const float* __restrict__ pin, float* __restrict__ pout, float* sumsq) {
-  constexpr int ROWS = 32;
-  constexpr int PPR = RP / 8;                   // 16-byte pieces per row
-  constexpr int NP = ROWS * PPR / 32;           // matrix pieces per lane (4 for RP=32, 2 for RP=16)
-  constexpr int MAT_BYTES = ROWS * RP * 2;
-  constexpr int VEC_OFF = MAT_BYTES;            // d[32] bf16 (64 B) | g[32] bf16 (64 B) | g2[32] fp32 (128 B)
-  constexpr int TILE = MAT_BYTES + 256;
-  constexpr int STAGES = 8;
-  extern __shared__ __align__(128) uint8_t smem_lra[];
-  __shared__ float pacc[RP];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int piece = lane % PPR;
-  if (threadIdx.x < RP) pacc[threadIdx.x] = 0.f;
-  float pv[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) pv[c] = (mode > 0) ? pin[piece * 8 + c] : 0.f;
-  __syncthreads();
-  float acc[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-  float ssq = 0.f;
-  uint8_t* ring_gen = smem_lra + warp * STAGES * TILE;
-  const uint32_t ring = smem_u32_generic(ring_gen);
-  const long long nchunks = (n + ROWS - 1) / ROWS;
-  const long long gw = (long long)blockIdx.x * 8 + warp, tw = (long long)gridDim.x * 8;
-
-  auto issue = [&](long long ck, int st) {
-    const uint32_t tile = ring + st * TILE;
-    const long long r0 = ck * ROWS;
-    const long long rows_valid = (n - r0) < ROWS ? (n - r0) : ROWS;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      const int p = lane + 32 * i;
-      const bool ok = (p / PPR) < rows_valid;
-      cp_async16(tile + p * 16, ok ? (const void*)(Mtx + r0 * RP + p * 8) : (const void*)Mtx, ok ? 16 : 0);
-    }
-    if (lane < 16) {
-      // lanes 0-3: d, lanes 4-7: g (modes 0, 1), lanes 8-15: g2 (mode 2)
-      const int grp = lane < 4 ? 0 : (lane < 8 ? 1 : 2);
-      const int k = lane < 4 ? lane : (lane < 8 ? lane - 4 : lane - 8);
-      if (grp == 0 || (grp == 1 && mode < 2) || (grp == 2 && mode == 2)) {
-        const int elems = grp == 2 ? 4 : 8;                       // elements per 16-byte piece
-        long long valid = (rows_valid - (long long)k * elems) * (grp == 2 ? 4 : 2);
-        valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
-        const void* src = grp == 0 ? (const void*)(d + r0 + k * 8) : (grp == 1 ? (const void*)(g + r0 + k * 8) : (const void*)(g2 + r0 + k * 4));
-        const uint32_t dst = tile + VEC_OFF + (grp == 0 ? 0 : (grp == 1 ? 64 : 128)) + k * 16;
-        cp_async16(dst, valid > 0 ? src : (const void*)Mtx, (int)valid);
-      }
-    }
-  };
-
-  long long ck_issue = gw;
-#pragma unroll 1
-  for (int s0 = 0; s0 < STAGES - 1; ++s0) {
-    if (ck_issue < nchunks) issue(ck_issue, s0);
-    cp_async_commit();
-    ck_issue += tw;
-  }
-  int stage = 0;
-  for (long long ck = gw; ck < nchunks; ck += tw) {
-    {
-      const int s_issue = (stage + STAGES - 1) % STAGES;
-      if (ck_issue < nchunks) issue(ck_issue, s_issue);
-      cp_async_commit();
-      ck_issue += tw;
-    }
-    cp_async_wait<STAGES - 1>();
-    __syncwarp();
-    const uint8_t* tile = ring_gen + stage * TILE;
-    const bf16* dv = reinterpret_cast<const bf16*>(tile + VEC_OFF);
-    const bf16* gv = reinterpret_cast<const bf16*>(tile + VEC_OFF + 64);
-    const float* g2v = reinterpret_cast<const float*>(tile + VEC_OFF + 128);
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      const int p = lane + 32 * i;
-      const int lrow = p / PPR;
-      const long long row = ck * ROWS + lrow;
-      const bool ok = row < n;
-      const uint4 raw = *reinterpret_cast<const uint4*>(tile + p * 16);
-      float x[8];
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { float2 f = __bfloat1622float2(h2[c]); x[2 * c] = f.x; x[2 * c + 1] = f.y; }
-      const float dd = ok ? __bfloat162float(dv[lrow]) : 0.f;
-      if (mode == 0) {
-        const float y = ok ? __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(gv[lrow]))) : 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(x[c], y, acc[c]);
-      } else {
-        float dot = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) dot = fmaf(x[c], pv[c], dot);
-#pragma unroll
-        for (int o = 1; o < PPR; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (mode == 1) {
-          const float y = ok ? __bfloat162float(__float2bfloat16_rn(dd * __bfloat162float(gv[lrow]))) + dot : 0.f;
-          if (ok && piece == 0) g2[row] = y;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] = fmaf(x[c], y, acc[c]);
-        } else {
-          if (ok && piece == 0) {
-            const bf16 o = __float2bfloat16_rn(dd * (g2v[lrow] + dot));
-            out[row] = o;
-            const float f = __bfloat162float(o);
-            ssq = fmaf(f, f, ssq);
-          }
-        }
-      }
-    }
-    __syncwarp();
-    stage = (stage + 1) % STAGES;
-  }
-  cp_async_wait<0>();
-  if (mode < 2) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float v = acc[c];
-#pragma unroll
-      for (int o = PPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane < PPR) atomicAdd(&pacc[piece * 8 + c], v);
-    }
-    __syncthreads();
-    if (threadIdx.x < RP) atomicAdd(&pout[threadIdx.x], pacc[threadIdx.x]);
-  } else if (sumsq) {
-    float v = warp_sum(ssq);
-    if (lane == 0) atomicAdd(sumsq, v);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // apply sweeps fed by the bulk-copy engine: one producer thread issues cp.async.bulk (TMA 1-D) copies of whole 256-row blocks of the
 // factor (16 KB for r = 32) plus the block's d / g / g2 slices into an 8-stage mbarrier ring; 8 consumer warps do the row dot products
