@@ -167,3 +167,113 @@ def test_kwns4_checkpoint_carries_private_rng_states():
     assert torch.equal(opt2.cpu_rng_state, opt.cpu_rng_state)
     ref_style = {k: v for k, v in sd.items() if k != "psgd_rng"}
     opt2.load_state_dict(ref_style)
+
+
+# ---- the collective choreography of the row-sharded LRA preconditioner (lra_sharded.ShardedLRA) under gloo, world_size 2 ----
+# The engine stages are replaced by a CPU stand-in with the same data flow (stage 1: per-row sums that must be SUM-reduced; stage 2: a row
+# update that needs the reduced sums and leaves two per-shard maxima that must be MAX-reduced; stage 4: a row update that needs the
+# reduced maxima; apply: two projections SUM-reduced between three row passes, and a global sum of squares).  What is under test is the
+# host logic the GPU box cannot show on one device: which buffers are reduced, with which operation, in which order, and the agreement
+# on the CPU coin.  (The arithmetic of the real stages is checked on the GPU: tests/test_gpu_sharded_lra.py, tools/check_sharded_lra.py.)
+def _make_cpu_stage_class():
+    from psgd_torch_b200.lra_sharded import ShardedLRA, ST_SWEEP1, ST_SWEEP2, ST_FINISH
+
+    class CpuStages(ShardedLRA):
+        def __init__(self, UVd, group=None):
+            self.UVd, self.Luvd, self.group = UVd, None, group
+            self.dev = torch.device("cpu")
+            r = UVd[0].shape[1]
+            self._views = [torch.zeros(2 * r + 1), torch.zeros(2), torch.zeros(r), torch.zeros(r)]
+            self._sumsq = torch.zeros(1)
+            self.coin_seen = None
+
+        def update_stage(self, stages, gh, v, lr, betaL, damping, whiten, update_U):
+            U, V, d = self.UVd
+            if stages == ST_SWEEP1:
+                self.coin_seen = update_U
+                self.sums.copy_(torch.cat([(U * gh).sum(0), (V * v).sum(0), (gh * gh).sum().reshape(1)]))
+            elif stages == ST_SWEEP2:
+                r = U.shape[1]
+                su, sv, sq = self.sums[:r], self.sums[r:2 * r], self.sums[2 * r]
+                (U if update_U else V).add_(lr * gh * (su if update_U else sv) / (1.0 + sq))
+                self._dd = (U * su).sum(1, keepdim=True) - (V * sv).sum(1, keepdim=True)
+                self.maxima.copy_(torch.stack([self._dd.abs().max(), (v * d).abs().max()]))
+            elif stages == ST_FINISH:
+                d.sub_(lr / (self.maxima[0] + self.maxima[1]) * self._dd * d)
+
+        def apply_stage(self, modes, g, out):
+            U, V, d = self.UVd
+            if modes == 1:
+                self.proj1.copy_((V * (d * g)).sum(0)); self.proj2.zero_(); self._sumsq.zero_()
+            elif modes == 2:
+                self._y = d * g + U @ self.proj1.reshape(-1, 1)
+                self.proj2.copy_((U * self._y).sum(0))
+            else:
+                out.copy_(d * (self._y + V @ self.proj2.reshape(-1, 1)))
+                self._sumsq.copy_((out * out).sum().reshape(1))
+
+    return CpuStages
+
+
+def _lra_inputs(n, r):
+    g = torch.Generator().manual_seed(17)
+    U, V = 0.1 * torch.randn(n, r, generator=g), 0.1 * torch.randn(n, r, generator=g)
+    d = 1.0 + 0.1 * torch.rand(n, 1, generator=g)
+    steps = [(torch.randn(n, 1, generator=g), torch.randn(n, 1, generator=g)) for _ in range(3)]
+    return U, V, d, steps
+
+
+def _lra_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from psgd_torch_b200 import partition
+    Cls = _make_cpu_stage_class()
+    n, r = 1000, 4
+    U, V, d, steps = _lra_inputs(n, r)
+    lo, hi = partition.row_shard(n, world, rank, align=8)
+    sh = Cls([U[lo:hi].clone(), V[lo:hi].clone(), d[lo:hi].clone()])
+    torch.manual_seed(1000 + rank)          # different CPU generators: the coin must still agree (rank 0's draw)
+    outs, coins = [], []
+    for g, v in steps:
+        coin = sh._agree(bool(torch.rand([]) < 0.5))
+        coins.append(coin)
+        sh._update(g[lo:hi], v[lo:hi], 0.1, 0.9, 0.0, True, coin)
+        ssq = torch.zeros(1)
+        outs.append((sh.precond_grad_lra(g[lo:hi], sumsq_out=ssq), float(ssq)))
+    q.put((rank, lo, hi, [x.clone() for x in sh.UVd], [(o.clone(), s_) for o, s_ in outs], coins))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_lra_choreography():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_lra_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][5] == res[1][5], "every rank must use rank 0's coin (psgd.py:1035)"
+    coins = res[0][5]
+    # single-process run of the same stand-in on all rows with the same coins
+    Cls = _make_cpu_stage_class()
+    n, r = 1000, 4
+    U, V, d, steps = _lra_inputs(n, r)
+    whole = Cls([U.clone(), V.clone(), d.clone()])
+    wouts = []
+    for (g, v), coin in zip(steps, coins):
+        whole._update(g, v, 0.1, 0.9, 0.0, True, coin)
+        ssq = torch.zeros(1)
+        wouts.append((whole.precond_grad_lra(g, sumsq_out=ssq), float(ssq)))
+    for k in range(3):
+        got = torch.cat([res[0][3][k], res[1][3][k]])
+        assert torch.allclose(got, whole.UVd[k], rtol=1e-5, atol=1e-6), k
+    for i, (wo, ws_) in enumerate(wouts):
+        got = torch.cat([res[0][4][i][0], res[1][4][i][0]])
+        assert torch.allclose(got, wo, rtol=1e-4, atol=1e-4)     # fp32 partial sums in a different order
+        assert abs(res[0][4][i][1] - ws_) < 1e-4 * abs(ws_) and abs(res[1][4][i][1] - ws_) < 1e-4 * abs(ws_)   # global sum of squares on every rank
