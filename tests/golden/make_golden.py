@@ -224,6 +224,38 @@ def geom_cases(dq):
     torch.save(out, os.path.join(OUT, f"geom_{fn}.pt"))
 
 
+def rosenbrock(x):
+    f = x.reshape(-1)
+    x1, x2 = f[0::2], f[1::2]
+    return torch.sum(100.0 * (x2 - x1 ** 2) ** 2 + (1.0 - x1) ** 2)
+
+
+CLOSURE_CASES = [   # (class, kwargs): loss trajectories of the reference's closure-style optimizers on Rosenbrock (10x10 + 6 parameters), CPU fp32
+    ("KronWhiten", dict(preconditioner_init_scale=None, lr_params=0.02, lr_preconditioner=0.3, momentum=0.9, dQ="Q0.5EQ1.5")),
+    ("KronWhiten", dict(preconditioner_init_scale=1.0, lr_params=0.02, lr_preconditioner=0.3, momentum=0.9, whiten_grad=False, dQ="EQ",
+                        update_preconditioner_first=False, preconditioner_update_probability=0.7)),
+    ("KronWhiten", dict(preconditioner_init_scale=None, lr_params=0.02, lr_preconditioner=0.2, dQ="QUAD4P")),
+    ("KronNewton", dict(preconditioner_init_scale=None, lr_params=0.3, lr_preconditioner=0.3, grad_clip_max_norm=1.0, dQ="Q0.5EQ1.5")),
+    ("KronNewton", dict(preconditioner_init_scale=0.1, lr_params=0.3, lr_preconditioner=0.3, grad_clip_max_norm=1.0, momentum=0.5, dQ="QEP",
+                        exact_hessian_vector_product=False, preconditioner_update_probability=0.8)),
+    ("LRAWhiten", dict(rank_of_approximation=5, preconditioner_init_scale=None, lr_params=0.02, lr_preconditioner=0.3, momentum=0.9)),
+    ("LRANewton", dict(rank_of_approximation=5, preconditioner_init_scale=0.1, lr_params=0.3, lr_preconditioner=0.3, grad_clip_max_norm=1.0)),
+]
+
+
+def closure_cases(steps=40):
+    """The reference's KronWhiten / KronNewton / LRAWhiten / LRANewton (psgd.py:516-654, 832-978, 1075-1330), unmodified, on CPU."""
+    out = []
+    for name, kw in CLOSURE_CASES:
+        torch.manual_seed(2024)
+        xs = [torch.zeros(10, 10, requires_grad=True), torch.full((6,), 0.5, requires_grad=True)]
+        opt = getattr(ref, name)(xs, **kw)
+        losses = [float(opt.step(lambda: rosenbrock(xs[0]) + rosenbrock(xs[1]))) for _ in range(steps)]
+        print(f"closure {name:10s} {kw.get('dQ', 'LRA'):10s}: loss {losses[0]:.4e} -> {losses[-1]:.4e}")
+        out.append({"cls": name, "kw": kw, "losses": losses, "x": [x.detach().clone() for x in xs]})
+    torch.save(out, os.path.join(OUT, "closures.pt"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # deterministic reduction order
     f32, bf16 = torch.float32, torch.bfloat16
@@ -247,3 +279,4 @@ if __name__ == "__main__":
                weight_decay=0.0, update_preconditioner_first=False)
     for dq in DQ_FUNCS:
         geom_cases(dq)
+    closure_cases()
