@@ -368,16 +368,12 @@ def update_precond_kron_whiten(dQ, QL, G, tape, lr=0.1, betaL=0.9, damping=1e-9)
     if dQ == "QEP":  # psgd.py:339-364
         balance_kron_precond(Q)
         Pg = precond_grad_kron(Q, _damped(G, damping, tape))
-        QPg = None
-
-        def term2_of(i, q, dense):
-            return (numel / q.numel() * q * q, False) if not dense else (numel / q.shape[0] * q @ q.T, False)
-        # term1 uses exprQs[i](q, Pg) with the factor as it is when its turn comes (earlier factors already updated, Pg fixed)
+        # term1 uses exprQs[i](q, Pg) with the factor as it is when its turn comes (Pg stays fixed)
         for i, q in enumerate(Q):
             dense = q.dim() >= 2
             QPg = _mode_apply(q, Pg, i, transpose=False)
             term1 = _gram(QPg, i, dense)
-            term2, _ = term2_of(i, q, dense)
+            term2 = numel / q.shape[0] * q @ q.T if dense else numel / q.numel() * q * q   # psgd.py:357 / 361
             if not dense:
                 ell = torch.max(term1 + term2)
                 L[i].copy_(torch.max(betaL * L[i] + (1 - betaL) * ell, ell))
