@@ -180,10 +180,15 @@ class NoiseTape:
     """Records (items=None) or replays (items=list) the random draws of one update, in draw order.
     Record mode draws from the torch global generators exactly where the reference does."""
 
-    def __init__(self, items=None):
+    def __init__(self, items=None, rounds=None):
         self.replay = items is not None
         self.items = list(items) if items is not None else []
         self.pos = 0
+        # PRO4P only: procrustes_step3 round counts per dense factor (psgd.py:444-449).  Record mode notes the counts the
+        # stopping test produced; a replay constructed with `rounds` performs exactly those counts and skips the test (in
+        # bf16 the test's outcome is rounding dependent, so step-wise parity needs the count pinned).
+        self.fixed_rounds = list(rounds) if rounds is not None else None
+        self.rounds = []
 
     def _next(self, make):
         if self.replay:
@@ -350,10 +355,14 @@ def _mul_diag(q, c, term1, term2):
 def _pro4p_after(tape):
     def after(q):
         """psgd.py:444-449: up to ten procrustes_step3 rotations, stop once q is almost symmetric (host-side branch)."""
-        for _ in range(10):
+        fixed = tape.fixed_rounds.pop(0) if tape.fixed_rounds is not None else None
+        done = 0
+        for _ in range(10 if fixed is None else fixed):
             procrustes_step3(q, tape.randn(32, q.shape[1], q))
-            if (q.T - q).abs().amax() < 0.001 * q.abs().amax():
+            done += 1
+            if fixed is None and (q.T - q).abs().amax() < 0.001 * q.abs().amax():
                 break
+        tape.rounds.append(done)
     return after
 
 
@@ -535,6 +544,19 @@ def update_precond_lra_whiten(UVd, Luvd, g, noise, lr=0.1, betaL=0.9, damping=1e
     v = noise["v"]
     damp = damping + torch.finfo(g.dtype).eps * g.abs()
     update_precond_lra(UVd, Luvd, v, g + damp * v, lr=lr, betaL=betaL, update_U=noise["update_U"])
+
+
+def draw_lra_newton_noise(h):
+    """RNG order of update_precond_lra_newton: randn_like(h) psgd.py:1198, torch.rand([]) psgd.py:1035."""
+    z = torch.randn_like(h)
+    update_U = bool(torch.rand([]) < 0.5)
+    return {"z": z, "update_U": update_U}
+
+
+def update_precond_lra_newton(UVd, Luvd, v, h, noise, lr=0.1, betaL=0.9, damping=1e-9):
+    """psgd.py:1193-1198: the pair (v, h) with independent damping noise z on the Hessian-vector product."""
+    damp = damping + torch.finfo(h.dtype).eps * h.abs()
+    update_precond_lra(UVd, Luvd, v, h + damp * noise["z"], lr=lr, betaL=betaL, update_U=noise["update_U"])
 
 
 # --------------------------------------------------------------------------------------

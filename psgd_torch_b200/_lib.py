@@ -73,6 +73,7 @@ SYMBOLS = {
     "psgd_lra_workspace_bytes": (_sz, [_vp, C.POINTER(LraT)]),
     "psgd_lra_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _i, _vp, _sz, _vp]),
     "psgd_lra_whiten_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _f, _i, _vp, _sz, _vp]),
+    "psgd_lra_newton_update": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _vp, _f, _f, _f, _i, _vp, _sz, _vp]),
     "psgd_lra_precond_grad": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _vp, _vp, _sz, _vp]),
     "psgd_lra_workspace_offsets": (_i, [_vp, C.POINTER(LraT), C.POINTER(_sz), C.POINTER(_sz)]),
     "psgd_lra_update_staged": (_i, [_vp, C.POINTER(LraT), _vp, _vp, _f, _f, _f, _i, _i, _i, _vp, _sz, _vp]),
@@ -80,6 +81,7 @@ SYMBOLS = {
     "psgd_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _f, _vp, _i, _f, _vp]),
     "psgd_timing_enable": (_i, [_vp, _i]),
     "psgd_timing_read": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "psgd_timing_gemm_launches": (_i64, [_vp]),
     "psgd_timing_executed_flops": (C.c_double, [_vp]),
     "psgd_debug_set_flags": (_i, [_vp, _i]),
     "psgd_debug_set_tile_n": (_i, [_vp, _i]),
@@ -123,31 +125,42 @@ def check(handle, rc, what):
         raise EngineError(f"{what} failed: {msg} ({rc}) {extra}")
 
 
-def handle_for(device):
-    """One engine context per CUDA device."""
-    lib = load_library()
+def _dev_index(device):
     dev = torch.device(device)
     if dev.type != "cuda":
         raise EngineError(f"psgd_torch_b200 runs on CUDA (sm_100a) tensors only, got a tensor on '{dev}'")
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    h = _handles.get(idx)
+    if idx != torch.cuda.current_device():
+        # kernels launch on the process's current device: a tensor of another device would be handed to the wrong GPU
+        raise EngineError(f"tensor lives on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}: wrap the call in "
+                          f"`with torch.cuda.device({idx}):` (one process per GPU is the supported layout)")
+    return idx
+
+
+def handle_for(device):
+    """One engine context per (CUDA device, current stream).  A context owns the split-K partial-tile buffer and arrival counters of the
+    tcgen05 GEMM, which assume stream order between the launches that share them, so calls issued on different streams get different
+    contexts (42 MB each) instead of racing on one."""
+    lib = load_library()
+    idx = _dev_index(device)
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    h = _handles.get(key)
     if h is None:
         with _lock:
-            h = _handles.get(idx)
+            h = _handles.get(key)
             if h is None:
                 out = C.c_void_p()
                 rc = lib.psgd_create(C.byref(out), idx)
                 check(None, rc, f"psgd_create(device={idx})")
                 h = out
-                _handles[idx] = h
+                _handles[key] = h
     return h
 
 
 def workspace(device, nbytes):
-    """A per-device scratch tensor, grown geometrically; all engine calls on a device are stream-ordered on the
-    current stream, so one buffer per (device, stream) is enough."""
-    dev = torch.device(device)
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    """A scratch tensor per (device, current stream), grown geometrically: engine calls on one stream are stream-ordered, so they can
+    share one buffer; calls on different streams never do (same keying as handle_for)."""
+    idx = _dev_index(device)
     key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -187,6 +200,10 @@ def set_fp32_tensor_cores(on, device=None):
 
 
 def launch_count(device=None):
+    """Kernels launched so far by every context of `device` (all devices if None)."""
+    lib = load_library()
     if device is None:
-        return sum(load_library().psgd_launch_count(h) for h in _handles.values())
-    return load_library().psgd_launch_count(handle_for(device))
+        return sum(lib.psgd_launch_count(h) for h in _handles.values())
+    idx = _dev_index(device)
+    handle_for(device)
+    return sum(lib.psgd_launch_count(h) for (i, _), h in _handles.items() if i == idx)

@@ -543,8 +543,14 @@ int psgd_set_fp32_tensor_cores(psgd_handle_t h, int on) {
 int psgd_timing_enable(psgd_handle_t h, int on) {
   Ctx* ctx = reinterpret_cast<Ctx*>(h);
   if (!ctx) return PSGD_ERR_INVALID_ARG;
+  const int want = on > 1 ? on : 8192;      // on > 1: size of the event pool (launches that can be timed between two resets)
+  if (on && ctx->ev_begin && ctx->ev_capacity < want) {
+    for (int i = 0; i < ctx->ev_capacity; ++i) { cudaEventDestroy(ctx->ev_begin[i]); cudaEventDestroy(ctx->ev_end[i]); }
+    delete[] ctx->ev_begin; delete[] ctx->ev_end;
+    ctx->ev_begin = nullptr; ctx->ev_end = nullptr;
+  }
   if (on && !ctx->ev_begin) {
-    ctx->ev_capacity = 8192;
+    ctx->ev_capacity = want;
     ctx->ev_begin = new (std::nothrow) cudaEvent_t[ctx->ev_capacity];
     ctx->ev_end = new (std::nothrow) cudaEvent_t[ctx->ev_capacity];
     if (!ctx->ev_begin || !ctx->ev_end) return PSGD_ERR_CUDA;
@@ -552,6 +558,7 @@ int psgd_timing_enable(psgd_handle_t h, int on) {
   }
   ctx->timing_on = on ? 1 : 0;
   ctx->timing_count = 0;
+  ctx->timing_seen = 0;
   ctx->timing_flops = 0.0;
   ctx->timing_flops_exec = 0.0;
   return PSGD_OK;
@@ -569,6 +576,8 @@ int psgd_timing_read(psgd_handle_t h, int* launches, double* total_ms, double* f
   *launches = ctx->timing_count; *total_ms = ms; *flops = ctx->timing_flops;
   return PSGD_OK;
 }
+
+int64_t psgd_timing_gemm_launches(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->timing_seen : 0; }
 
 double psgd_timing_executed_flops(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->timing_flops_exec : 0.0; }
 

@@ -154,6 +154,7 @@ struct Ctx {
   // optional per-launch timing of the tcgen05 GEMM kernel (bench.py roofline): CUDA events on the launching stream
   int timing_on;
   int timing_count;      // event pairs recorded since the last reset
+  int64_t timing_seen;   // tcgen05 GEMM launches since the last reset (recorded or not: the event pool is finite)
   double timing_flops;   // algorithmic FLOPs (2*M*N*K, true sizes) of the recorded launches
   double timing_flops_exec;  // FLOPs the tensor cores actually executed for them (tile-padded, upper-blocks-only for symmetric products)
   cudaEvent_t* ev_begin;
@@ -167,6 +168,18 @@ struct Ctx {
   void* x3_buf[2];
   size_t x3_cap[2];
   int fp32_tensor;   // opt-in (psgd_set_fp32_tensor_cores): big fp32 products as bf16 triples on the tensor cores
+};
+
+// cudaFuncSetAttribute acts on the current device's context: one "already done" flag per (call site, device) for processes that drive
+// several GPUs (the supported layout is one process per GPU, where this is a single flag)
+struct PerDeviceOnce {
+  bool done[64];
+  bool need(int dev) {
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
 };
 
 // one GEMM problem: C = epi(op(A) op(B)), op(A) M x K, op(B) K x N

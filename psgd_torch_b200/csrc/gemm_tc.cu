@@ -1064,15 +1064,14 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
   grp.error_flag = nullptr;
   grp.ws = ctx->ws;
   grp.ws_count = ctx->ws_count;
-  static bool attr_set[2] = {false, false};
-  const int ai = (BN == 256) ? 0 : 1;
-  if (!attr_set[ai]) {
+  static PerDeviceOnce attr_set;   // one per instantiation
+  if (attr_set.need(ctx->device)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(gemm_tc)");
-    attr_set[ai] = true;
   }
   int grid = units < sms ? units : sms;
-  const bool timed = ctx->timing_on && BN == 256 && ctx->timing_count < ctx->ev_capacity;
+  const bool timed = ctx->timing_on && ctx->timing_count < ctx->ev_capacity;
+  if (ctx->timing_on) ctx->timing_seen++;
   if (timed) cudaEventRecord(ctx->ev_begin[ctx->timing_count], st);
   gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
   if (timed) {
@@ -1168,15 +1167,15 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
   grp.mn_lbo = ctx->mn_lbo;
   grp.mn_sbo = ctx->mn_sbo;
   grp.error_flag = nullptr;
-  static bool attr_set = false;   // one flag per instantiation
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;   // one per instantiation
+  if (attr_set.need(ctx->device)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(gemm_tc2)");
-    attr_set = true;
   }
   const int max_pairs = ctx->num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   const bool timed = ctx->timing_on && ctx->timing_count < ctx->ev_capacity;
+  if (ctx->timing_on) ctx->timing_seen++;
   if (timed) cudaEventRecord(ctx->ev_begin[ctx->timing_count], st);
   gemm_tc2_kernel<BN><<<2 * pairs, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(grp);
   if (timed) {

@@ -123,7 +123,7 @@ constexpr int TRI_TC_MIN_B = 512;
 struct TriJob { const void* Q; int s; TriWs* t; };
 
 static int run_tri_inverse(Ctx* ctx, int dt, const TriJob* jobs, int nj, cudaStream_t st) {
-  static bool attr_done[2] = {false, false};
+  static PerDeviceOnce attr_done[2];
   int rc;
   int smax = 0;
   for (int jx = 0; jx < nj; ++jx) {
@@ -133,10 +133,9 @@ static int run_tri_inverse(Ctx* ctx, int dt, const TriJob* jobs, int nj, cudaStr
     if (s > smax) smax = s;
     rc = check_cuda(ctx, cudaMemsetAsync(t.Xf, 0, (size_t)s * s * 4, st), "memset"); if (rc) return rc;
     const int ai = dt == PSGD_BF16 ? 0 : 1;
-    if (!attr_done[ai]) {
+    if (attr_done[ai].need(ctx->device)) {
       if (dt == PSGD_BF16) cudaFuncSetAttribute(k_tri_inv_leaf<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_LEAF_SMEM);
       else cudaFuncSetAttribute(k_tri_inv_leaf<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_LEAF_SMEM);
-      attr_done[ai] = true;
     }
     DISPATCH_T(dt, (k_tri_inv_leaf<T><<<(s + TRI_NB - 1) / TRI_NB, 256, TRI_LEAF_SMEM, st>>>((const T*)J.Q, s, t.Xf)));
     LAUNCH_CHECK(ctx, "k_tri_inv_leaf");

@@ -685,13 +685,12 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   } else if (mma_path) {
     long long chunks = (n + 15) / 16;
     int grid1 = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
-    static bool attr_g = false;
-    if (!attr_g) {
+    static PerDeviceOnce attr_g;
+    if (attr_g.need(ctx->device)) {
       cudaFuncSetAttribute(k_lra_gram_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
       cudaFuncSetAttribute(k_lra_gram_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
       cudaFuncSetAttribute(k_lra_rotate_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
       cudaFuncSetAttribute(k_lra_rotate_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
-      attr_g = true;
     }
     if (r == 32) k_lra_gram_mma<32><<<grid1, 256, smem_mma, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.acc);
     else k_lra_gram_mma<16><<<grid1, 256, smem_mma, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.acc);
@@ -711,8 +710,8 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   float* scal = w.par + lra_par_scal_off(RP);
   if (stages & LRA_ST_SWEEP2) {
   size_t smem_small = ((size_t)8 * RP * RP + 24 * RP) * 4;
-  static bool small_attr = false;
-  if (!small_attr) { cudaFuncSetAttribute(k_lra_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); small_attr = true; }
+  static PerDeviceOnce small_attr;
+  if (small_attr.need(ctx->device)) cudaFuncSetAttribute(k_lra_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   k_lra_small<<<1, 256, smem_small, st>>>(w.acc, w.par, r, RP, lr, betaL, update_U, l->Lu, l->Lv, dt);
   ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_small"); if (rc) return rc;
   long long rows_blocks = (n + 127) / 128;
@@ -724,8 +723,8 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
     if (r == 32) k_lra_rotate_mma<32><<<gridr, 256, smem_mma, st>>>((bf16*)l->U, (bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.par, update_U, w.dd, scal);
     else k_lra_rotate_mma<16><<<gridr, 256, smem_mma, st>>>((bf16*)l->U, (bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.par, update_U, w.dd, scal);
   } else LRA_DISPATCH(dt, RP, {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_lra_sweep2<T, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) cudaFuncSetAttribute(k_lra_sweep2<T, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     k_lra_sweep2<T, R_><<<grid2, 128, smem2, st>>>((T*)l->U, (T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.par, update_U, w.dd, scal);
   });
   ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep2"); if (rc) return rc;
@@ -782,6 +781,25 @@ int psgd_lra_whiten_update(psgd_handle_t h, const psgd_lra_t* l, const void* g, 
   return lra_update_impl(ctx, l, v, w.hbuf, lr, betaL, update_U, w, st);
 }
 
+// psgd.py:1193-1198: the pair (v, hvp) with independent damping noise z on the Hessian-vector product: h = hvp + (damping + eps|hvp|) z
+int psgd_lra_newton_update(psgd_handle_t h, const psgd_lra_t* l, const void* v, const void* hvp, const void* z, float lr, float betaL,
+                           float damping, int update_U, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !v || !hvp || !z) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_lra(l); if (rc) return rc;
+  if (!l->Lu || !l->Lv || !l->Ld) return PSGD_ERR_INVALID_ARG;
+  LraWs w;
+  layout_lra(l, workspace, w);
+  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = l->n;
+  int grid = (int)(((n + 255) / 256) < (long long)ctx->num_sms * 8 ? ((n + 255) / 256) : (long long)ctx->num_sms * 8);
+  if (l->dtype == PSGD_BF16) k_lra_damp<bf16><<<grid, 256, 0, st>>>((const bf16*)hvp, (const bf16*)z, (bf16*)w.hbuf, n, damping, dtype_eps(PSGD_BF16));
+  else k_lra_damp<float><<<grid, 256, 0, st>>>((const float*)hvp, (const float*)z, (float*)w.hbuf, n, damping, dtype_eps(PSGD_F32));
+  ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_damp"); if (rc) return rc;
+  return lra_update_impl(ctx, l, v, w.hbuf, lr, betaL, update_U, w, st);
+}
+
 static int lra_apply_impl(psgd_handle_t h, const psgd_lra_t* l, const void* g, void* out, float* sumsq_out, void* workspace,
                           size_t workspace_bytes, void* stream, int modes);
 
@@ -825,11 +843,10 @@ static int lra_apply_impl(psgd_handle_t h, const psgd_lra_t* l, const void* g, v
     const long long n_full = tma_ok ? n / 256 : 0;
     const long long n_rem = n - n_full * 256;
     const int tile_bytes = 256 * r * 2 + 256 * 2 + 256 * 2 + 256 * 4;
-    static bool attr_a = false;
-    if (!attr_a) {
+    static PerDeviceOnce attr_a;
+    if (attr_a.need(ctx->device)) {
       cudaFuncSetAttribute(k_lra_apply_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (256 * 32 * 2 + 2048));
       cudaFuncSetAttribute(k_lra_apply_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (256 * 16 * 2 + 2048));
-      attr_a = true;
     }
     int gridt = (int)(n_full < (long long)ctx->num_sms ? n_full : (long long)ctx->num_sms);
     long long need_r = ((n_rem + rpi - 1) / rpi + 4 * 8 - 1) / (4 * 8);

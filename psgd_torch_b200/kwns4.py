@@ -120,6 +120,27 @@ class KWNS4(torch.optim.Optimizer):
             else:
                 self.cuda_rng_state = None
 
+    def _rng_enter(self):
+        """ddp.py:100-104: swap the private (synchronised) generator states in; returns the caller's states."""
+        if not self.is_distributed:
+            return None
+        ext = [torch.get_rng_state(), None]
+        torch.set_rng_state(self.cpu_rng_state)
+        if self.cuda_rng_state is not None:
+            ext[1] = torch.cuda.get_rng_state()
+            torch.cuda.set_rng_state(self.cuda_rng_state)
+        return ext
+
+    def _rng_exit(self, ext):
+        """ddp.py:172-176"""
+        if ext is None:
+            return
+        self.cpu_rng_state = torch.get_rng_state()
+        torch.set_rng_state(ext[0])
+        if self.cuda_rng_state is not None:
+            self.cuda_rng_state = torch.cuda.get_rng_state()
+            torch.cuda.set_rng_state(ext[1])
+
     # ---- owner-computes sharding (shard_preconditioners=True) ----
     def _sharding_active(self):
         return self.shard_preconditioners and self.is_distributed and torch.distributed.get_world_size() > 1
@@ -147,6 +168,9 @@ class KWNS4(torch.optim.Optimizer):
         # synchronised private state, because each rank now consumes a different amount of the main streams
         seed = int(torch.frombuffer(bytearray(self.cpu_rng_state[:8].numpy().tobytes()), dtype=torch.int64)[0]) & 0x7FFFFFFF
         self._coin_gen = torch.Generator().manual_seed(seed)
+        if getattr(self, "_coin_state", None) is not None:     # resumed from a checkpoint
+            self._coin_gen.set_state(self._coin_state)
+            self._coin_state = None
 
     # ---- hooks overridden by the DTensor variant ----
     def _local(self, t):
@@ -169,47 +193,122 @@ class KWNS4(torch.optim.Optimizer):
             self._sumsq[device] = b
         return b
 
+    # ---- checkpoints ----
+    _EXPRS_TAG = "psgd_exprs/v1"
+
+    def _gather_sharded_state(self):
+        """shard_preconditioners=True: every rank holds the state of the parameters it owns only.  Collective (all ranks call
+        state_dict()): the owner broadcasts (Q, L, ema, step) of each of its parameters, so that every rank returns the full state and the
+        usual rank-0-only checkpoint is complete."""
+        dist = torch.distributed
+        me = dist.get_rank()
+        full = {}
+        plist = [p for group in self.param_groups for p in group["params"]]
+        has = torch.zeros(len(plist), dtype=torch.int64, device=self._local(plist[0]).device if plist else "cpu")
+        for i, p in enumerate(plist):
+            if self._owner.get(id(p)) == me and len(self.state.get(p, {})) > 0:
+                has[i] = 1 + self.state[p]["step"]
+        dist.all_reduce(has, op=dist.ReduceOp.MAX)
+        has = has.tolist()
+        for group in self.param_groups:
+            for p in group["params"]:
+                i = plist.index(p)
+                if has[i] == 0:
+                    continue
+                owner = self._owner[id(p)]
+                lp = self._local(p)
+                pre = group["preconditioner_dtype"] or lp.dtype
+                if owner == me:
+                    st = self.state[p]
+                else:
+                    shape = lp.squeeze().shape
+                    QL, exprs = psgd.init_kron(torch.empty(shape, dtype=pre, device=lp.device), Scale=group["preconditioner_init_scale"],
+                                               max_size=group["preconditioner_max_size"], max_skew=group["preconditioner_max_skew"], dQ=self.dQ)
+                    st = {"QL": QL, "exprs": exprs, "step": has[i] - 1,
+                          "ema": None if group["momentum"] == 0.0 else torch.zeros(shape, dtype=pre, device=lp.device)}
+                for t in list(st["QL"][0]) + list(st["QL"][1]) + ([st["ema"]] if st["ema"] is not None else []):
+                    dist.broadcast(t, src=owner)
+                full[p] = st
+        return full
+
     def state_dict(self):
-        """The reference's state_dict plus, under the extra key "psgd_rng", the private CPU / CUDA generator states of a distributed run
-        (ddp.py:92,96 keep them as attributes and forget them in checkpoints, so a resumed reference run draws different numbers than an
-        uninterrupted one).  A checkpoint written by the reference (no such key) loads unchanged."""
-        sd = super().state_dict()
+        """The reference's state_dict (keys "QL", "step", "ema" per parameter) with three differences:
+          * `exprs` (callables) is replaced by a plain tag -- it is rebuilt from the factor shapes on load, so the checkpoint holds tensors
+            and python scalars only (torch.load(weights_only=True) accepts it);
+          * the private CPU / CUDA generator states of a distributed run ride in param_groups[0]["psgd_rng"] (ddp.py:92,96 keep them as
+            attributes and forget them in checkpoints, so a resumed reference run draws different numbers than an uninterrupted one);
+          * with shard_preconditioners=True the call is COLLECTIVE (every rank must make it): owned states are broadcast so that every
+            rank returns the complete state."""
+        saved = None
+        if self._sharding_active() and self._owner is not None:
+            saved = dict(self.state)
+            for p, st in self._gather_sharded_state().items():
+                self.state[p] = st
+        try:
+            sd = super().state_dict()
+        finally:
+            if saved is not None:
+                self.state.clear()
+                self.state.update(saved)
+        sd["state"] = {k: {kk: (self._EXPRS_TAG if kk == "exprs" else vv) for kk, vv in st.items()} for k, st in sd["state"].items()}
         if getattr(self, "is_distributed", False):
-            sd["psgd_rng"] = {"cpu": self.cpu_rng_state.clone(),
-                              "cuda": None if self.cuda_rng_state is None else self.cuda_rng_state.clone()}
+            sd["param_groups"] = [dict(g) for g in sd["param_groups"]]
+            rng = {"cpu": self.cpu_rng_state.clone(), "cuda": None if self.cuda_rng_state is None else self.cuda_rng_state.clone()}
+            if getattr(self, "_coin_gen", None) is not None:
+                rng["coin"] = self._coin_gen.get_state().clone()
+            sd["param_groups"][0]["psgd_rng"] = rng
         return sd
 
     def load_state_dict(self, state_dict):
-        """torch.optim.Optimizer.load_state_dict casts every floating state tensor to the PARAMETER's dtype, which would silently turn a
-        bf16 preconditioner (and its momentum buffer) into fp32 on resume -- the reference has the same quirk.  Restore the group's
-        preconditioner_dtype for Q and ema (L stays fp32, psgd.py:96-98) so that a resumed run continues on the same arithmetic."""
-        state_dict = dict(state_dict)
-        rng = state_dict.pop("psgd_rng", None)
+        """torch.optim.Optimizer.load_state_dict casts every floating state tensor to the PARAMETER's dtype: a bf16 preconditioner of an fp32
+        parameter would come back as fp32, and -- worse -- the fp32 Lipschitz constants (and an fp32 preconditioner) of a bf16 parameter would
+        be truncated to 8 mantissa bits.  Q, L and ema are therefore restored from the checkpoint's own tensors: Q / ema in the group's
+        preconditioner_dtype, L in fp32 (psgd.py:96-98).  `exprs` is rebuilt from the factor shapes.  A checkpoint written by the reference
+        wrapper (same keys, no RNG entry) loads unchanged; with shard_preconditioners=True every rank loads the full state and keeps the
+        parameters it owns."""
+        raw_state = state_dict["state"]
+        state_dict = {"state": {k: dict(v) for k, v in raw_state.items()}, "param_groups": [dict(g) for g in state_dict["param_groups"]],
+                      **{k: v for k, v in state_dict.items() if k not in ("state", "param_groups")}}
+        rng = state_dict.pop("psgd_rng", None)                        # round-1 checkpoints kept it at the top level
+        rng = state_dict["param_groups"][0].pop("psgd_rng", rng) if state_dict["param_groups"] else rng
+        for st in state_dict["state"].values():
+            st.pop("exprs", None)                                     # callables (reference) or the tag: rebuilt below
+        super().load_state_dict(state_dict)
         if rng is not None and getattr(self, "is_distributed", False):
             self.cpu_rng_state = rng["cpu"].clone().cpu()
             if rng.get("cuda") is not None and self.cuda_rng_state is not None:
                 self.cuda_rng_state = rng["cuda"].clone().cpu()
-        super().load_state_dict(state_dict)
+            if rng.get("coin") is not None:
+                if getattr(self, "_coin_gen", None) is not None:
+                    self._coin_gen.set_state(rng["coin"])
+                else:
+                    self._coin_state = rng["coin"]
+        idx = 0
+        me = torch.distributed.get_rank() if self._sharding_active() else 0
+        if self._sharding_active() and self._owner is None:
+            self._assign_owners()
         for group in self.param_groups:
             pd = group["preconditioner_dtype"]
             for p in group["params"]:
+                raw = raw_state.get(idx, raw_state.get(str(idx)))
+                idx += 1
                 st = self.state.get(p)
-                if not st:
+                if not st or raw is None:
                     continue
-                dt = pd or p.dtype
-                Q, L = st["QL"]
-                st["QL"] = [[q.to(dt).contiguous() for q in Q], [l.to(torch.float32) for l in L]]
-                if st.get("ema") is not None:
-                    st["ema"] = st["ema"].to(dt).contiguous()
+                if self._sharding_active() and self._owner[id(p)] != me:
+                    del self.state[p]                                 # another rank owns this parameter's preconditioner
+                    continue
+                lp = self._local(p)
+                dt = pd or lp.dtype
+                Qr, Lr = raw["QL"]
+                st["QL"] = [[q.detach().to(device=lp.device, dtype=dt).contiguous().clone() for q in Qr],
+                            [l.detach().to(device=lp.device, dtype=torch.float32).clone() for l in Lr]]
+                st["ema"] = None if raw.get("ema") is None else raw["ema"].detach().to(device=lp.device, dtype=dt).contiguous().clone()
+                st["exprs"] = psgd.exprs_for_state(st["QL"][0], self.dQ)
 
     @torch.no_grad()
     def step(self):
-        if self.is_distributed:  # ddp.py:100-104
-            external_cpu_rng_state = torch.get_rng_state()
-            torch.set_rng_state(self.cpu_rng_state)
-            if self.cuda_rng_state is not None:
-                external_cuda_rng_state = torch.cuda.get_rng_state()
-                torch.cuda.set_rng_state(self.cuda_rng_state)
+        external = self._rng_enter()
 
         lib = _lib.load_library()
         sharded = self._sharding_active()
@@ -226,17 +325,24 @@ class KWNS4(torch.optim.Optimizer):
             wd, lr_params = group["weight_decay"], group["lr_params"]
             for p in group["params"]:
                 grad = p.grad
-                if grad is None:
-                    continue
+                local_p = self._local(p)
                 if sharded:
+                    # owner and receivers must take the same decision or the broadcast below dead-locks: the skip tests use what
+                    # every rank sees alike (the parameter), never the local gradient, and a missing gradient on the owner is an error
+                    if local_p.numel() == 0:
+                        continue
                     owner = self._owner[id(p)]
                     if owner != my_rank:   # the owner computes; this rank only receives the updated parameter
-                        pending.append(torch.distributed.broadcast(self._local(p), src=owner, async_op=True))
+                        pending.append(torch.distributed.broadcast(local_p, src=owner, async_op=True))
                         continue
+                    if grad is None:
+                        raise _lib.EngineError("shard_preconditioners=True: the owner rank has no gradient for a parameter the other ranks "
+                                               "are waiting for (every parameter handed to KWNS4 must receive a gradient on every step)")
+                if grad is None:
+                    continue
                 grad = self._local(grad)
                 if grad.numel() == 0:  # dtensor.py:124-125
                     continue
-                local_p = self._local(p)
                 if not local_p.is_contiguous():
                     raise _lib.EngineError("KWNS4 (B200 engine) needs contiguous parameters")
                 grad = grad.contiguous()
@@ -298,12 +404,7 @@ class KWNS4(torch.optim.Optimizer):
         for w in pending:
             w.wait()
 
-        if self.is_distributed:  # ddp.py:172-176
-            self.cpu_rng_state = torch.get_rng_state()
-            torch.set_rng_state(external_cpu_rng_state)
-            if self.cuda_rng_state is not None:
-                self.cuda_rng_state = torch.cuda.get_rng_state()
-                torch.cuda.set_rng_state(external_cuda_rng_state)
+        self._rng_exit(external)
 
 
 class KWNS4DTensor(KWNS4):

@@ -10,6 +10,7 @@ import torch
 
 from . import _lib
 from . import psgd
+from .kwns4 import KWNS4
 
 
 class LRAWhitenOptimizer(torch.optim.Optimizer):
@@ -47,9 +48,57 @@ class LRAWhitenOptimizer(torch.optim.Optimizer):
         self._m, self._counter_m = None, 0
         self._dtype, self._device, self._n = dtype, device, n
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=device)
+        # RNG discipline of KWNS4 (ddp.py:88-96): under torch.distributed the ranks draw randn_like(g) and the U/V coin from private
+        # generator states synchronised at construction, so that the replicated preconditioners stay identical
+        self._init_rng_sync()
+
+    _needs_rng_sync = KWNS4._needs_rng_sync
+    _init_rng_sync = KWNS4._init_rng_sync
+    _rng_enter = KWNS4._rng_enter
+    _rng_exit = KWNS4._rng_exit
+
+    # ---- checkpoints: the global preconditioner, its Lipschitz constants, the momentum buffer and its counter live outside the
+    # per-parameter state of torch.optim.Optimizer; they ride under the reserved state key "psgd_lra" (tensors + python scalars) ----
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["state"] = dict(sd["state"])
+        blob = {"UVd": [t.detach().clone() for t in self._UVd], "Luvd": [t.detach().clone() for t in self._Luvd],
+                "m": None if self._m is None else self._m.detach().clone(), "counter_m": int(self._counter_m)}
+        if self.is_distributed:
+            blob["rng_cpu"] = self.cpu_rng_state.clone()
+            blob["rng_cuda"] = None if self.cuda_rng_state is None else self.cuda_rng_state.clone()
+        sd["state"]["psgd_lra"] = blob
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = {**state_dict, "state": dict(state_dict["state"])}
+        blob = state_dict["state"].pop("psgd_lra", None)
+        super().load_state_dict(state_dict)
+        if blob is None:
+            return
+        mv = lambda t, dt: t.detach().to(device=self._device, dtype=dt).contiguous().clone()
+        UVd = [mv(t, self._dtype) for t in blob["UVd"]]
+        if UVd[0].shape != (self._n, self._UVd[0].shape[1]):
+            raise ValueError(f"checkpoint holds an LRA preconditioner of shape {tuple(UVd[0].shape)}, this optimizer needs "
+                             f"{(self._n, self._UVd[0].shape[1])}")
+        self._UVd = UVd
+        self._Luvd = [mv(t, torch.float32) for t in blob["Luvd"]]
+        self._m = None if blob["m"] is None else mv(blob["m"], self._dtype)
+        self._counter_m = int(blob["counter_m"])
+        if self.is_distributed and blob.get("rng_cpu") is not None:
+            self.cpu_rng_state = blob["rng_cpu"].clone().cpu()
+            if blob.get("rng_cuda") is not None and self.cuda_rng_state is not None:
+                self.cuda_rng_state = blob["rng_cuda"].clone().cpu()
 
     @torch.no_grad()
     def step(self):
+        ext = self._rng_enter()
+        try:
+            self._step()
+        finally:
+            self._rng_exit(ext)
+
+    def _step(self):
         g = self.param_groups[0]
         lib = _lib.load_library()
         h = _lib.handle_for(self._device)

@@ -144,6 +144,16 @@ def _exprs_for(dQ, order, exprGs, exprQs):
     return (_ExprP(order), exprGs)
 
 
+def exprs_for_state(Q, dQ="Q0.5EQ1.5"):
+    """Rebuild the `exprs` tuple of init_kron from the factors of a loaded checkpoint (dense factor = 2-D, diagonal = 1-D, scalar tensor =
+    one 0-dim factor): the expressions depend on the order and on which factors are dense, nothing else."""
+    if len(Q) == 1 and Q[0].dim() == 0:
+        return _exprs_for(dQ, 0, (_ExprG(0, False, 0),), (_ExprQ(0, False, 0),))
+    order = len(Q)
+    return _exprs_for(dQ, order, tuple(_ExprG(i, q.dim() == 2, order) for i, q in enumerate(Q)),
+                      tuple(_ExprQ(i, q.dim() == 2, order) for i, q in enumerate(Q)))
+
+
 # ------------------------------------------------------------------------------------------------
 # engine plumbing
 # ------------------------------------------------------------------------------------------------
@@ -467,11 +477,21 @@ def precond_grad_lra(UVd, g, sumsq_out=None):
     return out
 
 
-def update_precond_lra_newton(UVd, Luvd, v, h, lr=0.1, betaL=0.9, damping=1e-9, update_U=None):
-    """psgd.py:1193-1198: LRA Newton update = update_precond_lra on (v, h + damping * randn_like(h)) (independent noise on the Hvp).
-    RNG order: randn_like(h) then the CPU coin of update_precond_lra."""
-    damping = damping + torch.finfo(h.dtype).eps * h.abs()   # psgd.py:1197
-    update_precond_lra(UVd, Luvd, v, h + damping * torch.randn_like(h), lr=lr, betaL=betaL, update_U=update_U)
+def update_precond_lra_newton(UVd, Luvd, v, h, lr=0.1, betaL=0.9, damping=1e-9, update_U=None, noise=None):
+    """psgd.py:1193-1198: LRA Newton update = update_precond_lra on (v, h + (damping + eps|h|) * randn_like(h)): independent noise on the
+    Hessian-vector product.  RNG order: randn_like(h) then the CPU coin of update_precond_lra.  The damped Hvp is formed by the engine
+    (psgd_lra_newton_update: the damping pass of the whitening update with a separate probe); `noise` = {"z", "update_U"} replays draws."""
+    if noise is None:
+        noise = {"z": torch.randn_like(h), "update_U": bool(torch.rand([]) < 0.5) if update_U is None else bool(update_U)}
+    l = _lra_desc(UVd, Luvd)
+    dev = UVd[0].device
+    hd = _lib.handle_for(dev)
+    lib = _lib.load_library()
+    ws = _lib.workspace(dev, lib.psgd_lra_workspace_bytes(hd, C.byref(l)))
+    rc = lib.psgd_lra_newton_update(hd, C.byref(l), _lib.ptr(v.contiguous()), _lib.ptr(h.contiguous()), _lib.ptr(noise["z"].contiguous()),
+                                    float(lr), float(betaL), float(damping), int(noise["update_U"]), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream_ptr(dev))
+    _lib.check(hd, rc, "psgd_lra_newton_update")
 
 
 # north_star's names for the LRA functions (old.py:657,744; SURVEY.md 0): thin aliases of the psgd.py math
@@ -487,11 +507,15 @@ class NoiseTape:
     reference draws (randn_like(G), randn(32, s) per norm bound, the CPU coin torch.rand([])); a list of pre-drawn items replays them
     (parity tests feed the numbers the reference consumed)."""
 
-    def __init__(self, items=None, device=None):
+    def __init__(self, items=None, device=None, rounds=None):
         self.replay = items is not None
         self.items = list(items) if items is not None else []
         self.pos = 0
         self.device = device
+        # PRO4P: procrustes_step3 round counts per dense factor (psgd.py:444-449).  `rounds` pins them (the stopping test is skipped) so
+        # that a bf16 parity test runs the rounds the reference ran; `self.rounds` records what was done.
+        self.fixed_rounds = list(rounds) if rounds is not None else None
+        self.rounds = []
 
     def _next(self, make):
         if self.replay:
@@ -597,6 +621,18 @@ def _almost_symmetric(q):
     return gap < 0.001 * amax
 
 
+def _pro4p_rounds(q, tape):
+    """psgd.py:444-449: rotate until the factor is almost symmetric (at most ten rounds; host-side branch like the reference's)."""
+    fixed = tape.fixed_rounds.pop(0) if tape.fixed_rounds is not None else None
+    done = 0
+    for _ in range(10 if fixed is None else fixed):
+        procrustes_step3(q, V0=tape.randn(_K_PROBES, q.shape[1], q))
+        done += 1
+        if fixed is None and _almost_symmetric(q):
+            break
+    tape.rounds.append(done)
+
+
 def _kron_update(dQ, QL, X, V, lr, betaL, damping, noise, damp=True):
     """One update through psgd_kron_update.  Draw order = the reference's: randn_like(X) (if damped), then per dense factor the
     norm-bound probe randn(32, s) (psgd.py:62) followed by that factor's procrustes probes (Q0.5EQ1.5: one, psgd.py:87; PRO4P: one
@@ -647,10 +683,7 @@ def _kron_update(dQ, QL, X, V, lr, betaL, damping, noise, damp=True):
             call(stages)
             stages = 0
             if q.dim() == 2:
-                for _ in range(10):
-                    procrustes_step3(q, V0=tape.randn(_K_PROBES, q.shape[1], q))
-                    if _almost_symmetric(q):
-                        break
+                _pro4p_rounds(q, tape)
     if dQ != "QEP" and tape.rand() < 0.01:  # psgd.py:318, 390, 418 ...
         stages |= _lib.STAGE_BALANCE
     if stages:
@@ -730,10 +763,7 @@ def _kron_update_nd(dQ, QL, X, V, lr, betaL, damping, tape, damp):
                                            _lib.stream_ptr(X.device))
             _lib.check(h, rc, "psgd_kron_factor_step")
             if dQ == "PRO4P":                        # psgd.py:444-449
-                for _ in range(10):
-                    procrustes_step3(q, V0=tape.randn(_K_PROBES, s, q))
-                    if _almost_symmetric(q):
-                        break
+                _pro4p_rounds(q, tape)
         else:
             term1 = torch.sum(M1.float() * M1.float(), dim=1).contiguous()
             if src2 is not None:

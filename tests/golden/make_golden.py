@@ -168,11 +168,13 @@ def spd_pair(shape, dtype, gen_seed):
     return V.to(dtype), (0.5 * H).to(dtype)
 
 
-def geom_cases(dq):
+def geom_cases(dq, specs=None, suffix=""):
     """All golden cases of one geometry: whitening and Newton-pair updates by the unmodified reference (psgd.py:330-513,
     657-829), with the oracle run side by side in record mode on the same seed (its NoiseTape is stored for replay)."""
     f32, bf16 = torch.float32, torch.bfloat16
     fn = DQ_FUNCS[dq]
+    if specs is not None:
+        return _geom_cases(dq, fn, specs, suffix)
     specs = [("whiten", (24, 40), f32, 3), ("whiten", (8, 300), f32, 3), ("whiten", (300, 8), f32, 2), ("whiten", (50,), f32, 3),
              ("whiten", (136, 200), f32, 2), ("newton", (24, 40), f32, 3), ("newton", (8, 300), f32, 2)]
     specs += [("whiten", (5, 6, 7), f32, 2)]                                   # order 3: all dense
@@ -182,6 +184,10 @@ def geom_cases(dq):
         specs += [("whiten", (24, 40), bf16, 3), ("whiten", (136, 200), bf16, 2), ("newton", (24, 40), bf16, 2)]
     if dq == "Q0.5EQ1.5":
         specs = [s for s in specs if s[0] == "newton"]  # the whitening form has its own fixtures (kron_*.pt)
+    return _geom_cases(dq, fn, specs, suffix)
+
+
+def _geom_cases(dq, fn, specs, suffix):
     out = []
     for (mode, shape, dtype, steps) in specs:
         t0 = torch.zeros(*shape, dtype=dtype)
@@ -217,11 +223,99 @@ def geom_cases(dq):
             for a, b in zip(QL_ref[1], QL_o[1]):
                 worst = max(worst, float((a - b).abs() / a.abs()))
             case["steps"].append({**inputs, "seed": seed, "tape": list(tape.items), "X": X, "Q": [q.clone() for q in QL_ref[0]],
-                                  "L": [l.clone() for l in QL_ref[1]], "Pg": Pg.clone()})
+                                  "L": [l.clone() for l in QL_ref[1]], "Pg": Pg.clone(), "rounds": list(tape.rounds)})
         print(f"geom {dq:10s} {mode:6s} shape={tuple(shape)} {dtype}: oracle-vs-reference worst rel err {worst:.3e}")
         case["oracle_vs_reference"] = worst
         out.append(case)
-    torch.save(out, os.path.join(OUT, f"geom_{fn}.pt"))
+    torch.save(out, os.path.join(OUT, f"geom_{fn}{suffix}.pt"))
+
+
+def lra_newton_case(name, n, r, dtype, steps=4, lr=0.1):
+    """update_precond_lra_newton (psgd.py:1193-1198) by the unmodified reference on (v, Hvp) pairs of a diagonal-plus-low-rank SPD
+    Hessian; the oracle side by side on the same seed."""
+    g0 = torch.Generator().manual_seed(11)
+    U = torch.randn(n, r, generator=g0)
+    U = (U * (0.1 ** 0.5 / torch.linalg.vector_norm(U))).to(dtype)
+    V = torch.randn(n, r, generator=g0)
+    V = (V * (0.1 ** 0.5 / torch.linalg.vector_norm(V))).to(dtype)
+    d = torch.ones(n, 1, dtype=dtype)
+    hd = 0.3 + torch.rand(n, 1, generator=g0)
+    W = torch.randn(n, 3, generator=g0) / n ** 0.5
+    UVd_r, Luvd_r = [U.clone(), V.clone(), d.clone()], [torch.zeros([], dtype=torch.float32) for _ in range(3)]
+    UVd_o, Luvd_o = [U.clone(), V.clone(), d.clone()], [torch.zeros([], dtype=torch.float32) for _ in range(3)]
+    case = {"name": name, "n": n, "r": r, "dtype": str(dtype), "lr": lr, "betaL": 0.9, "damping": 1e-9, "U0": U, "V0": V, "d0": d,
+            "steps": []}
+    worst = 0.0
+    for s in range(steps):
+        v = torch.randn(n, 1, generator=g0)
+        h = (hd * v + W @ (W.T @ v)).to(dtype)
+        v = v.to(dtype)
+        seed = 555 + 29 * s
+        torch.manual_seed(seed)
+        ref.update_precond_lra_newton(UVd_r, Luvd_r, v, h, lr=lr, betaL=0.9, damping=1e-9)
+        Pg = ref.precond_grad_lra(UVd_r, h)
+        torch.manual_seed(seed)
+        noise = orc.draw_lra_newton_noise(h)
+        orc.update_precond_lra_newton(UVd_o, Luvd_o, v, h, noise, lr=lr, betaL=0.9, damping=1e-9)
+        Pg_o = orc.precond_grad_lra(UVd_o, h)
+        for a, b in zip(UVd_r + [Pg], UVd_o + [Pg_o]):
+            worst = max(worst, float((a.float() - b.float()).norm() / a.float().norm()))
+        case["steps"].append({"v": v, "h": h, "seed": seed, "noise": noise, "U": UVd_r[0].clone(), "V": UVd_r[1].clone(),
+                              "d": UVd_r[2].clone(), "L": [l.clone() for l in Luvd_r], "Pg": Pg.clone()})
+    print(f"{name:28s} n={n} r={r} {dtype}: oracle-vs-reference worst normwise rel err {worst:.3e}")
+    case["oracle_vs_reference"] = worst
+    torch.save(case, os.path.join(OUT, f"lranewton_{name}.pt"))
+    return worst
+
+
+def kwns4_checkpoint_case(name, shape, pdtype, ptype, save_at=3, steps=5, **kw):
+    """A checkpoint WRITTEN BY THE REFERENCE WRAPPER (ddp.py:131-137 state keys) in the middle of a run, plus the rest of the reference's
+    trajectory: the drop-in must load it and continue like the reference does.  `exprs` (closures of the opt_einsum stand-in; with the real
+    opt_einsum: ContractExpression objects) is dropped from the saved state -- every other key is the reference's own."""
+    sys.modules["psgd"] = ref
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kwns4_reference", "/root/reference/wrapped_as_torch_optimizer_for_ddp.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    del sys.modules["psgd"]
+    g0 = torch.Generator().manual_seed(8)
+    p_ref = torch.nn.Parameter(torch.randn(*shape, generator=g0).to(ptype))
+    opt = mod.KWNS4([p_ref], preconditioner_dtype=pdtype, **kw)
+    case = {"name": name, "shape": list(shape), "pdtype": str(pdtype), "ptype": str(ptype), "kw": kw, "save_at": save_at, "steps": []}
+    for s in range(steps):
+        if s == save_at:
+            sd = opt.state_dict()
+            sd = {"state": {k: {kk: vv for kk, vv in st.items() if kk != "exprs"} for k, st in sd["state"].items()},
+                  "param_groups": sd["param_groups"]}
+            case["checkpoint"] = copy.deepcopy(sd)
+            case["p_at_save"] = p_ref.detach().clone()
+        grad = structured_grad(shape, torch.float32, 3100 + s).to(ptype)
+        seed = 4141 + s
+        p_ref.grad = grad.clone()
+        torch.manual_seed(seed)
+        opt.step()
+        torch.manual_seed(seed)
+        do_update = bool(torch.rand([]) < kw.get("preconditioner_update_probability", 1.0))
+        st = opt.state[p_ref]
+        gq = grad.squeeze().to(pdtype) if pdtype else grad.squeeze()
+        # the draws of this step, re-drawn in the reference's order (the Q shapes are all draw_kron_noise needs)
+        noise = orc.draw_kron_noise(gq, st["QL"][0]) if do_update else None
+        case["steps"].append({"grad": grad, "seed": seed, "do_update": do_update, "noise": noise, "p": p_ref.detach().clone(),
+                              "Q": [q.clone() for q in st["QL"][0]], "L": [l.clone() for l in st["QL"][1]],
+                              "ema": None if st["ema"] is None else st["ema"].clone()})
+    print(f"{name:28s} reference checkpoint at step {save_at}, keys {sorted(case['checkpoint']['state'][0].keys())}")
+    torch.save(case, os.path.join(OUT, f"refckpt_{name}.pt"))
+
+
+def round2_cases():
+    """Fixtures added in round 2 (existing files are left untouched): update_precond_lra_newton, and PRO4P in bf16 with the
+    procrustes_step3 round counts recorded (a parity test replays exactly the rounds the reference ran, psgd.py:444-449)."""
+    f32, bf16 = torch.float32, torch.bfloat16
+    lra_newton_case("r8_f32", 500, 8, f32)
+    lra_newton_case("r16_bf16", 1000, 16, bf16)
+    geom_cases("PRO4P", specs=[("whiten", (24, 40), bf16, 3), ("whiten", (136, 200), bf16, 2), ("newton", (24, 40), bf16, 2)], suffix="_bf16")
+    kwns4_checkpoint_case("f32", (16, 24), f32, f32, lr_params=1e-2)
+    kwns4_checkpoint_case("bf16_param", (16, 24), f32, bf16, lr_params=1e-2)    # bf16 parameter with an fp32 preconditioner
 
 
 def rosenbrock(x):
@@ -258,6 +352,9 @@ def closure_cases(steps=40):
 
 if __name__ == "__main__":
     torch.set_num_threads(1)  # deterministic reduction order
+    if "--round2" in sys.argv:
+        round2_cases()
+        sys.exit(0)
     f32, bf16 = torch.float32, torch.bfloat16
     kron_case("dd_f32", (24, 40), f32)
     kron_case("dd_bf16", (24, 40), bf16)
@@ -280,3 +377,4 @@ if __name__ == "__main__":
     for dq in DQ_FUNCS:
         geom_cases(dq)
     closure_cases()
+    round2_cases()

@@ -16,7 +16,7 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN, load_golden, relerr
+from conftest import GOLDEN, check, load_golden, parity_log, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -55,14 +55,17 @@ def test_geometry_engine_matches_reference_golden(fname):
     for case in load_golden(fname):
         dq, mode, dtype = case["dQ"], case["mode"], DT[case["dtype"]]
         tol = 1e-5 if dtype == torch.float32 else 3e-2
-        if dq == "PRO4P":
+        if dq == "PRO4P" and dtype == torch.float32:
             tol = 1e-4
         QL, exprs = psgd.init_kron(torch.zeros(case["shape"], dtype=dtype, device=dev), Scale=1.0, dQ=dq)
         for q, q0 in zip(QL[0], case["Q0"]):
             assert torch.equal(q.cpu(), q0)
         tag = f"{dq} {mode} {tuple(case['shape'])} {case['dtype']}"
         for si, st in enumerate(case["steps"]):
-            tape = psgd.NoiseTape(st["tape"], device=dev)
+            # PRO4P in bf16: the outcome of the stopping test of psgd.py:448 is rounding dependent, so the replay runs exactly the
+            # procrustes_step3 rounds the reference ran (recorded with the fixture)
+            fixed = st.get("rounds") if (dq == "PRO4P" and dtype == torch.bfloat16) else None
+            tape = psgd.NoiseTape(st["tape"], device=dev, rounds=fixed)
             inputs = {k: st[k].to(dev) for k in ("G", "V", "Hvp") if k in st}
             _engine_update(psgd, dq, mode, QL, exprs, inputs, tape, case["lr"])
             if tape.pos != len(tape.items):
@@ -74,6 +77,11 @@ def test_geometry_engine_matches_reference_golden(fname):
             # orders differ by a few percent (measured 3.4e-2 here), so L gets its own bf16 tolerance
             ltol = tol if dtype == torch.float32 else 6e-2
             lerrs = [relerr(l, lr_) for l, lr_ in zip(QL[1], st["L"])]
+            for i, e in enumerate(errs[:-1]):
+                parity_log(f"golden {fname} {tag} step {si}", f"Q[{i}]", e, tol)
+            parity_log(f"golden {fname} {tag} step {si}", "precond_grad", errs[-1], tol)
+            for i, e in enumerate(lerrs):
+                parity_log(f"golden {fname} {tag} step {si}", f"L[{i}]", e, ltol)
             if not (all(e < tol for e in errs) and all(e < ltol for e in lerrs)):   # NaN fails too
                 errs += lerrs
                 bad.append(f"{tag} step {si}: " + " ".join(f"{e:.2e}" for e in errs))
@@ -142,8 +150,6 @@ def _pair(m, n, seed, dtype):
 def test_geometry_engine_matches_oracle_midsize(dq, mode, shape, dtype):
     from psgd_torch_b200 import psgd
     from oracle import psgd_oracle as orc
-    if dq == "PRO4P" and dtype == torch.bfloat16:
-        pytest.skip("PRO4P in bf16: the number of procrustes_step3 rounds is rounding dependent (psgd.py:448), no step-wise parity")
     if dq == "Q0.5EQ1.5" and mode == "whiten":
         pytest.skip("covered by test_gpu_parity.py")
     dev = _dev()
@@ -152,7 +158,7 @@ def test_geometry_engine_matches_oracle_midsize(dq, mode, shape, dtype):
     lr = 0.5 if dq not in ("PRO4P", "QUAD4P") else 0.2
     QLe, exprs = psgd.init_kron(torch.zeros(m, n, dtype=dtype, device=dev), Scale=1.0, dQ=dq)
     tol = 1e-5 if dtype == torch.float32 else 2e-2
-    if dq == "PRO4P":
+    if dq == "PRO4P" and dtype == torch.float32:
         tol = 1e-4
     for step in range(3):
         if mode == "whiten":
@@ -171,25 +177,27 @@ def test_geometry_engine_matches_oracle_midsize(dq, mode, shape, dtype):
         else:
             orc.update_precond_kron_newton(dq, [Qo, Lo], inputs["V"], inputs["Hvp"], tape, lr=lr)
         items = list(tape.items)
+        # PRO4P in bf16: the stopping test of psgd.py:448 is rounding dependent -> the fp64 yardstick and the engine run exactly the rounds
+        # the bf16 reference arithmetic ran
+        fixed = list(tape.rounds) if (dq == "PRO4P" and dtype == torch.bfloat16) else None
         if dtype == torch.bfloat16:
-            t64 = orc.NoiseTape([x.double() if isinstance(x, torch.Tensor) else x for x in items])
+            t64 = orc.NoiseTape([x.double() if isinstance(x, torch.Tensor) else x for x in items], rounds=fixed)
             if mode == "whiten":
                 orc.update_precond_kron_whiten(dq, [Q64, L64], inputs["G"].double(), t64, lr=lr)
             else:
                 orc.update_precond_kron_newton(dq, [Q64, L64], inputs["V"].double(), inputs["Hvp"].double(), t64, lr=lr)
-        etape = psgd.NoiseTape(items, device=dev)
+        etape = psgd.NoiseTape(items, device=dev, rounds=fixed)
         _engine_update(psgd, dq, mode, QLe, exprs, {k: v.to(dev) for k, v in inputs.items()}, etape, lr)
         assert etape.pos == len(items), (etape.pos, len(items))
-        for qe, qo, q64 in zip(QLe[0], Qo, Q64):
-            assert relerr(qe, qo) < tol, (step, relerr(qe, qo))
-            if dtype == torch.bfloat16:
-                assert relerr(qe, q64) <= 1.5 * relerr(qo, q64) + 2e-3, (step, relerr(qe, q64), relerr(qo, q64))
-        for le, lo in zip(QLe[1], Lo):
-            assert relerr(le, lo) < (1e-5 if dtype == torch.float32 else 3e-2), (step, relerr(le, lo))
+        tag = f"geometry midsize {dq} {mode} {m}x{n} {dtype} step {step}"
+        for i, (qe, qo, q64) in enumerate(zip(QLe[0], Qo, Q64)):
+            check(tag, f"Q[{i}]", qe, qo, tol, yard=q64 if dtype == torch.bfloat16 else None)
+        for i, (le, lo) in enumerate(zip(QLe[1], Lo)):
+            check(tag, f"L[{i}]", le, lo, 1e-5 if dtype == torch.float32 else 3e-2)
         X = _structured(m, n, 300 + step, dtype)
         Pe = _engine_apply(psgd, dq, QLe, exprs, X.to(dev))
         Po = orc.precond_grad_kron_dq(dq, [q.detach().cpu() for q in QLe[0]], X)
-        assert relerr(Pe, Po) < tol
+        check(tag, "precond_grad", Pe, Po, tol)
 
 
 def test_procrustes_step3_matches_oracle():

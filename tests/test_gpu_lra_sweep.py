@@ -10,7 +10,7 @@ import os
 import pytest
 import torch
 
-from conftest import relerr
+from conftest import parity_log, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -62,4 +62,6 @@ def test_lra_rank_and_dtype_sweep(r, dtype):
                 assert relerr(le, l64) <= 1.5 * relerr(lo, l64) + 1e-2, (step, float(le), float(lo), float(l64))
         worst = [max(w, e) for w, e in zip(worst, errs)]
     what = "vs the oracle" if dtype == torch.float32 else "vs fp64"
+    for name, wv in zip(("U", "V", "d", "precond_grad"), worst):
+        parity_log(f"lra rank/dtype sweep (configs[4], 1/512 GPT-2 slice) r={r} {dtype}", f"{name}, worst of 20 steps {what}", wv, tol)
     print(f"LRA sweep r={r:2d} {str(dtype):15s} n={n}: worst rel err over 20 steps {what}  U {worst[0]:.2e}  V {worst[1]:.2e}  d {worst[2]:.2e}  Pg {worst[3]:.2e}")

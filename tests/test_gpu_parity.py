@@ -13,7 +13,7 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN, load_golden, relerr
+from conftest import GOLDEN, check, load_golden, parity_log, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -43,16 +43,17 @@ def test_kron_engine_matches_reference_golden(fname):
     Q = [q.clone().to(dev) for q in case["Q0"]]
     L = [l.clone().to(dev) for l in case["L0"]]
     _, exprs = psgd.init_kron(torch.zeros(case["shape"], dtype=Q[0].dtype, device=dev), max_skew=case["max_skew"])
-    for st in case["steps"]:
+    for si, st in enumerate(case["steps"]):
         G = st["G"].to(dev)
         psgd.update_precond_kron_whiten_q0p5eq1p5([Q, L], exprs, G, lr=case["lr"], betaL=case["betaL"], damping=case["damping"],
                                                   noise=_noise_to(st["noise"], dev))
-        for q, qr in zip(Q, st["Q"]):
-            assert relerr(q, qr) < tol, fname
-        for l, lr_ in zip(L, st["L"]):
-            assert relerr(l, lr_) < tol, fname
+        tag = f"golden {fname} step {si}"
+        for i, (q, qr) in enumerate(zip(Q, st["Q"])):
+            check(tag, f"Q[{i}]", q, qr, tol)
+        for i, (l, lr_) in enumerate(zip(L, st["L"])):
+            check(tag, f"L[{i}]", l, lr_, tol)
         Pg = psgd.precond_grad_kron([Q, L], exprs, G)
-        assert relerr(Pg, st["Pg"]) < tol, fname
+        check(tag, "precond_grad", Pg, st["Pg"], tol)
 
 
 def _structured(m, n, seed, dtype):
@@ -104,15 +105,14 @@ def test_kron_engine_matches_oracle_midsize(shape, dtype, path):
             orc.update_precond_kron_whiten_q0p5eq1p5([Qo, Lo], G, noise, lr=0.5, betaL=0.9, damping=1e-9)
             psgd.update_precond_kron_whiten_q0p5eq1p5(QLe, exprs, G.to(dev), lr=0.5, betaL=0.9, damping=1e-9, noise=_noise_to(noise, dev))
             tol = 1e-5 if dtype == torch.float32 else 2e-2
-            for qe, qo, q64 in zip(QLe[0], Qo, Q64):
-                assert relerr(qe, qo) < tol
-                if dtype == torch.bfloat16:
-                    assert relerr(qe, q64) <= 1.5 * relerr(qo, q64) + 2e-3
-            for le, lo in zip(QLe[1], Lo):
-                assert relerr(le, lo) < (1e-5 if dtype == torch.float32 else 3e-2)
+            tag = f"kron midsize {m}x{n} {dtype} path {path} step {step}"
+            for i, (qe, qo, q64) in enumerate(zip(QLe[0], Qo, Q64)):
+                check(tag, f"Q[{i}]", qe, qo, tol, yard=q64 if dtype == torch.bfloat16 else None)
+            for i, (le, lo) in enumerate(zip(QLe[1], Lo)):
+                check(tag, f"L[{i}]", le, lo, 1e-5 if dtype == torch.float32 else 3e-2)
             Pe = psgd.precond_grad_kron(QLe, exprs, G.to(dev))
             Po = orc.precond_grad_kron([q.detach().cpu() for q in QLe[0]], G)
-            assert relerr(Pe, Po) < tol
+            check(tag, "precond_grad", Pe, Po, tol)
     finally:
         lib.psgd_set_gemm_path(_lib.handle_for(dev), 0)
 
@@ -244,14 +244,15 @@ def test_lra_engine_matches_reference_golden(fname):
     tol = 3e-2 if bf else 2e-5
     UVd = [case["U0"].clone().to(dev), case["V0"].clone().to(dev), case["d0"].clone().to(dev)]
     Luvd = [torch.zeros([], dtype=torch.float32, device=dev) for _ in range(3)]
-    for st in case["steps"]:
+    for si, st in enumerate(case["steps"]):
         noise = {"v": st["noise"]["v"].to(dev), "update_U": st["noise"]["update_U"]}
         psgd.update_precond_lra_whiten(UVd, Luvd, st["g"].to(dev), lr=case["lr"], betaL=case["betaL"], damping=case["damping"], noise=noise)
-        for x, xr in zip(UVd, (st["U"], st["V"], st["d"])):
-            assert relerr(x, xr) < tol, fname
-        for l, lr_ in zip(Luvd, st["L"]):
-            assert relerr(l, lr_) < tol, fname
-        assert relerr(psgd.precond_grad_lra(UVd, st["g"].to(dev)), st["Pg"]) < tol, fname
+        tag = f"golden {fname} step {si}"
+        for name, x, xr in zip("UVd", UVd, (st["U"], st["V"], st["d"])):
+            check(tag, name, x, xr, tol)
+        for name, l, lr_ in zip(("Lu", "Lv", "Ld"), Luvd, st["L"]):
+            check(tag, name, l, lr_, tol)
+        check(tag, "precond_grad", psgd.precond_grad_lra(UVd, st["g"].to(dev)), st["Pg"], tol)
 
 
 KWNS4_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "kwns4_*.pt")))
@@ -274,14 +275,15 @@ def test_kwns4_wrapper_matches_reference_golden(fname, monkeypatch):
             queue.append(_noise_to(st["noise"], dev))
         opt.step()
         tol_p = 1e-6 if pdtype == torch.float32 else 2e-3
-        assert relerr(p, st["p"]) < tol_p, fname
+        tag = f"kwns4 wrapper golden {fname} step {len(opt.state[p]) and opt.state[p]['step']}"
+        check(tag, "param", p, st["p"], tol_p)
         state = opt.state[p]
         tol = 1e-5 if pdtype == torch.float32 else 2e-2
-        for q, qr in zip(state["QL"][0], st["Q"]):
+        for i, (q, qr) in enumerate(zip(state["QL"][0], st["Q"])):
             assert q.dtype == qr.dtype and q.shape == qr.shape      # state layout identical to the reference's
-            assert relerr(q, qr) < tol, fname
+            check(tag, f"Q[{i}]", q, qr, tol)
         if st["ema"] is not None:
-            assert relerr(state["ema"], st["ema"]) < tol, fname
+            check(tag, "ema", state["ema"], st["ema"], tol)
     assert not queue
 
 
@@ -332,14 +334,14 @@ def test_lra_tensor_core_sweeps_match_oracle(n, r):
         orc.update_precond_lra_whiten(UV64, L64, g.double(), {"v": noise["v"].double(), "update_U": noise["update_U"]}, lr=0.1, betaL=0.9, damping=1e-9)
         psgd.update_precond_lra_whiten(UVe, Le, g.to(dev), lr=0.1, betaL=0.9, damping=1e-9,
                                        noise={"v": noise["v"].to(dev), "update_U": noise["update_U"]})
-        for xe, xo, x64 in zip(UVe, UVo, UV64):
-            assert relerr(xe, xo) < 3e-2
-            assert relerr(xe, x64) <= 1.5 * relerr(xo, x64) + 2e-3
-        for le, l64 in zip(Le, L64):
-            assert relerr(le, l64) < 3e-2
+        tag = f"lra mma sweeps bf16 n={n} r={r} step {step}"
+        for name, xe, xo, x64 in zip("UVd", UVe, UVo, UV64):
+            check(tag, name, xe, xo, 3e-2, yard=x64)
+        for name, le, l64 in zip(("Lu", "Lv", "Ld"), Le, L64):
+            check(tag, name + " vs fp64", le, l64, 3e-2)
         Pe = psgd.precond_grad_lra(UVe, g.to(dev))
         P64 = orc.precond_grad_lra([x.detach().cpu().double() for x in UVe], g.double())
-        assert relerr(Pe, P64) < 1e-2
+        check(tag, "precond_grad vs fp64", Pe, P64, 1e-2)
 
 
 def test_kwns4_on_the_reference_demo_shape():

@@ -242,7 +242,9 @@ def _lra_worker(rank, world, port, q):
         sh._update(g[lo:hi], v[lo:hi], 0.1, 0.9, 0.0, True, coin)
         ssq = torch.zeros(1)
         outs.append((sh.precond_grad_lra(g[lo:hi], sumsq_out=ssq), float(ssq)))
-    q.put((rank, lo, hi, [x.clone() for x in sh.UVd], [(o.clone(), s_) for o, s_ in outs], coins))
+    # numpy arrays travel through the queue by value (tensors would travel as shared-memory handles served by this process, which may
+    # have exited by the time the parent unpickles them)
+    q.put((rank, lo, hi, [x.numpy().copy() for x in sh.UVd], [(o.numpy().copy(), s_) for o, s_ in outs], coins))
     dist.destroy_process_group()
 
 
@@ -271,9 +273,84 @@ def test_world_size_2_gloo_sharded_lra_choreography():
         ssq = torch.zeros(1)
         wouts.append((whole.precond_grad_lra(g, sumsq_out=ssq), float(ssq)))
     for k in range(3):
-        got = torch.cat([res[0][3][k], res[1][3][k]])
+        got = torch.cat([torch.from_numpy(res[0][3][k]), torch.from_numpy(res[1][3][k])])
         assert torch.allclose(got, whole.UVd[k], rtol=1e-5, atol=1e-6), k
     for i, (wo, ws_) in enumerate(wouts):
-        got = torch.cat([res[0][4][i][0], res[1][4][i][0]])
+        got = torch.cat([torch.from_numpy(res[0][4][i][0]), torch.from_numpy(res[1][4][i][0])])
         assert torch.allclose(got, wo, rtol=1e-4, atol=1e-4)     # fp32 partial sums in a different order
         assert abs(res[0][4][i][1] - ws_) < 1e-4 * abs(ws_) and abs(res[1][4][i][1] - ws_) < 1e-4 * abs(ws_)   # global sum of squares on every rank
+
+
+# ---- checkpoints ----
+def test_kwns4_loads_a_checkpoint_written_by_the_reference_wrapper():
+    """tests/golden/refckpt_*.pt hold state_dict()s written by the unmodified reference KWNS4 (ddp.py:131-137 keys) mid-run.  Loading must
+    keep every tensor bit-exact in the dtype the reference held it in -- in particular the fp32 Lipschitz constants and an fp32
+    preconditioner of a bf16 parameter, which torch.optim.Optimizer.load_state_dict would truncate to the parameter's dtype."""
+    import torch
+    from conftest import load_golden
+    from psgd_torch_b200 import kwns4
+    for name in ("refckpt_f32.pt", "refckpt_bf16_param.pt"):
+        case = load_golden(name)
+        ptype = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}[case["ptype"]]
+        pdtype = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}[case["pdtype"]]
+        p = torch.nn.Parameter(case["p_at_save"].clone().to(ptype))
+        opt = kwns4.KWNS4([p], preconditioner_dtype=pdtype, **case["kw"])
+        opt.load_state_dict(case["checkpoint"])
+        st, ref = opt.state[p], case["checkpoint"]["state"][0]
+        assert st["step"] == ref["step"] == case["save_at"]
+        for q, qr in zip(st["QL"][0], ref["QL"][0]):
+            assert q.dtype == pdtype and torch.equal(q, qr)
+        for l, lr_ in zip(st["QL"][1], ref["QL"][1]):
+            assert l.dtype == torch.float32 and torch.equal(l, lr_) and float(l) > 0
+        assert st["ema"].dtype == pdtype and torch.equal(st["ema"], ref["ema"])
+        assert callable(st["exprs"][0]) and len(st["exprs"][1]) == len(st["QL"][0])     # rebuilt from the factor shapes
+
+
+def test_kwns4_checkpoint_holds_tensors_and_scalars_only():
+    """state_dict() replaces the `exprs` callables by a tag, so torch.load(weights_only=True) accepts the file; a round trip restores
+    Q / L / ema exactly and the private RNG states from param_groups[0]."""
+    import io
+    import torch
+    from psgd_torch_b200 import kwns4, psgd
+    p = torch.nn.Parameter(torch.zeros(6, 5, dtype=torch.bfloat16))
+    opt = kwns4.KWNS4([p])
+    QL, exprs = psgd.init_kron(torch.zeros(6, 5, dtype=torch.bfloat16))
+    QL[0][0] += 0.01 * torch.randn_like(QL[0][0])      # 6^2 > 30: diagonal factor; QL[0][1] is the dense 5 x 5 one
+    QL[0][1] += 0.01 * torch.randn(5, 5).bfloat16()
+    QL[1][0].fill_(1.2345678)                        # not representable in bf16
+    opt.state[p] = {"QL": QL, "exprs": exprs, "step": 7, "ema": torch.randn(6, 5).bfloat16()}
+    opt.is_distributed, opt.cpu_rng_state, opt.cuda_rng_state = True, torch.get_rng_state(), None
+    buf = io.BytesIO(); torch.save(opt.state_dict(), buf); buf.seek(0)
+    sd = torch.load(buf, weights_only=True)
+    assert set(sd.keys()) == {"state", "param_groups"}
+    p2 = torch.nn.Parameter(torch.zeros(6, 5, dtype=torch.bfloat16))
+    opt2 = kwns4.KWNS4([p2])
+    opt2.is_distributed, opt2.cpu_rng_state, opt2.cuda_rng_state = True, torch.zeros_like(opt.cpu_rng_state), None
+    opt2.load_state_dict(sd)
+    st = opt2.state[p2]
+    assert st["step"] == 7 and torch.equal(st["QL"][0][0], QL[0][0]) and st["QL"][0][0].dtype == torch.bfloat16
+    assert st["QL"][1][0].dtype == torch.float32 and float(st["QL"][1][0]) == float(QL[1][0])
+    assert torch.equal(opt2.cpu_rng_state, opt.cpu_rng_state) and "psgd_rng" not in opt2.param_groups[0]
+    assert type(st["exprs"][0]).__name__ == "_ExprP"
+
+
+def test_lra_optimizer_checkpoint_round_trip():
+    """LRAWhitenOptimizer keeps its global preconditioner (U, V, d), Lipschitz constants, momentum buffer and counter under the reserved
+    state key "psgd_lra": a resumed run continues from the fitted preconditioner instead of a fresh random one."""
+    import io
+    import torch
+    from psgd_torch_b200 import LRAWhitenOptimizer
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(5))]
+    opt = LRAWhitenOptimizer(ps, rank_of_approximation=4, preconditioner_init_scale=0.5, momentum=0.9)
+    opt._m, opt._counter_m = torch.randn(26, 1), 11
+    opt._Luvd[0].fill_(3.25)
+    buf = io.BytesIO(); torch.save(opt.state_dict(), buf); buf.seek(0)
+    torch.manual_seed(2)
+    ps2 = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(5))]
+    opt2 = LRAWhitenOptimizer(ps2, rank_of_approximation=4, preconditioner_init_scale=0.5, momentum=0.9)
+    assert not torch.equal(opt2._UVd[0], opt._UVd[0])
+    opt2.load_state_dict(torch.load(buf, weights_only=True))
+    for a, b in zip(opt2._UVd + opt2._Luvd + [opt2._m], opt._UVd + opt._Luvd + [opt._m]):
+        assert torch.equal(a, b)
+    assert opt2._counter_m == 11
