@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "kron_kernels.cuh"
+#include "bounds.cuh"
 
 namespace psgd {
 
@@ -219,7 +220,62 @@ struct BoundJob {
 // finish: mode 0 -> dense-factor L update + step (needs t2, lr, betaL, L, fs); mode 1 -> procrustes normaliser (fs); mode 2 -> bound only
 struct BoundFinish { int mode; float t2, lr, betaL; float* L; float* fs; };
 
+// the whole evaluation of up to NB_MAX_JOBS bounds as one persistent cooperative kernel (bounds.cuh)
+static bool bound_fusable(const Ctx* ctx, int dt, const BoundJob& J) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return ctx->nb_sync && ctx->gemm_path != 1 && !(ctx->debug_flags & (4 | 256)) && dt == PSGD_BF16 && J.s >= 128 && (J.s % 8) == 0 &&
+         J.s <= NB_MAX_S && al16(J.A) && al16(J.V0) && al16(J.Va) && al16(J.Vb);
+}
+
+static int run_bounds_fused(Ctx* ctx, int dt, const BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st) {
+  NbParams P;
+  memset(&P, 0, sizeof(P));
+  int units = 0, smax = 0;
+  for (int j = 0; j < n; ++j) {
+    const BoundJob& J = jb[j];
+    NbJob& o = P.job[j];
+    o.A = (const bf16*)J.A; o.V0 = (const bf16*)J.V0; o.row_sumsq = J.row_sumsq; o.nf_src = J.nf_src;
+    o.Va = (bf16*)J.Va; o.Vb = (bf16*)J.Vb; o.scal = J.w->scal; o.rn1 = J.w->rn1; o.rn3 = J.w->rn3; o.rn4 = J.w->rn4; o.dots = J.w->sc1;
+    o.s = J.s; o.unit0 = units; o.nunits = (J.s + NB_W - 1) / NB_W;
+    units += o.nunits;
+    if (J.s > smax) smax = J.s;
+    const BoundFinish f = fin ? fin[j] : BoundFinish{2, 0.f, 0.f, 0.f, nullptr, nullptr};
+    o.mode = f.mode; o.t2 = f.t2; o.lr = f.lr; o.betaL = f.betaL; o.L = f.L; o.fs = f.fs;
+  }
+  P.njobs = n; P.total_units = units; P.dtype = dt; P.tiny = dtype_tiny(dt);
+  P.barrier = ctx->nb_sync; P.done = ctx->nb_sync + 1;
+  const int smem = NB_STAGES * NB_STAGE_BYTES + ((smax + NB_KC - 1) / NB_KC) * NB_KC * 2;
+  static PerDeviceOnce attr;
+  if (attr.need(ctx->device)) {
+    cudaError_t e = cudaFuncSetAttribute(k_norm_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, NB_STAGES * NB_STAGE_BYTES + NB_MAX_S * 2);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(k_norm_bounds)");
+  }
+  const int grid = units < ctx->num_sms ? units : ctx->num_sms;
+  void* args[1] = {&P};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_norm_bounds, dim3(grid), dim3(NB_THREADS), args, (size_t)smem, st);
+  ctx->launches++;
+  return check_cuda(ctx, e == cudaSuccess ? cudaGetLastError() : e, "k_norm_bounds");
+}
+
+static int run_bounds_unfused(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st);
+
 static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st) {
+  BoundJob fj[NB_MAX_JOBS], oj[2];
+  BoundFinish ff[NB_MAX_JOBS], of[2];
+  int nf = 0, no = 0;
+  for (int j = 0; j < n; ++j) {
+    const BoundFinish f = fin ? fin[j] : BoundFinish{2, 0.f, 0.f, 0.f, nullptr, nullptr};
+    if (bound_fusable(ctx, dt, jb[j]) && nf < NB_MAX_JOBS) { fj[nf] = jb[j]; ff[nf++] = f; }
+    else if (no < 2) { oj[no] = jb[j]; of[no++] = f; }
+    else return PSGD_ERR_INVALID_ARG;
+  }
+  if (nf) { int rc = run_bounds_fused(ctx, dt, fj, nf, ff, st); if (rc) return rc; }
+  if (no) { int rc = run_bounds_unfused(ctx, dt, oj, no, of, st); if (rc) return rc; }
+  return PSGD_OK;
+}
+
+// round-1 form: probe initialisation, four grouped GEMM launches, finish -- kept for fp32 / small / unaligned matrices (SIMT products)
+static int run_bounds_unfused(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st) {
   const float tiny = dtype_tiny(dt);
   bool tc_form[2];
   for (int j = 0; j < n; ++j) {
@@ -513,6 +569,16 @@ int psgd_create(psgd_handle_t* out, int device) {
     }
     cudaSetDevice(prev);
   }
+  {  // grid-barrier / completion counters of the fused norm-bound kernel (self-resetting)
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (coop && cudaMalloc(&ctx->nb_sync, 256) == cudaSuccess) cudaMemset(ctx->nb_sync, 0, 256);
+    else { ctx->nb_sync = nullptr; cudaGetLastError(); }
+    cudaSetDevice(prev);
+  }
   *out = reinterpret_cast<psgd_handle_t>(ctx);
   return PSGD_OK;
 }
@@ -520,6 +586,7 @@ int psgd_create(psgd_handle_t* out, int device) {
 void psgd_destroy(psgd_handle_t h) {
   Ctx* ctx = reinterpret_cast<Ctx*>(h);
   if (!ctx) return;
+  if (ctx->nb_sync) cudaFree(ctx->nb_sync);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws_count) cudaFree(ctx->ws_count);
   for (int i = 0; i < 2; ++i) if (ctx->x3_buf[i]) cudaFree(ctx->x3_buf[i]);

@@ -1,0 +1,384 @@
+// bounds.cuh -- norm_lower_bound_spd / norm_lower_bound_skh (psgd.py:46-93) as ONE persistent cooperative kernel per group of matrices.
+//
+// The reference evaluates a bound as: nf = max diag (spd) / max |A| (skh); A' = A / nf; j = argmax row norm; V = A'[j] + sgn(<A'[j], V0>) V0
+// (32 probes); then four dependent products V <- V A' with a row normalisation after the 1st and 3rd, and returns nf * max row norm.
+// Each product needs ALL of A (32 MB at s = 4096) for 1 GFLOP of work: memory-bound, and A (plus the second factor's matrix) fits in the
+// 126 MB L2, so the whole evaluation can run out of L2 -- if it is one kernel.  Round 1 issued it as 1 + 4 + 1 launches per pair of
+// factors (about 100 us at s = 4096); here every CTA of a persistent grid keeps a 64-column slab of one matrix per step and the steps are
+// separated by grid barriers:
+//
+//   phase I   : per slab, partial dot products <A'[j], V0[p]> (the signs of the probe rotation, psgd.py:63)          -> barrier
+//   step 0    : V1 = (A'[j] + sgn V0) A'      the rotated probes are formed on the fly in shared memory               -> barrier
+//   step 1    : V2 = normalise(V1) A'         the normalisation (psgd.py:66) is a per-probe factor of the epilogue    -> barrier
+//   step 2    : V3 = V2 A'                                                                                             -> barrier
+//   step 3    : row norms of normalise(V3) A' only (nothing stored)
+//   finish    : the CTA that finishes last turns the norms into the bound and into what its consumer needs (Lipschitz update + step
+//               sizes of the dense factor, psgd.py:413-415; the Procrustes normaliser, psgd.py:118)
+//
+// Work unit = (matrix, 64-column slab): out[32 x 64] = V[32 x s] A[s x 64], K streamed in 128-row stages through a cp.async ring
+// (A stage 16 KB + V stage 8 KB, XOR-swizzled for ldmatrix), 8 warps each taking one k16 slice of every stage on mma.sync m16n8k16
+// (bf16 in, fp32 accumulate; 32 probes are far below a tcgen05 tile and the bound is L2 bandwidth), cross-warp reduction through
+// shared memory, epilogue: scale, round to bf16, store, per-probe sums of squares (atomics, 32 per unit).
+#pragma once
+#include "common.cuh"
+#include "kron_kernels.cuh"
+
+namespace psgd {
+
+constexpr int NB_W = 64;          // columns of A per work unit
+constexpr int NB_KC = 128;        // k rows per pipeline stage (8 warps x 16)
+constexpr int NB_STAGES = 5;
+constexpr int NB_THREADS = 256;
+constexpr int NB_MAX_JOBS = 16;
+constexpr int NB_MAX_S = 16384;   // the selected row of A is kept in shared memory (2 bytes per column)
+constexpr int NB_A_BYTES = NB_KC * NB_W * 2;
+constexpr int NB_V_BYTES = 32 * NB_KC * 2;
+constexpr int NB_STAGE_BYTES = NB_A_BYTES + NB_V_BYTES;
+constexpr int NB_RED_LD = 72;     // floats per row of the cross-warp reduction buffer (64 + 8: conflict-free float2 stores)
+static_assert(8 * 32 * NB_RED_LD * 4 <= NB_STAGES * NB_STAGE_BYTES, "reduction buffer aliases the pipeline stages");
+
+struct NbJob {
+  const bf16* A;          // s x s, row-major, ld = s
+  const bf16* V0;         // 32 x s probes (psgd.py:62 / 87)
+  const float* row_sumsq; // s: squared row norms of A (from the producing kernel's epilogue)
+  const float* nf_src;    // max diag (spd) or max |A| (skh)
+  bf16* Va; bf16* Vb;     // 32 x s ping-pong
+  float* scal;            // SC_* block
+  float* rn1; float* rn3; float* rn4; float* dots;   // 32 floats each, zero on entry
+  int s;
+  int unit0, nunits;
+  int mode;               // finish: 0 dense-factor L update + step sizes, 1 Procrustes normaliser, 2 bound only
+  float t2, lr, betaL;
+  float* L; float* fs;
+};
+
+struct NbParams {
+  NbJob job[NB_MAX_JOBS];
+  int njobs;
+  int total_units;
+  int dtype;
+  float tiny;
+  unsigned* barrier;      // grid barrier counter (zero on entry, reset by the finishing CTA)
+  unsigned* done;
+};
+
+__device__ __forceinline__ unsigned nb_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all CTAs of the (cooperative, co-resident) grid; `target` = gridDim.x * number of barriers so far.  Bounded spin: a bug must trap,
+// not hang the GPU.
+__device__ __forceinline__ void nb_grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (nb_ld_acquire(counter) < target) {
+      __nanosleep(40);
+      if (++spins == 4096u) t0 = clock64();
+      if (spins > 4096u && (spins & 1023u) == 0u && clock64() - t0 > 8000000000LL) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void nb_cp_async16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nb_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void nb_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void nb_ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void nb_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void nb_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// argmax_i row_sumsq[i] (first maximal index, like torch.argmax) by the whole block; result broadcast through shared memory
+__device__ __forceinline__ int nb_block_argmax(const float* __restrict__ x, int s, float* sv, int* si) {
+  float best = -1.f;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < s; i += NB_THREADS) {
+    const float v = __ldcg(x + i);
+    if (v > best) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    best = lane < NB_THREADS / 32 ? sv[lane] : -1.f;
+    bi = lane < NB_THREADS / 32 ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) si[8] = (bi == 0x7fffffff) ? 0 : bi;
+  }
+  __syncthreads();
+  return si[8];
+}
+
+// bound = nf * max_p sqrt(rn[p]) (psgd.py:68) and its consumer -- the body of k_bound_finish for one matrix, run by one thread
+__device__ __forceinline__ void nb_finish_job(const NbJob& J, int dtype, float tiny) {
+  float v = 0.f;
+  for (int p = 0; p < 32; ++p) v = fmaxf(v, __ldcg(J.rn4 + p));
+  const float nf = __ldcg(J.nf_src) + tiny;
+  const float bound = round_to(dtype, nf * round_to(dtype, sqrtf(v)));
+  J.scal[SC_NF] = nf;
+  J.scal[SC_INV_NF] = 1.f / nf;
+  J.scal[SC_BOUND] = bound;
+  if (J.mode == 0) {
+    const float ell = round_to(dtype, bound + J.t2);
+    const float Ln = fmaxf(J.betaL * (*J.L) + (1.f - J.betaL) * ell, ell);
+    *J.L = Ln;
+    const float c = J.lr / Ln;
+    J.fs[FS_ALPHA] = -c;
+    J.fs[FS_BETA] = 1.f + c * J.t2;
+  } else if (J.mode == 1) {
+    J.fs[FS_INV_SR] = 1.f / (bound + tiny);
+  }
+}
+
+__global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_constant__ NbParams P) {
+  extern __shared__ __align__(128) uint8_t nb_smem[];
+  bf16* a_row = reinterpret_cast<bf16*>(nb_smem + NB_STAGES * NB_STAGE_BYTES);   // row j of A', zero beyond s (up to the stage boundary)
+  float* red = reinterpret_cast<float*>(nb_smem);
+  __shared__ float s_sgn[32];
+  __shared__ float s_scale[32];
+  __shared__ float s_sv[8];
+  __shared__ int s_si[9];
+  __shared__ int s_last;
+  const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(nb_smem));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned ncta = gridDim.x;
+  unsigned nbar = 0;
+
+  auto job_of = [&](int u) {
+    int ji = 0;
+    for (int i = 1; i < P.njobs; ++i)
+      if (u >= P.job[i].unit0) ji = i;
+    return ji;
+  };
+
+  // ------------------------------ phase I: signs of the probe rotation (psgd.py:63) ------------------------------
+  {
+    int cur = -1, j = 0;
+    float inv_nf = 0.f;
+    for (int u = blockIdx.x; u < P.total_units; u += ncta) {
+      const int ji = job_of(u);
+      const NbJob& J = P.job[ji];
+      if (ji != cur) {
+        j = nb_block_argmax(J.row_sumsq, J.s, s_sv, s_si);
+        inv_nf = 1.f / (__ldcg(J.nf_src) + P.tiny);
+        cur = ji;
+      }
+      const int p = tid >> 3, c0 = (u - J.unit0) * NB_W + (tid & 7) * 8;
+      float part = 0.f;
+      if (c0 < J.s) {
+        float a[8], v[8];
+        ld8(J.A + (size_t)j * J.s + c0, a);
+        ld8(J.V0 + (size_t)p * J.s + c0, v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) part += rbf(rbf(a[t] * inv_nf) * v[t]);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      if ((tid & 7) == 0 && part != 0.f) atomicAdd(J.dots + p, part);
+    }
+  }
+  nb_grid_barrier(P.barrier, ncta * (++nbar));
+
+  // ------------------------------ the four products ------------------------------
+  for (int st = 0; st < 4; ++st) {
+    int cur = -1;
+    float inv_nf = 0.f;
+    for (int u = blockIdx.x; u < P.total_units; u += ncta) {
+      const int ji = job_of(u);
+      const NbJob& J = P.job[ji];
+      const int s = J.s;
+      const int nkb = (s + NB_KC - 1) / NB_KC;
+      if (ji != cur) {
+        __syncthreads();                     // previous unit's readers of s_scale / a_row are done
+        inv_nf = 1.f / (__ldcg(J.nf_src) + P.tiny);
+        if (st == 0) {
+          const int j = nb_block_argmax(J.row_sumsq, s, s_sv, s_si);
+          for (int k = tid; k < nkb * NB_KC; k += NB_THREADS)
+            a_row[k] = k < s ? __float2bfloat16_rn(__bfloat162float(J.A[(size_t)j * s + k]) * inv_nf) : __float2bfloat16_rn(0.f);
+          if (tid < 32) { const float d = __ldcg(J.dots + tid); s_sgn[tid] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+          if (blockIdx.x == (unsigned)(J.unit0 % (int)ncta) && tid == 0) reinterpret_cast<int*>(J.scal)[SC_J] = j;
+        }
+        if (tid < 32) {
+          float sc = inv_nf;
+          if (st == 1) sc *= fminf(1.f / (sqrtf(__ldcg(J.rn1 + tid)) + P.tiny), 3.0e38f);
+          if (st == 3) sc *= fminf(1.f / (sqrtf(__ldcg(J.rn3 + tid)) + P.tiny), 3.0e38f);
+          s_scale[tid] = fminf(sc, 3.0e38f);
+        }
+        __syncthreads();
+        cur = ji;
+      }
+      const bf16* Vsrc = st == 0 ? J.V0 : (st == 2 ? J.Vb : J.Va);
+      bf16* Vdst = st == 1 ? J.Vb : J.Va;
+      const int col0 = (u - J.unit0) * NB_W;
+
+      auto issue = [&](int kb) {
+        const uint32_t sa = smem_base + (uint32_t)(kb % NB_STAGES) * NB_STAGE_BYTES;
+        const uint32_t sv = sa + NB_A_BYTES;
+        const int c = tid & 7;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (tid >> 3) + 32 * i;
+          const int gk = kb * NB_KC + r, gn = col0 + c * 8;
+          const bool ok = gk < s && gn < s;
+          nb_cp_async16(sa + r * 128 + ((c ^ (r & 7)) << 4), ok ? (const void*)(J.A + (size_t)gk * s + gn) : (const void*)J.A, ok ? 16 : 0);
+        }
+        const int cv = tid & 15;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int p = (tid >> 4) + 16 * i;
+          const int gk = kb * NB_KC + cv * 8;
+          const bool ok = gk < s;
+          nb_cp_async16(sv + p * 256 + (((cv & 8) | ((cv ^ p) & 7)) << 4), ok ? (const void*)(Vsrc + (size_t)p * s + gk) : (const void*)Vsrc,
+                        ok ? 16 : 0);
+        }
+      };
+
+      float acc[2][8][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+#pragma unroll 1
+      for (int kb = 0; kb < NB_STAGES - 1; ++kb) {
+        if (kb < nkb) issue(kb);
+        nb_cp_commit();
+      }
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        nb_cp_wait<NB_STAGES - 2>();
+        uint8_t* stg = nb_smem + (kb % NB_STAGES) * NB_STAGE_BYTES;
+        if (st == 0) {
+          // rotated probes V = A'[j] + sgn V0 (psgd.py:63), formed in place on the chunks this thread itself copied
+          const int cv = tid & 15;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int p = (tid >> 4) + 16 * i;
+            bf16* vp = reinterpret_cast<bf16*>(stg + NB_A_BYTES + p * 256 + (((cv & 8) | ((cv ^ p) & 7)) << 4));
+            float v[8], a[8], o[8];
+            ld8(vp, v);
+            ld8(a_row + kb * NB_KC + cv * 8, a);
+            const float sg = s_sgn[p];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) o[t] = a[t] + sg * v[t];
+            st8(vp, o);
+          }
+        }
+        __syncthreads();
+        if (kb + NB_STAGES - 1 < nkb) issue(kb + NB_STAGES - 1);
+        nb_cp_commit();
+        // this warp's k16 slice of the stage
+        const uint32_t sa = smem_base + (uint32_t)(kb % NB_STAGES) * NB_STAGE_BYTES;
+        const uint32_t sv = sa + NB_A_BYTES;
+        uint32_t af[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int row = mt * 16 + (lane & 15);
+          const int kc = 2 * warp + (lane >> 4);
+          nb_ldsm_x4(sv + row * 256 + (((kc & 8) | ((kc ^ row) & 7)) << 4), af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          const int krow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int nc = np * 2 + (lane >> 4);
+          uint32_t b0, b1, b2, b3;
+          nb_ldsm_x4_t(sa + krow * 128 + ((nc ^ (krow & 7)) << 4), b0, b1, b2, b3);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            nb_mma(acc[mt][2 * np], af[mt], b0, b1);
+            nb_mma(acc[mt][2 * np + 1], af[mt], b2, b3);
+          }
+        }
+      }
+      nb_cp_wait<0>();
+      __syncthreads();                       // every warp is done with the stages: the reduction buffer aliases them
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int p = mt * 16 + (lane >> 2) + hh * 8;
+            const int n = nt * 8 + (lane & 3) * 2;
+            *reinterpret_cast<float2*>(&red[(warp * 32 + p) * NB_RED_LD + n]) = make_float2(acc[mt][nt][2 * hh], acc[mt][nt][2 * hh + 1]);
+          }
+      __syncthreads();
+      {
+        const int p = tid >> 3, n0 = (tid & 7) * 8;
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float4 x = *reinterpret_cast<const float4*>(&red[(w * 32 + p) * NB_RED_LD + n0]);
+          const float4 y = *reinterpret_cast<const float4*>(&red[(w * 32 + p) * NB_RED_LD + n0 + 4]);
+          o[0] += x.x; o[1] += x.y; o[2] += x.z; o[3] += x.w; o[4] += y.x; o[5] += y.y; o[6] += y.z; o[7] += y.w;
+        }
+        const float sc = s_scale[p];
+        float ss = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { o[t] = rbf(o[t] * sc); ss = fmaf(o[t], o[t], ss); }
+        const bool ok = col0 + n0 < s;
+        if (ok && st < 3) st8(Vdst + (size_t)p * s + col0 + n0, o);
+        if (!ok) ss = 0.f;
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        float* rn = st == 0 ? J.rn1 : (st == 2 ? J.rn3 : (st == 3 ? J.rn4 : nullptr));
+        if (rn && (tid & 7) == 0) atomicAdd(rn + p, ss);
+      }
+      __syncthreads();                       // the next unit's copies overwrite the reduction buffer
+    }
+    if (st < 3) nb_grid_barrier(P.barrier, ncta * (++nbar));
+  }
+
+  // ------------------------------ finish: the CTA that arrives last ------------------------------
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(P.done, 1u);
+    s_last = (old == ncta - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (tid < P.njobs) nb_finish_job(P.job[tid], P.dtype, P.tiny);
+    __syncthreads();
+    if (tid == 0) { *P.barrier = 0u; *P.done = 0u; __threadfence(); }
+  }
+}
+
+}  // namespace psgd

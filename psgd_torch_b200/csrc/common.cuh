@@ -167,6 +167,7 @@ struct Ctx {
   // operands of an fp32 product re-expressed as bf16 triples (hi + mid + lo, concatenated along K) for the tensor cores; grown on demand
   void* x3_buf[2];
   size_t x3_cap[2];
+  unsigned* nb_sync; // [0] grid-barrier counter, [1] completion counter of the fused norm-bound kernel (bounds.cuh); null: not available
   int fp32_tensor;   // opt-in (psgd_set_fp32_tensor_cores): big fp32 products as bf16 triples on the tensor cores
 };
 

@@ -43,8 +43,11 @@ PARITY_LOG = os.environ.get("PSGD_PARITY_LOG", os.path.join(ROOT, "gpurun_out", 
 
 def pytest_sessionstart(session):
     markexpr = getattr(session.config.option, "markexpr", "") or ""
-    if "gpu" in markexpr and "not gpu" not in markexpr:
+    if "gpu" in markexpr and "not gpu" not in markexpr and not session.config.option.collectonly:
         try:
+            import torch
+            if not torch.cuda.is_available():
+                return
             os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
             with open(PARITY_LOG, "w") as f:
                 f.write("# case | quantity | measured normwise rel. error | tolerance | reference arithmetic's own error vs fp64 (bf16 cases)\n")

@@ -471,3 +471,74 @@ def test_kwns4_state_dict_roundtrip_and_dtensor_variant():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fname", ["refckpt_f32.pt", "refckpt_bf16_param.pt"])
+def test_kwns4_continues_from_a_reference_written_checkpoint(fname, monkeypatch):
+    """a state_dict() written by the unmodified reference wrapper mid-run (ddp.py:131-137 keys) is loaded into the
+    drop-in, which then continues on the engine and must follow the reference's own continuation (same gradients, same draws)."""
+    from psgd_torch_b200 import KWNS4, psgd
+    dev = _dev()
+    case = load_golden(fname)
+    ptype = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}[case["ptype"]]
+    pdtype = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}[case["pdtype"]]
+    p = torch.nn.Parameter(case["p_at_save"].clone().to(dev))
+    opt = KWNS4([p], preconditioner_dtype=pdtype, **case["kw"])
+    opt.load_state_dict(case["checkpoint"])
+    assert opt.state[p]["QL"][0][0].device.type == "cuda" and opt.state[p]["QL"][1][0].dtype == torch.float32
+    queue = []
+    monkeypatch.setattr(psgd, "draw_kron_noise", lambda G, Q: queue.pop(0))
+    for si in range(case["save_at"], len(case["steps"])):
+        st = case["steps"][si]
+        p.grad = st["grad"].clone().to(dev)
+        if st["do_update"]:
+            queue.append(_noise_to(st["noise"], dev))
+        opt.step()
+        tag = f"kwns4 resumed from reference checkpoint {fname} step {si}"
+        check(tag, "param", p, st["p"], 1e-6 if ptype == torch.float32 else 4e-3)
+        for i, (q, qr) in enumerate(zip(opt.state[p]["QL"][0], st["Q"])):
+            check(tag, f"Q[{i}]", q, qr, 1e-5)
+        for i, (l, lr_) in enumerate(zip(opt.state[p]["QL"][1], st["L"])):
+            check(tag, f"L[{i}]", l, lr_, 1e-5)
+        check(tag, "ema", opt.state[p]["ema"], st["ema"], 1e-5)
+    assert not queue
+
+
+@pytest.mark.parametrize("s", [128, 264, 1000, 2048, 4096])
+@pytest.mark.parametrize("kind", ["spd", "skh"])
+def test_fused_norm_bound_kernel_matches_oracle_and_the_unfused_form(s, kind):
+    """psgd.py:46-93 in bf16: the persistent cooperative kernel (bounds.cuh: probe rotation, four L2-resident products with grid barriers,
+    finish) against the bf16 oracle, an fp64 evaluation, and the round-1 form (separate GEMM launches, debug flag bit 8)."""
+    from psgd_torch_b200 import psgd, _lib
+    from oracle import psgd_oracle as orc
+    dev = _dev()
+    g = torch.Generator().manual_seed(s)
+    if kind == "spd":
+        W = torch.randn(s, s + 16, generator=g)
+        A = (W @ W.T / s + 2.0 * torch.diag(torch.rand(s, generator=g))).bfloat16()
+        f_e, f_o = psgd.norm_lower_bound_spd, orc.norm_lower_bound_spd
+    else:
+        R = torch.randn(s, s, generator=g) * (1.0 + torch.arange(s) % 3)[:, None]
+        A = (R - R.T).bfloat16()
+        A = (A - A.T).bfloat16() / 2      # exactly skew in bf16
+        f_e, f_o = psgd.norm_lower_bound_skh, orc.norm_lower_bound_skh
+    V0 = torch.randn(32, s, generator=g).bfloat16()
+    b_o = f_o(A, V0).float()
+    b_64 = f_o(A.double(), V0.double())
+    lib, h = _lib.load_library(), _lib.handle_for(dev)
+    l0 = _lib.launch_count(dev)
+    b_e = f_e(A.to(dev), V0=V0.to(dev)).float()
+    fused_launches = _lib.launch_count(dev) - l0
+    lib.psgd_debug_set_flags(h, 256)
+    try:
+        l0 = _lib.launch_count(dev)
+        b_u = f_e(A.to(dev), V0=V0.to(dev)).float()
+        unfused_launches = _lib.launch_count(dev) - l0
+    finally:
+        lib.psgd_debug_set_flags(h, 0)
+    tag = f"norm_lower_bound_{kind} bf16 s={s}"
+    assert fused_launches < unfused_launches and fused_launches <= 3, (fused_launches, unfused_launches)   # row stats + fused kernel + copy
+    check(tag, "bound (fused kernel) vs bf16 oracle", b_e, b_o, 2e-2, yard=b_64, floor=1e-2)
+    check(tag, "bound (fused kernel) vs unfused form", b_e, b_u, 2e-2)
+    lam = float(torch.linalg.matrix_norm(A.double(), 2))
+    assert 0.4 * lam <= float(b_e) <= 1.02 * lam
