@@ -351,28 +351,21 @@ static int run_procrustes(Ctx* ctx, int dt, DenseItem* it, int n, float max_step
   for (int i = 0; i < n; ++i) fin[i] = BoundFinish{1, 0.f, 0.f, 0.f, nullptr, it[i].f->fs};
   int rc = run_bounds(ctx, dt, jb, n, fin, st); if (rc) return rc;
   for (int i = 0; i < n; ++i) {
-    g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].Qn, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].RQ, it[i].s);     // RQ = R Qn / |R|
+    // RQ = R Qn / |R| with tr(RQ) and <RQ, R> (= -tr(R RQ): R is skew) from the epilogue    psgd.py:119-120
+    g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].Qn, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].RQ, it[i].s);
     g[i].epi.alpha_ptr = it[i].f->fs + FS_INV_SR; g[i].epi.trace = it[i].f->fs + FS_TR1;
+    g[i].epi.dotm = it[i].T; g[i].epi.ld_dot = it[i].s; g[i].epi.dot_out = it[i].f->fs + FS_DOT;
   }
   rc = launch_gemm_group(ctx, g, n, st); if (rc) return rc;
   for (int i = 0; i < n; ++i) {
-    g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].RQ, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].RRQ, it[i].s);    // RRQ = R RQ / |R|
-    g[i].epi.alpha_ptr = it[i].f->fs + FS_INV_SR; g[i].epi.trace = it[i].f->fs + FS_TR2;
+    // Q = Qn + a (RQ + a/2 RRQ), RRQ = R RQ / |R| never materialised: the step length a follows from the two traces the previous
+    // product left on the device (psgd.py:121-124; Epi::pro_fs)
+    g[i] = gemm_desc(dt, it[i].T, it[i].s, 0, it[i].RQ, it[i].s, 0, it[i].s, it[i].s, it[i].s, it[i].q, it[i].s);
+    g[i].epi.alpha_ptr = it[i].f->fs + FS_INV_SR; g[i].epi.pro_fs = it[i].f->fs; g[i].epi.pro_max_step = max_step;
+    g[i].epi.D = it[i].Qn; g[i].epi.ldd = it[i].s; g[i].epi.d_dtype = dt; g[i].epi.beta = 1.f;
+    g[i].epi.D2 = it[i].RQ; g[i].epi.ldd2 = it[i].s;
   }
-  rc = launch_gemm_group(ctx, g, n, st); if (rc) return rc;
-  for (int i = 0; i < n; ++i) {
-    const size_t numel = (size_t)it[i].s * it[i].s;
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    if (dt == PSGD_BF16 && numel % 8 == 0 && al16(it[i].Qn) && al16(it[i].RQ) && al16(it[i].RRQ) && al16(it[i].q)) {
-      k_procrustes_finish_bf16x8<<<ew_blocks(ctx, numel / 8), 256, 0, st>>>((const bf16*)it[i].Qn, (const bf16*)it[i].RQ, (const bf16*)it[i].RRQ,
-                                                                            (bf16*)it[i].q, numel / 8, it[i].f->fs, max_step);
-    } else {
-      DISPATCH_T(dt, (k_procrustes_finish<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)it[i].Qn, (const T*)it[i].RQ, (const T*)it[i].RRQ,
-                                                                                     (T*)it[i].q, numel, it[i].f->fs, max_step)));
-    }
-    LAUNCH_CHECK(ctx, "k_procrustes_finish");
-  }
-  return PSGD_OK;
+  return launch_gemm_group(ctx, g, n, st);
 }
 
 // psgd.py:412-416 for up to two dense factors: bound of term1, L update, Newton-Schulz step, procrustes

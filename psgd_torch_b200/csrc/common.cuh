@@ -48,6 +48,9 @@ __host__ __device__ inline float dtype_tiny(int) { return 1.1754943508222875e-38
 //   materialised low-precision tensors), accumulated with atomics into fp32 device buffers that the caller
 //   zeroed beforehand.
 // ---------------------------------------------------------------------------------------------
+// slots of the per-factor update scalars (device floats written by one kernel's epilogue / finish and read by the next kernel's epilogue)
+enum { FS_ALPHA = 0, FS_BETA = 1, FS_INV_SR = 2, FS_TR1 = 3, FS_TR2 = 4, FS_TR3 = 5, FS_DOT = 6, FS_COUNT = 8 };
+
 struct Epi {
   void* C;
   int ldc;
@@ -64,6 +67,18 @@ struct Epi {
   const float* d_row_scale;  // optional per-row / per-column factors of the D term (fp32): used to add back the bf16 rounding residual of
   const float* d_col_scale;  // the diagonal of P = Q^T Q, (P_bf16 + diag(resid)) X = P_bf16 X + resid_i X_ij
   float* diag_resid;       // [M]: (unrounded - rounded) value of C[i,i]
+  const void* D2;          // optional second addend: + beta2 * D2[i,j] (dtype d_dtype)
+  int ldd2;
+  float beta2;
+  // procrustes_step2 finish (psgd.py:121-124) folded into the epilogue of the product R (RQ): with tr1 = pro_fs[FS_TR1] = tr(RQ) and
+  // tr2 = tr(R RQ) / |R| = -pro_fs[FS_INV_SR] * pro_fs[FS_DOT] (R is skew: tr(R X) = -<R, X>, accumulated by the previous product's `dot`
+  // reduction), a = tr2 < 0 ? min(-tr1 / tr2, pro_max_step) : pro_max_step; then alpha *= a^2 / 2 and beta2 = a, so that with D = Q and
+  // D2 = RQ the product writes Q + a (RQ + a/2 RRQ) directly -- RRQ is never materialised and needs no extra pass
+  const float* pro_fs;
+  float pro_max_step;
+  const void* dotm;        // optional: dot_out += sum_ij C[i,j] * dotm[i,j] (dtype d_dtype, over the rounded C)
+  int ld_dot;
+  float* dot_out;
   // row (axis 1) / column (axis 2) normalisation folded with a device scalar: factor = min(*norm_inv_nf / (sqrt(norm_sumsq[idx]) + norm_tiny), 3e38)
   // (psgd.py:66 `V /= |V| + tiny` followed by the /nf of the next product; the clamp keeps 0 * factor = 0 when a probe row is exactly 0)
   const float* norm_sumsq;
@@ -84,6 +99,7 @@ __host__ inline Epi make_epi(void* C, int ldc, int out_dtype) {
   e.alpha = 1.f; e.alpha_ptr = nullptr;
   e.D = nullptr; e.ldd = 0; e.d_dtype = out_dtype; e.beta = 0.f; e.beta_ptr = nullptr;
   e.row_scale = nullptr; e.col_scale = nullptr; e.d_row_scale = nullptr; e.d_col_scale = nullptr; e.diag_resid = nullptr;
+  e.D2 = nullptr; e.ldd2 = 0; e.beta2 = 0.f; e.pro_fs = nullptr; e.pro_max_step = 0.f; e.dotm = nullptr; e.ld_dot = 0; e.dot_out = nullptr;
   e.norm_sumsq = nullptr; e.norm_inv_nf = nullptr; e.norm_tiny = 0.f; e.norm_axis = 0;
   e.row_sumsq = nullptr; e.col_sumsq = nullptr; e.diag_max = nullptr; e.abs_max = nullptr; e.trace = nullptr;
   e.total_sumsq = nullptr;
@@ -93,6 +109,13 @@ __host__ inline Epi make_epi(void* C, int ldc, int out_dtype) {
 // non-negative float max via integer atomics (buffer initialised to 0)
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
   if (v > 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+// step length of procrustes_step2 (psgd.py:121-123) from the device scalars described at Epi::pro_fs
+__device__ __forceinline__ float epi_procrustes_step(const Epi& e) {
+  const float tr1 = e.pro_fs[FS_TR1];
+  const float tr2 = -e.pro_fs[FS_INV_SR] * e.pro_fs[FS_DOT];
+  return (tr2 < 0.f) ? fminf(-tr1 / tr2, e.pro_max_step) : e.pro_max_step;
 }
 
 __device__ __forceinline__ float epi_norm_factor(const Epi& e, int idx) {

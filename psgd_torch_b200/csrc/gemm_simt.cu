@@ -75,8 +75,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
   const Epi& e = g.epi;
   float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
   float beta = e.beta * (e.beta_ptr ? *e.beta_ptr : 1.f);
+  float beta2 = e.beta2;
+  if (e.pro_fs) { const float a = epi_procrustes_step(e); alpha *= 0.5f * a * a; beta2 = a; }
   float csum[4] = {0.f, 0.f, 0.f, 0.f};
-  float tot = 0.f, amax = 0.f, tr = 0.f, dmax = 0.f;
+  float tot = 0.f, amax = 0.f, tr = 0.f, dmax = 0.f, dot = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int gm = m0 + ty * 4 + i;
@@ -92,7 +94,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
       if (e.col_scale) v *= e.col_scale[gn];
       if (e.norm_axis == 2) v *= epi_norm_factor(e, gn);
       if (e.D) v += beta * ld_as_float(e.D, e.d_dtype, (size_t)gm * e.ldd + gn) * (e.d_row_scale ? e.d_row_scale[gm] : 1.f) * (e.d_col_scale ? e.d_col_scale[gn] : 1.f);
+      if (e.D2) v += beta2 * ld_as_float(e.D2, e.d_dtype, (size_t)gm * e.ldd2 + gn);
       float r = round_to(e.out_dtype, v);
+      if (e.dotm) dot = fmaf(r, ld_as_float(e.dotm, e.d_dtype, (size_t)gm * e.ld_dot + gn), dot);
       if (e.diag_resid && gm == gn) e.diag_resid[gm] = v - r;
       st_from_float(e.C, e.out_dtype, (size_t)gm * e.ldc + gn, v);
       rsum += r * r;
@@ -111,6 +115,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc g) {
     }
   }
   if (e.total_sumsq) { float s = warp_sum(tot); if ((tid & 31) == 0) atomicAdd(e.total_sumsq, s); }
+  if (e.dot_out) { float s = warp_sum(dot); if ((tid & 31) == 0 && s != 0.f) atomicAdd(e.dot_out, s); }
   if (e.abs_max) { float s = warp_max(amax); if ((tid & 31) == 0) atomic_max_nonneg(e.abs_max, s); }
   if (e.trace && m0 < n0 + SM_T && n0 < m0 + SM_T) { float s = warp_sum(tr); if ((tid & 31) == 0 && s != 0.f) atomicAdd(e.trace, s); }
   if (e.diag_max && m0 < n0 + SM_T && n0 < m0 + SM_T) { float s = warp_max(dmax); if ((tid & 31) == 0) atomic_max_nonneg(e.diag_max, s); }

@@ -240,13 +240,43 @@ __device__ __forceinline__ void locate_tile(const TcGroup& g, int t, int bn_full
 // epilogue for one 32-column chunk of one accumulator row
 // ------------------------------------------------------------------------------------------------
 struct RowAcc {
-  float row_sumsq, tot, amax, tr, dmax;
+  float row_sumsq, tot, amax, tr, dmax, dot;
 };
 
 // mirror: 0 = plain block, 1 = strictly-upper block of a symmetric output (also writes C[col][row] and credits the column sums to
 // row_sumsq[col], i.e. the row norms of the mirrored block)
+// v[j] += f * X[row, col0 + j] (32 columns, 16-byte loads; N % 8 == 0 so every vector is fully in or out of range)
+__device__ __forceinline__ void epi_add_tile(float* v, const void* X, int x_dtype, int ldx, int row, int col0, int N, float f) {
+  if (x_dtype == PSGD_BF16) {
+    const bf16* xp = reinterpret_cast<const bf16*>(X) + (size_t)row * ldx + col0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (col0 + q * 8 < N) {
+        uint4 u = *reinterpret_cast<const uint4*>(xp + q * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 x = __bfloat1622float2(h[t]);
+          v[q * 8 + 2 * t] = fmaf(f, x.x, v[q * 8 + 2 * t]);
+          v[q * 8 + 2 * t + 1] = fmaf(f, x.y, v[q * 8 + 2 * t + 1]);
+        }
+      }
+    }
+  } else {
+    const float* xp = reinterpret_cast<const float*>(X) + (size_t)row * ldx + col0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (col0 + q * 4 < N) {
+        float4 x = *reinterpret_cast<const float4*>(xp + q * 4);
+        v[q * 4] = fmaf(f, x.x, v[q * 4]); v[q * 4 + 1] = fmaf(f, x.y, v[q * 4 + 1]);
+        v[q * 4 + 2] = fmaf(f, x.z, v[q * 4 + 2]); v[q * 4 + 3] = fmaf(f, x.w, v[q * 4 + 3]);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int row, int col0, uint32_t* raw, float alpha,
-                                               float beta, int lane, RowAcc& ra, int mirror) {
+                                               float beta, float beta2, int lane, RowAcc& ra, int mirror) {
   float v[32];
   const bool row_ok = row < M;
   float rs = (e.row_scale && row_ok) ? e.row_scale[row] : 1.f;
@@ -292,6 +322,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
       }
     }
   }
+  if (e.D2 && row_ok) epi_add_tile(v, e.D2, e.d_dtype, e.ldd2, row, col0, N, beta2);
   float diag_unrounded = 0.f;
   const bool on_diag = row >= col0 && row < col0 + 32;
   if (e.diag_resid && on_diag) {
@@ -344,11 +375,21 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, int M, int N, int r
     }
   }
   // reductions over the rounded values; out-of-range elements contribute 0
-  const bool need_red = e.row_sumsq || e.col_sumsq || e.total_sumsq || e.abs_max || e.trace || e.diag_max;
+  const bool need_red = e.row_sumsq || e.col_sumsq || e.total_sumsq || e.abs_max || e.trace || e.diag_max || e.dot_out;
   if (!need_red) return;
 #pragma unroll
   for (int j = 0; j < 32; ++j)
     if (!row_ok || col0 + j >= N) v[j] = 0.f;
+  if (e.dot_out && row_ok) {
+    float m[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m[j] = 0.f;
+    epi_add_tile(m, e.dotm, e.d_dtype, e.ld_dot, row, col0, N, 1.f);
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d = fmaf(v[j], m[j], d);
+    ra.dot += d;
+  }
   float s = 0.f, am = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) { s = fmaf(v[j], v[j], s); am = fmaxf(am, fabsf(v[j])); }
@@ -534,12 +575,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       locate_tile(g, t, BN, pi, tm, tn, kslice);
       const TcProblem& p = g.p[pi];
       const Epi& e = p.epi;
-      const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
+      float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
       const float beta = e.beta * (e.beta_ptr ? *e.beta_ptr : 1.f);
+      float beta2 = e.beta2;
+      if (e.pro_fs) { const float a = epi_procrustes_step(e); alpha *= 0.5f * a * a; beta2 = a; }
       mbar_wait_relaxed(tfull_bar(acc), acc_phase, g.error_flag);
       tc_fence_after();
       const int row = tm * TC_BM + quarter * 32 + lane;
-      RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
+      RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const int bn = p.bn_eff;
       const int nchunks = bn / 32;
       bool run_epilogue = true;
@@ -632,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           } else {
             tmem_ld_wait();
           }
-          if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
+          if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, beta2, lane, ra, mirror);
         }
       }
       // release the accumulator buffer to the MMA warp
@@ -642,6 +685,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // per-row / per-warp reductions
       if (e.row_sumsq && row < p.M) atomicAdd(&e.row_sumsq[row], ra.row_sumsq);
       if (e.total_sumsq) { float s = warp_sum(ra.tot); if (lane == 0) atomicAdd(e.total_sumsq, s); }
+      if (e.dot_out) { float s = warp_sum(ra.dot); if (lane == 0 && s != 0.f) atomicAdd(e.dot_out, s); }
       if (e.abs_max) { float s = warp_max(ra.amax); if (lane == 0) atomic_max_nonneg(e.abs_max, s); }
       if (e.trace) { float s = warp_sum(ra.tr); if (lane == 0 && s != 0.f) atomicAdd(e.trace, s); }
       if (e.diag_max) { float s = warp_max(ra.dmax); if (lane == 0) atomic_max_nonneg(e.diag_max, s); }
@@ -874,13 +918,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm
       locate_tile2(g, t, pi, pm, tn);
       const TcProblem& p = g.p[pi];
       const Epi& e = p.epi;
-      const float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
+      float alpha = e.alpha * (e.alpha_ptr ? *e.alpha_ptr : 1.f);
       const float beta = e.beta * (e.beta_ptr ? *e.beta_ptr : 1.f);
+      float beta2 = e.beta2;
+      if (e.pro_fs) { const float a = epi_procrustes_step(e); alpha *= 0.5f * a * a; beta2 = a; }
       mbar_wait_relaxed(tfull_bar(acc), acc_phase, g.error_flag);
       tc_fence_after();
       const int tm = pm * 2 + (int)rank;                 // this CTA's 128-row block
       const int row = tm * TC_BM + quarter * 32 + lane;
-      RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f};
+      RowAcc ra = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = tn * BN + c * 32;
@@ -894,13 +940,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1) gemm
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c * 32);
         tmem_ld_32x32(taddr, raw);
         tmem_ld_wait();
-        if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, lane, ra, mirror);
+        if (col0 < p.N) epilogue_chunk(e, p.M, p.N, row, col0, raw, alpha, beta, beta2, lane, ra, mirror);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_tempty0 : leader_tempty1);
       if (e.row_sumsq && row < p.M) atomicAdd(&e.row_sumsq[row], ra.row_sumsq);
       if (e.total_sumsq) { float s = warp_sum(ra.tot); if (lane == 0) atomicAdd(e.total_sumsq, s); }
+      if (e.dot_out) { float s = warp_sum(ra.dot); if (lane == 0 && s != 0.f) atomicAdd(e.dot_out, s); }
       if (e.abs_max) { float s = warp_max(ra.amax); if (lane == 0) atomic_max_nonneg(e.abs_max, s); }
       if (e.trace) { float s = warp_sum(ra.tr); if (lane == 0 && s != 0.f) atomicAdd(e.trace, s); }
       if (e.diag_max) { float s = warp_max(ra.dmax); if (lane == 0) atomic_max_nonneg(e.diag_max, s); }
@@ -965,10 +1012,10 @@ bool tc_eligible(const GemmDesc& g) {
   if (g.N % 8) return false;
   const int ovec = g.epi.out_dtype == PSGD_BF16 ? 8 : 4;
   if (g.epi.ldc % ovec) return false;
-  if (g.epi.D) {
-    const int dvec = g.epi.d_dtype == PSGD_BF16 ? 8 : 4;
-    if (!al16(g.epi.D) || g.epi.ldd % dvec) return false;
-  }
+  const int dvec = g.epi.d_dtype == PSGD_BF16 ? 8 : 4;
+  if (g.epi.D && (!al16(g.epi.D) || g.epi.ldd % dvec)) return false;
+  if (g.epi.D2 && (!al16(g.epi.D2) || g.epi.ldd2 % dvec)) return false;
+  if (g.epi.dotm && (!al16(g.epi.dotm) || g.epi.ld_dot % dvec)) return false;
   return true;
 }
 
@@ -997,7 +1044,7 @@ static int launch_tc(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStre
     if (rc) return rc;
     p.tiles_m = (g.M + TC_BM - 1) / TC_BM;
     p.tiles_n = (g.N + BN - 1) / BN;
-    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis) ? 1 : 0;
+    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.D2 && !g.epi.dotm && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis) ? 1 : 0;
     if (p.sym) {
       ntiles[i] = 0;
       for (int tm = 0; tm < p.tiles_m; ++tm) ntiles[i] += p.tiles_n - (tm * TC_BM) / BN;
@@ -1100,7 +1147,7 @@ static int tc2_choice(const Ctx* ctx, const GemmDesc* gs, int n) {
   for (int i = 0; i < n; ++i) {
     const GemmDesc& g = gs[i];
     if (g.M < 256 || g.N <= 128) return 0;
-    const bool sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis);
+    const bool sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.D2 && !g.epi.dotm && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis);
     const long pm = (g.M + TC2_BM - 1) / TC2_BM, pn = (g.N + TC2_BN - 1) / TC2_BN;
     const long tm = (g.M + TC_BM - 1) / TC_BM;
     if (sym) {
@@ -1154,7 +1201,7 @@ static int launch_tc2(Ctx* ctx, TcGroup& grp, const GemmDesc* gs, int n, cudaStr
     p.tiles_m = (g.M + TC2_BM - 1) / TC2_BM;
     p.tiles_n = (g.N + Cfg::BN - 1) / Cfg::BN;
     p.tile_start = tiles; p.tile_first = 0; p.splits = 1; p.kb_split = 0; p.ws_slot0 = 0; p.nsplit = 1; p.bn_eff = Cfg::BN;
-    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis) ? 1 : 0;
+    p.sym = (!(ctx->debug_flags & 1) && g.sym && g.M == g.N && !g.epi.D && !g.epi.D2 && !g.epi.dotm && !g.epi.row_scale && !g.epi.col_scale && !g.epi.col_sumsq && !g.epi.norm_axis) ? 1 : 0;
     if (p.sym) {
       for (int pm = 0; pm < p.tiles_m; ++pm) tiles += p.tiles_n - pm;
     } else {

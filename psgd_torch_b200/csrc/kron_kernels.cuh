@@ -8,8 +8,7 @@ namespace psgd {
 
 // slots of the per-bound scalar block (floats)
 enum { SC_INV_NF = 0, SC_NF = 1, SC_J = 2, SC_BOUND = 3, SC_COUNT = 8 };
-// slots of the per-factor update scalars
-enum { FS_ALPHA = 0, FS_BETA = 1, FS_INV_SR = 2, FS_TR1 = 3, FS_TR2 = 4, FS_TR3 = 5, FS_COUNT = 8 };
+// (slots of the per-factor update scalars FS_*: common.cuh)
 
 // 8 bf16 <-> 8 floats through one 16-byte access
 __device__ __forceinline__ void ld8(const bf16* p, float* x) {
@@ -272,33 +271,6 @@ __global__ void k_bound_finish(const float* __restrict__ rn, int k, float* scal,
     } else if (mode == 1) {
       fs[FS_INV_SR] = 1.f / (bound + tiny);
     }
-  }
-}
-
-// a = tr_RRQ < 0 ? min(-tr_RQ/tr_RRQ, max_step) : max_step;  Q = Qn + a*(RQ + 0.5*a*RRQ)   psgd.py:121-124
-template <typename T>
-__global__ void k_procrustes_finish(const T* __restrict__ Qn, const T* __restrict__ RQ, const T* __restrict__ RRQ,
-                                    T* __restrict__ Q, size_t numel, const float* __restrict__ fs, float max_step) {
-  float tr1 = fs[FS_TR1], tr2 = fs[FS_TR2];
-  float a = (tr2 < 0.f) ? fminf(-tr1 / tr2, max_step) : max_step;
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < numel; i += stride)
-    Q[i] = from_f<T>(to_f<T>(Qn[i]) + a * (to_f<T>(RQ[i]) + 0.5f * a * to_f<T>(RRQ[i])));
-}
-
-__global__ void k_procrustes_finish_bf16x8(const bf16* __restrict__ Qn, const bf16* __restrict__ RQ, const bf16* __restrict__ RRQ,
-                                           bf16* __restrict__ Q, size_t nvec, const float* __restrict__ fs, float max_step) {
-  const float tr1 = fs[FS_TR1], tr2 = fs[FS_TR2];
-  const float a = (tr2 < 0.f) ? fminf(-tr1 / tr2, max_step) : max_step;
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < nvec; i += stride) {
-    float q[8], r1[8], r2[8], o[8];
-    ld8(Qn + i * 8, q); ld8(RQ + i * 8, r1); ld8(RRQ + i * 8, r2);
-#pragma unroll
-    for (int t = 0; t < 8; ++t) o[t] = q[t] + a * (r1[t] + 0.5f * a * r2[t]);
-    st8(Q + i * 8, o);
   }
 }
 
