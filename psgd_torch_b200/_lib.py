@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libpsgd_b200.so")
 
 PSGD_BF16, PSGD_F32 = 0, 1
 PSGD_DIAG, PSGD_DENSE = 0, 1
+MAX_BATCH = 16   # units per batched call (KB_MAX in csrc/kron_kernels.cuh)
 # psgd_dq_t / stage bits of psgd_kron_update
 DQ_CODES = {"Q0.5EQ1.5": 0, "Q0p5EQ1p5": 0, "EQ": 1, "QEP": 2, "QEQ": 3, "QUAD": 4, "QUAD4P": 5, "PRO4P": 6}
 STAGE_PREPARE, STAGE_FACTOR_L, STAGE_FACTOR_R, STAGE_BALANCE = 1, 2, 4, 8
@@ -55,6 +56,10 @@ SYMBOLS = {
     "psgd_kron_workspace_bytes": (_sz, [_vp, C.POINTER(KronT)]),
     "psgd_kron_whiten_q0p5eq1p5_update": (_i, [_vp, C.POINTER(KronT), _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),
     "psgd_kron_precond_grad": (_i, [_vp, C.POINTER(KronT), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "psgd_kron_batch_workspace_bytes": (_sz, [_vp, C.POINTER(KronT), _i]),
+    "psgd_kron_whiten_q0p5eq1p5_update_batched": (_i, [_vp, C.POINTER(KronT), _i, C.POINTER(_vp), _f, _f, _f, C.POINTER(KronNoiseT),
+                                                  C.POINTER(_i), _vp, _sz, _vp]),
+    "psgd_kron_precond_grad_batched": (_i, [_vp, C.POINTER(KronT), _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _sz, _vp]),
     "psgd_kron_balance": (_i, [_vp, C.POINTER(KronT), _vp, _sz, _vp]),
     "psgd_kron_update_workspace_bytes": (_sz, [_vp, C.POINTER(KronT), _i]),
     "psgd_kron_update": (_i, [_vp, C.POINTER(KronT), _i, _vp, _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),

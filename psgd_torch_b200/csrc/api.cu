@@ -164,12 +164,9 @@ static void layout_bound(Bump& b, BoundWs& w) {
   w.sc1 = (float*)b.take(32 * 4); w.sc3 = (float*)b.take(32 * 4);
 }
 
-static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
-  Bump b(base);
-  const int es = dtype_size(k->dtype);
-  const size_t m = k->m, n = k->has_r ? k->n : 1;
+// zeroed part (reductions, scalars) and buffers of one unit; a batch lays out every unit's zeroed part first so that ONE memset clears them
+static void layout_kron_zero(Bump& b, const psgd_kron_t* k, KronWs& w) {
   const int sdim[2] = {k->m, k->has_r ? k->n : 0};
-  const int dense[2] = {k->kind_l == PSGD_DENSE, k->has_r && k->kind_r == PSGD_DENSE};
   w.zero_begin = (char*)b.take(0);
   size_t z0 = b.off;
   for (int i = 0; i < 2; ++i) {
@@ -186,6 +183,13 @@ static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
   }
   w.bal = (float*)b.take(2 * 4);
   w.zero_bytes = b.off - z0;
+}
+
+static void layout_kron_bufs(Bump& b, const psgd_kron_t* k, KronWs& w) {
+  const int es = dtype_size(k->dtype);
+  const size_t m = k->m, n = k->has_r ? k->n : 1;
+  const int sdim[2] = {k->m, k->has_r ? k->n : 0};
+  const int dense[2] = {k->kind_l == PSGD_DENSE, k->has_r && k->kind_r == PSGD_DENSE};
   w.qsq[0] = (float*)b.take(m * 4);
   w.qsq[1] = (float*)b.take(n * 4);
   w.presid[0] = (float*)b.take(m * 4);
@@ -196,16 +200,43 @@ static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
     for (int j = 0; j < 4; ++j) w.S[i][j] = b.take(sd * sd * es);
     w.Va[i] = b.take(32 * sd * es); w.Vb[i] = b.take(32 * sd * es);
   }
+}
+
+static void layout_kron(const psgd_kron_t* k, void* base, KronWs& w) {
+  Bump b(base);
+  layout_kron_zero(b, k, w);
+  layout_kron_bufs(b, k, w);
   w.total = b.off;
 }
 
-// up to TC_MAX independent GEMMs: one grouped tcgen05 launch when all qualify, else one launch each
+// n units: [zeroed parts of all units][buffers of unit 0][buffers of unit 1]...
+static size_t layout_kron_batch(const psgd_kron_t* ks, int n, void* base, KronWs* w, char** zero_begin, size_t* zero_bytes) {
+  Bump b(base);
+  char* z0p = (char*)b.take(0);
+  const size_t z0 = b.off;
+  for (int u = 0; u < n; ++u) layout_kron_zero(b, ks + u, w[u]);
+  if (zero_begin) *zero_begin = z0p;
+  if (zero_bytes) *zero_bytes = b.off - z0;
+  for (int u = 0; u < n; ++u) { layout_kron_bufs(b, ks + u, w[u]); w[u].total = b.off; }
+  return b.off;
+}
+
+// any number of independent GEMMs: runs of tcgen05-eligible problems share grouped launches (TC_GROUP_MAX per launch), the rest go one by one
+constexpr int TC_GROUP_MAX = 4;
 static int launch_gemm_group(Ctx* ctx, const GemmDesc* gs, int n, cudaStream_t st) {
-  if (n <= 0) return PSGD_OK;
-  bool all_tc = ctx->gemm_path != 1 && n <= 4;
-  for (int i = 0; i < n && all_tc; ++i) all_tc = tc_eligible(gs[i]) && gs[i].M > 0 && gs[i].N > 0;
-  if (all_tc) return launch_gemm_tc_group(ctx, gs, n, st);
-  for (int i = 0; i < n; ++i) { int rc = launch_gemm(ctx, gs[i], st); if (rc) return rc; }
+  int i = 0;
+  while (i < n) {
+    if (gs[i].M <= 0 || gs[i].N <= 0) { ++i; continue; }
+    if (ctx->gemm_path != 1 && tc_eligible(gs[i])) {
+      int j = i + 1;
+      while (j < n && j - i < TC_GROUP_MAX && gs[j].M > 0 && gs[j].N > 0 && tc_eligible(gs[j])) ++j;
+      int rc = launch_gemm_tc_group(ctx, gs + i, j - i, st); if (rc) return rc;
+      i = j;
+    } else {
+      int rc = launch_gemm(ctx, gs[i], st); if (rc) return rc;
+      ++i;
+    }
+  }
   return PSGD_OK;
 }
 
@@ -244,10 +275,10 @@ static int run_bounds_fused(Ctx* ctx, int dt, const BoundJob* jb, int n, const B
   }
   P.njobs = n; P.total_units = units; P.dtype = dt; P.tiny = dtype_tiny(dt);
   P.barrier = ctx->nb_sync; P.done = ctx->nb_sync + 1;
-  const int smem = NB_STAGES * NB_STAGE_BYTES + ((smax + NB_KC - 1) / NB_KC) * NB_KC * 2;
+  const int smem = NB_RING_BYTES + ((smax + NB_KC - 1) / NB_KC) * NB_KC * 2;
   static PerDeviceOnce attr;
   if (attr.need(ctx->device)) {
-    cudaError_t e = cudaFuncSetAttribute(k_norm_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, NB_STAGES * NB_STAGE_BYTES + NB_MAX_S * 2);
+    cudaError_t e = cudaFuncSetAttribute(k_norm_bounds, cudaFuncAttributeMaxDynamicSharedMemorySize, NB_RING_BYTES + NB_MAX_S * 2);
     if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(k_norm_bounds)");
   }
   const int grid = units < ctx->num_sms ? units : ctx->num_sms;
@@ -260,17 +291,20 @@ static int run_bounds_fused(Ctx* ctx, int dt, const BoundJob* jb, int n, const B
 static int run_bounds_unfused(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st);
 
 static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st) {
-  BoundJob fj[NB_MAX_JOBS], oj[2];
-  BoundFinish ff[NB_MAX_JOBS], of[2];
-  int nf = 0, no = 0;
+  BoundJob fj[NB_MAX_JOBS];
+  BoundFinish ff[NB_MAX_JOBS];
+  int nf = 0;
   for (int j = 0; j < n; ++j) {
     const BoundFinish f = fin ? fin[j] : BoundFinish{2, 0.f, 0.f, 0.f, nullptr, nullptr};
-    if (bound_fusable(ctx, dt, jb[j]) && nf < NB_MAX_JOBS) { fj[nf] = jb[j]; ff[nf++] = f; }
-    else if (no < 2) { oj[no] = jb[j]; of[no++] = f; }
-    else return PSGD_ERR_INVALID_ARG;
+    if (bound_fusable(ctx, dt, jb[j])) {
+      fj[nf] = jb[j]; ff[nf++] = f;
+      if (nf == NB_MAX_JOBS) { int rc = run_bounds_fused(ctx, dt, fj, nf, ff, st); if (rc) return rc; nf = 0; }
+    } else {
+      BoundJob one = jb[j];
+      int rc = run_bounds_unfused(ctx, dt, &one, 1, &f, st); if (rc) return rc;
+    }
   }
   if (nf) { int rc = run_bounds_fused(ctx, dt, fj, nf, ff, st); if (rc) return rc; }
-  if (no) { int rc = run_bounds_unfused(ctx, dt, oj, no, of, st); if (rc) return rc; }
   return PSGD_OK;
 }
 
@@ -333,9 +367,11 @@ struct DenseItem {
 };
 
 // procrustes_step2 (psgd.py:101-124) on it[i].Qn -> writes it[i].q
+constexpr int KB_ITEMS = 2 * KB_MAX;   // dense factors travelling together through one batched update
 static int run_procrustes(Ctx* ctx, int dt, DenseItem* it, int n, float max_step, cudaStream_t st) {
-  BoundJob jb[2];
-  GemmDesc g[2];
+  if (n > KB_ITEMS) return PSGD_ERR_INVALID_ARG;
+  BoundJob jb[KB_ITEMS];
+  GemmDesc g[KB_ITEMS];
   for (int i = 0; i < n; ++i) {
     const int s = it[i].s;
     dim3 grid((s + 63) / 64, (s + 63) / 64);
@@ -347,7 +383,7 @@ static int run_procrustes(Ctx* ctx, int dt, DenseItem* it, int n, float max_step
     LAUNCH_CHECK(ctx, "k_skew");
     jb[i] = BoundJob{it[i].T, s, it[i].v_skh, it[i].f->r_row_sumsq, it[i].f->r_abs_max, &it[i].f->b_skh, it[i].Va, it[i].Vb};
   }
-  BoundFinish fin[2];
+  BoundFinish fin[KB_ITEMS];
   for (int i = 0; i < n; ++i) fin[i] = BoundFinish{1, 0.f, 0.f, 0.f, nullptr, it[i].f->fs};
   int rc = run_bounds(ctx, dt, jb, n, fin, st); if (rc) return rc;
   for (int i = 0; i < n; ++i) {
@@ -371,11 +407,12 @@ static int run_procrustes(Ctx* ctx, int dt, DenseItem* it, int n, float max_step
 // psgd.py:412-416 for up to two dense factors: bound of term1, L update, Newton-Schulz step, procrustes
 static int run_dense_factors(Ctx* ctx, int dt, DenseItem* it, int n, float lr, float betaL, cudaStream_t st) {
   if (n <= 0) return PSGD_OK;
-  BoundJob jb[2];
-  GemmDesc g[2];
+  if (n > KB_ITEMS) return PSGD_ERR_INVALID_ARG;
+  BoundJob jb[KB_ITEMS];
+  GemmDesc g[KB_ITEMS];
   for (int i = 0; i < n; ++i)
     jb[i] = BoundJob{it[i].T, it[i].s, it[i].v_spd, it[i].f->row_sumsq, it[i].f->diag_max, &it[i].f->b_spd, it[i].Va, it[i].Vb};
-  BoundFinish fin[2];
+  BoundFinish fin[KB_ITEMS];
   for (int i = 0; i < n; ++i) fin[i] = BoundFinish{0, it[i].t2, lr, betaL, it[i].L, it[i].f->fs};
   int rc = run_bounds(ctx, dt, jb, n, fin, st); if (rc) return rc;
   for (int i = 0; i < n; ++i) {
@@ -392,17 +429,34 @@ static int run_dense_factors(Ctx* ctx, int dt, DenseItem* it, int n, float lr, f
 // out = (Q_L^T Q_L) X (Q_R^T Q_R)   psgd.py:322-327 / 403, min-flop contraction order
 // reductions (on out): row_sumsq / col_sumsq / total_sumsq, any may be null
 // ---------------------------------------------------------------------------------------------
+// A batched call records each unit's products level by level (products of one level are independent across units and share grouped
+// launches); plan == nullptr launches at once.  Levels: 0 symmetric products P = Q^T Q, 1-2 left side, 3-4 right side.
+struct ChainPlan {
+  GemmDesc g[5][2];
+  int cnt[5];
+  bool squares_done;   // the batch driver has already formed the fp32 squares of the diagonal factors (k_square_to_f32_multi)
+};
+
+static int chain_emit(Ctx* ctx, ChainPlan* plan, int level, const GemmDesc& g, cudaStream_t st) {
+  if (!plan) return launch_gemm(ctx, g, st);
+  plan->g[level][plan->cnt[level]++] = g;
+  return PSGD_OK;
+}
+
 static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, void* out, float* row_sumsq, float* col_sumsq,
-                     float* total_sumsq, cudaStream_t st) {
+                     float* total_sumsq, cudaStream_t st, ChainPlan* plan = nullptr) {
   const int dt = k->dtype;
   const int m = k->m, n = k->has_r ? k->n : 1;
   const bool dl = k->kind_l == PSGD_DENSE, dr = k->has_r && k->kind_r == PSGD_DENSE;
   int rc;
-  if (!dl) { DISPATCH_T(dt, (k_square_to_f32<T><<<(m + 255) / 256, 256, 0, st>>>((const T*)k->QL, w.qsq[0], m))); LAUNCH_CHECK(ctx, "k_square"); }
-  if (k->has_r && !dr) { DISPATCH_T(dt, (k_square_to_f32<T><<<(n + 255) / 256, 256, 0, st>>>((const T*)k->QR, w.qsq[1], n))); LAUNCH_CHECK(ctx, "k_square"); }
+  if (!(plan && plan->squares_done)) {
+    if (!dl) { DISPATCH_T(dt, (k_square_to_f32<T><<<(m + 255) / 256, 256, 0, st>>>((const T*)k->QL, w.qsq[0], m))); LAUNCH_CHECK(ctx, "k_square"); }
+    if (k->has_r && !dr) { DISPATCH_T(dt, (k_square_to_f32<T><<<(n + 255) / 256, 256, 0, st>>>((const T*)k->QR, w.qsq[1], n))); LAUNCH_CHECK(ctx, "k_square"); }
+  }
   const float* rs = dl ? nullptr : w.qsq[0];
   const float* cs = (!k->has_r || dr) ? nullptr : w.qsq[1];
   if (!dl && !dr) {
+    if (plan) return PSGD_ERR_INVALID_ARG;   // the batch driver handles all-diagonal units itself (k_scale2d_multi)
     size_t numel = (size_t)m * n;
     DISPATCH_T(dt, (k_scale2d<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)X, (T*)out, m, n, rs, cs, row_sumsq, col_sumsq,
                                                                        total_sumsq)));
@@ -435,7 +489,8 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
     int ns = 0;
     if (pl) { sy[ns] = gemm_desc(dt, k->QL, m, 1, k->QL, m, 0, m, m, m, PL, m); sy[ns].sym = 1; sy[ns].epi.diag_resid = w.presid[0]; ++ns; }
     if (pr) { sy[ns] = gemm_desc(dt, k->QR, n, 1, k->QR, n, 0, n, n, n, PR, n); sy[ns].sym = 1; sy[ns].epi.diag_resid = w.presid[1]; ++ns; }
-    rc = launch_gemm_group(ctx, sy, ns, st); if (rc) return rc;
+    if (plan) { for (int i = 0; i < ns; ++i) plan->g[0][plan->cnt[0]++] = sy[i]; }
+    else { rc = launch_gemm_group(ctx, sy, ns, st); if (rc) return rc; }
   }
   if (dl) {
     if (pl) {
@@ -444,15 +499,15 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
       // (P_bf16 + diag(resid)) X: the diagonal of P is large and nearly constant, its bf16 rounding would be a systematic bias
       g.epi.D = X; g.epi.ldd = n; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.d_row_scale = w.presid[0];
       if (!dr) set_final(g);
-      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      rc = chain_emit(ctx, plan, 1, g, st); if (rc) return rc;
       Y = dstL;
     } else {      // chain: Q_L X then Q_L^T (.): 4 m^2 n
       void* dstL = dr ? w.B0 : out;
       g = gemm_desc(dt, k->QL, m, 0, X, n, 0, m, n, m, w.B2, n);
-      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      rc = chain_emit(ctx, plan, 1, g, st); if (rc) return rc;
       g = gemm_desc(dt, k->QL, m, 1, w.B2, n, 0, m, n, m, dstL, n);
       if (!dr) set_final(g);
-      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      rc = chain_emit(ctx, plan, 2, g, st); if (rc) return rc;
       Y = dstL;
     }
   }
@@ -462,15 +517,66 @@ static int run_chain(Ctx* ctx, const psgd_kron_t* k, KronWs& w, const void* X, v
       g = gemm_desc(dt, Y, n, 0, PR, n, 0, m, n, n, out, n);
       g.epi.D = Y; g.epi.ldd = n; g.epi.d_dtype = dt; g.epi.beta = 1.f; g.epi.d_col_scale = w.presid[1];
       set_final(g);
-      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      rc = chain_emit(ctx, plan, 3, g, st); if (rc) return rc;
     } else {      // Y Q_R^T then (.) Q_R
       void* tr = (Y == w.B2) ? w.B0 : w.B2;
       g = gemm_desc(dt, Y, n, 0, k->QR, n, 1, m, n, n, tr, n);
-      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      rc = chain_emit(ctx, plan, 3, g, st); if (rc) return rc;
       g = gemm_desc(dt, tr, n, 0, k->QR, n, 0, m, n, n, out, n);
       set_final(g);
-      rc = launch_gemm(ctx, g, st); if (rc) return rc;
+      rc = chain_emit(ctx, plan, 4, g, st); if (rc) return rc;
     }
+  }
+  return PSGD_OK;
+}
+
+// (kron_i Q_i^T Q_i) X for every unit of a same-shape batch: X[u] -> out[u]; optional per-unit reductions on the outputs
+struct ChainIO { const void* X; void* out; float* row_sumsq; float* col_sumsq; float* total_sumsq; };
+
+static int run_chain_batch(Ctx* ctx, const psgd_kron_t* ks, int n, KronWs* w, const ChainIO* io, cudaStream_t st) {
+  const psgd_kron_t& k0 = ks[0];
+  const int dt = k0.dtype;
+  const int m = k0.m, nn = k0.has_r ? k0.n : 1;
+  const bool dl = k0.kind_l == PSGD_DENSE, dr = k0.has_r && k0.kind_r == PSGD_DENSE;
+  if (n == 1) return run_chain(ctx, ks, w[0], io[0].X, io[0].out, io[0].row_sumsq, io[0].col_sumsq, io[0].total_sumsq, st);
+  // squares of the diagonal factors, one launch per side
+  if (!dl) {
+    CPtrTab q; PtrTab o;
+    for (int u = 0; u < n; ++u) { q.p[u] = ks[u].QL; o.p[u] = w[u].qsq[0]; }
+    DISPATCH_T(dt, (k_square_to_f32_multi<T><<<dim3((m + 255) / 256, n), 256, 0, st>>>(q, o, m)));
+    LAUNCH_CHECK(ctx, "k_square_multi");
+  }
+  if (k0.has_r && !dr) {
+    CPtrTab q; PtrTab o;
+    for (int u = 0; u < n; ++u) { q.p[u] = ks[u].QR; o.p[u] = w[u].qsq[1]; }
+    DISPATCH_T(dt, (k_square_to_f32_multi<T><<<dim3((nn + 255) / 256, n), 256, 0, st>>>(q, o, nn)));
+    LAUNCH_CHECK(ctx, "k_square_multi");
+  }
+  if (!dl && !dr) {   // 1-D tensors / diag x diag: one scaling kernel for the whole batch
+    CPtrTab X, rs, cs; PtrTab out, rss, css, tss;
+    for (int u = 0; u < n; ++u) {
+      X.p[u] = io[u].X; out.p[u] = io[u].out; rs.p[u] = w[u].qsq[0]; cs.p[u] = k0.has_r ? w[u].qsq[1] : nullptr;
+      rss.p[u] = io[u].row_sumsq; css.p[u] = io[u].col_sumsq; tss.p[u] = io[u].total_sumsq;
+    }
+    const size_t numel = (size_t)m * nn;
+    int bx = (int)((numel + 255) / 256); if (bx > ctx->num_sms * 8) bx = ctx->num_sms * 8; if (bx < 1) bx = 1;
+    DISPATCH_T(dt, (k_scale2d_multi<T><<<dim3(bx, n), 256, 0, st>>>(X, out, m, nn, rs, cs, rss, css, tss)));
+    LAUNCH_CHECK(ctx, "k_scale2d_multi");
+    return PSGD_OK;
+  }
+  ChainPlan plans[KB_MAX];
+  for (int u = 0; u < n; ++u) {
+    memset(plans[u].cnt, 0, sizeof(plans[u].cnt));
+    plans[u].squares_done = true;
+    int rc = run_chain(ctx, ks + u, w[u], io[u].X, io[u].out, io[u].row_sumsq, io[u].col_sumsq, io[u].total_sumsq, st, &plans[u]);
+    if (rc) return rc;
+  }
+  GemmDesc lvl[2 * KB_MAX];
+  for (int level = 0; level < 5; ++level) {
+    int c = 0;
+    for (int u = 0; u < n; ++u)
+      for (int i = 0; i < plans[u].cnt[level]; ++i) lvl[c++] = plans[u].g[level][i];
+    int rc = launch_gemm_group(ctx, lvl, c, st); if (rc) return rc;
   }
   return PSGD_OK;
 }
@@ -667,88 +773,152 @@ size_t psgd_kron_workspace_bytes(psgd_handle_t, const psgd_kron_t* k) {
   return w.total;
 }
 
-int psgd_kron_whiten_q0p5eq1p5_update(psgd_handle_t h, const psgd_kron_t* k, const void* G, float lr, float betaL, float damping,
-                                      const psgd_kron_noise_t* noise, int do_balance, void* workspace, size_t workspace_bytes,
-                                      void* stream) {
-  Ctx* ctx = reinterpret_cast<Ctx*>(h);
-  if (!ctx || !G || !noise || !noise->N) return PSGD_ERR_INVALID_ARG;
-  int rc = validate_kron(k); if (rc) return rc;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  KronWs w;
-  layout_kron(k, workspace, w);
-  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
-  const int dt = k->dtype;
-  const int m = k->m, n = k->has_r ? k->n : 1;
-  const size_t numel = (size_t)m * n;
-  const bool dense[2] = {k->kind_l == PSGD_DENSE, k->has_r && k->kind_r == PSGD_DENSE};
-  if ((dense[0] && (!noise->V0_spd_l || !noise->V0_skh_l)) || (dense[1] && (!noise->V0_spd_r || !noise->V0_skh_r)))
-    return PSGD_ERR_INVALID_ARG;
-  rc = check_cuda(ctx, cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st), "memset"); if (rc) return rc;
+}  // extern "C"
+
+namespace psgd {
+static int validate_batch(const psgd_kron_t* ks, int n) {
+  if (!ks || n < 1 || n > KB_MAX) return PSGD_ERR_INVALID_ARG;
+  for (int u = 0; u < n; ++u) {
+    int rc = validate_kron(ks + u); if (rc) return rc;
+    if (ks[u].m != ks[0].m || ks[u].n != ks[0].n || ks[u].kind_l != ks[0].kind_l || ks[u].kind_r != ks[0].kind_r ||
+        ks[u].dtype != ks[0].dtype || ks[u].has_r != ks[0].has_r)
+      return PSGD_ERR_INVALID_ARG;   // one batch = one shape bucket
+  }
+  return PSGD_OK;
+}
+
+// psgd.py:394-419 for n units of one shape bucket, every stage issued once for the whole batch
+static int kron_update_batch(Ctx* ctx, const psgd_kron_t* ks, int n, const void* const* Gs, float lr, float betaL, float damping,
+                             const psgd_kron_noise_t* noises, const int* do_balance, KronWs* w, char* zero_begin, size_t zero_bytes,
+                             cudaStream_t st) {
+  const psgd_kron_t& k0 = ks[0];
+  const int dt = k0.dtype;
+  const int m = k0.m, nn = k0.has_r ? k0.n : 1;
+  const size_t numel = (size_t)m * nn;
+  const bool dense[2] = {k0.kind_l == PSGD_DENSE, k0.has_r && k0.kind_r == PSGD_DENSE};
+  for (int u = 0; u < n; ++u) {
+    if (!Gs[u] || !noises[u].N) return PSGD_ERR_INVALID_ARG;
+    if ((dense[0] && (!noises[u].V0_spd_l || !noises[u].V0_skh_l)) || (dense[1] && (!noises[u].V0_spd_r || !noises[u].V0_skh_r)))
+      return PSGD_ERR_INVALID_ARG;
+  }
+  int rc = check_cuda(ctx, cudaMemsetAsync(zero_begin, 0, zero_bytes, st), "memset"); if (rc) return rc;
 
   // G' = G + (damping + eps|G|) N      psgd.py:402-403
-  if (dt == PSGD_BF16 && numel % 8 == 0 && (reinterpret_cast<uintptr_t>(G) & 15u) == 0 && (reinterpret_cast<uintptr_t>(noise->N) & 15u) == 0) {
-    k_add_noise_bf16x8<<<ew_blocks(ctx, numel / 8), 256, 0, st>>>((const bf16*)G, (const bf16*)noise->N, (bf16*)w.B0, numel / 8, damping,
-                                                                  dtype_eps(dt));
-  } else {
-    DISPATCH_T(dt, (k_add_noise<T><<<ew_blocks(ctx, numel), 256, 0, st>>>((const T*)G, (const T*)noise->N, (T*)w.B0, numel, damping,
-                                                                          dtype_eps(dt))));
+  {
+    CPtrTab G, N; PtrTab O;
+    bool vec = dt == PSGD_BF16 && numel % 8 == 0;
+    for (int u = 0; u < n; ++u) {
+      G.p[u] = Gs[u]; N.p[u] = noises[u].N; O.p[u] = w[u].B0;
+      vec = vec && (reinterpret_cast<uintptr_t>(Gs[u]) & 15u) == 0 && (reinterpret_cast<uintptr_t>(noises[u].N) & 15u) == 0;
+    }
+    int bx = ew_blocks(ctx, vec ? numel / 8 : numel);
+    if (n > 1) { bx = (bx + n - 1) / n; if (bx < 1) bx = 1; }
+    if (vec) k_add_noise_multi<bf16, true><<<dim3(bx, n), 256, 0, st>>>(G, N, O, numel, damping, dtype_eps(dt));
+    else DISPATCH_T(dt, (k_add_noise_multi<T, false><<<dim3(bx, n), 256, 0, st>>>(G, N, O, numel, damping, dtype_eps(dt))));
+    LAUNCH_CHECK(ctx, "k_add_noise");
   }
-  LAUNCH_CHECK(ctx, "k_add_noise");
   // Pg = P G'  with the sums of squares the diagonal factors need fused into the last product
-  void* Pg = w.B1;
-  rc = run_chain(ctx, k, w, w.B0, Pg, dense[0] ? nullptr : w.f[0].term1, (k->has_r && !dense[1]) ? w.f[1].term1 : nullptr, nullptr, st);
-  if (rc) return rc;
+  ChainIO io[KB_MAX];
+  for (int u = 0; u < n; ++u)
+    io[u] = ChainIO{w[u].B0, w[u].B1, dense[0] ? nullptr : w[u].f[0].term1, (k0.has_r && !dense[1]) ? w[u].f[1].term1 : nullptr, nullptr};
+  rc = run_chain_batch(ctx, ks, n, w, io, st); if (rc) return rc;
 
-  // Grams of the dense factors (psgd.py:405) -- one grouped launch when both exist
-  GemmDesc gg[2];
-  int ng = 0;
-  if (dense[0]) {
-    gg[ng] = gemm_desc(dt, Pg, n, 0, Pg, n, 1, m, m, n, w.S[0][0], m); gg[ng].sym = 1;
-    gg[ng].epi.row_sumsq = w.f[0].row_sumsq; gg[ng].epi.diag_max = w.f[0].diag_max; ++ng;
+  // Grams of the dense factors (psgd.py:405) -- grouped launches over factors and units
+  {
+    GemmDesc gg[2 * KB_MAX];
+    int ng = 0;
+    for (int u = 0; u < n; ++u) {
+      void* Pg = w[u].B1;
+      if (dense[0]) {
+        gg[ng] = gemm_desc(dt, Pg, nn, 0, Pg, nn, 1, m, m, nn, w[u].S[0][0], m); gg[ng].sym = 1;
+        gg[ng].epi.row_sumsq = w[u].f[0].row_sumsq; gg[ng].epi.diag_max = w[u].f[0].diag_max; ++ng;
+      }
+      if (dense[1]) {
+        gg[ng] = gemm_desc(dt, Pg, nn, 1, Pg, nn, 0, nn, nn, m, w[u].S[1][0], nn); gg[ng].sym = 1;
+        gg[ng].epi.row_sumsq = w[u].f[1].row_sumsq; gg[ng].epi.diag_max = w[u].f[1].diag_max; ++ng;
+      }
+    }
+    rc = launch_gemm_group(ctx, gg, ng, st); if (rc) return rc;
   }
-  if (dense[1]) {
-    gg[ng] = gemm_desc(dt, Pg, n, 1, Pg, n, 0, n, n, m, w.S[1][0], n); gg[ng].sym = 1;
-    gg[ng].epi.row_sumsq = w.f[1].row_sumsq; gg[ng].epi.diag_max = w.f[1].diag_max; ++ng;
-  }
-  rc = launch_gemm_group(ctx, gg, ng, st); if (rc) return rc;
 
-  DenseItem items[2];
+  DenseItem items[KB_ITEMS];
   int nd = 0;
   for (int i = 0; i < 2; ++i) {
-    if (i == 1 && !k->has_r) break;
-    const int s = i == 0 ? m : n;
-    void* q = i == 0 ? k->QL : k->QR;
-    float* L = i == 0 ? k->LL : k->LR;
-    FactorWs& f = w.f[i];
+    if (i == 1 && !k0.has_r) break;
+    const int s = i == 0 ? m : nn;
     const float t2 = (float)((double)numel / (double)s);  // psgd.py:407 / 412
-    if (!dense[i]) {
-      DISPATCH_T(dt, (k_diag_update<T><<<1, 1024, 0, st>>>((T*)q, f.term1, s, t2, lr, betaL, L)));
+    if (!dense[i]) {   // diagonal factors of the whole batch: one launch (psgd.py:406-410)
+      PtrTab q, L; CPtrTab t1;
+      for (int u = 0; u < n; ++u) { q.p[u] = i == 0 ? ks[u].QL : ks[u].QR; L.p[u] = i == 0 ? ks[u].LL : ks[u].LR; t1.p[u] = w[u].f[i].term1; }
+      DISPATCH_T(dt, (k_diag_update_multi<T><<<n, 1024, 0, st>>>(q, t1, s, t2, lr, betaL, L)));
       LAUNCH_CHECK(ctx, "k_diag_update");
       continue;
     }
-    DenseItem& d = items[nd++];
-    d.s = s; d.q = q; d.L = L; d.t2 = t2;
-    d.T = w.S[i][0]; d.Qn = w.S[i][1]; d.RQ = w.S[i][2]; d.RRQ = w.S[i][3]; d.Va = w.Va[i]; d.Vb = w.Vb[i];
-    d.v_spd = i == 0 ? noise->V0_spd_l : noise->V0_spd_r;
-    d.v_skh = i == 0 ? noise->V0_skh_l : noise->V0_skh_r;
-    d.f = &f;
+    for (int u = 0; u < n; ++u) {
+      DenseItem& d = items[nd++];
+      FactorWs& f = w[u].f[i];
+      d.s = s; d.q = i == 0 ? ks[u].QL : ks[u].QR; d.L = i == 0 ? ks[u].LL : ks[u].LR; d.t2 = t2;
+      d.T = w[u].S[i][0]; d.Qn = w[u].S[i][1]; d.RQ = w[u].S[i][2]; d.RRQ = w[u].S[i][3]; d.Va = w[u].Va[i]; d.Vb = w[u].Vb[i];
+      d.v_spd = i == 0 ? noises[u].V0_spd_l : noises[u].V0_spd_r;
+      d.v_skh = i == 0 ? noises[u].V0_skh_l : noises[u].V0_skh_r;
+      d.f = &f;
+    }
   }
   rc = run_dense_factors(ctx, dt, items, nd, lr, betaL, st); if (rc) return rc;
-  if (do_balance) { rc = run_balance(ctx, k, w, st); if (rc) return rc; }
+  for (int u = 0; u < n; ++u)
+    if (do_balance && do_balance[u]) { rc = run_balance(ctx, ks + u, w[u], st); if (rc) return rc; }
   return PSGD_OK;
+}
+}  // namespace psgd
+
+extern "C" {
+
+size_t psgd_kron_batch_workspace_bytes(psgd_handle_t, const psgd_kron_t* ks, int n) {
+  if (validate_batch(ks, n)) return 0;
+  KronWs w[KB_MAX];
+  return layout_kron_batch(ks, n, nullptr, w, nullptr, nullptr);
+}
+
+int psgd_kron_whiten_q0p5eq1p5_update_batched(psgd_handle_t h, const psgd_kron_t* ks, int n, const void* const* Gs, float lr, float betaL,
+                                              float damping, const psgd_kron_noise_t* noises, const int* do_balance, void* workspace,
+                                              size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !Gs || !noises) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_batch(ks, n); if (rc) return rc;
+  KronWs w[KB_MAX];
+  char* zb = nullptr; size_t zn = 0;
+  const size_t total = layout_kron_batch(ks, n, workspace, w, &zb, &zn);
+  if (!workspace || workspace_bytes < total) return PSGD_ERR_WORKSPACE;
+  return kron_update_batch(ctx, ks, n, Gs, lr, betaL, damping, noises, do_balance, w, zb, zn, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int psgd_kron_whiten_q0p5eq1p5_update(psgd_handle_t h, const psgd_kron_t* k, const void* G, float lr, float betaL, float damping,
+                                      const psgd_kron_noise_t* noise, int do_balance, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  return psgd_kron_whiten_q0p5eq1p5_update_batched(h, k, 1, &G, lr, betaL, damping, noise, &do_balance, workspace, workspace_bytes, stream);
+}
+
+int psgd_kron_precond_grad_batched(psgd_handle_t h, const psgd_kron_t* ks, int n, const void* const* Xs, void* const* Hs, float* sumsq_out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx || !Xs || !Hs) return PSGD_ERR_INVALID_ARG;
+  int rc = validate_batch(ks, n); if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  KronWs w[KB_MAX];
+  const size_t total = layout_kron_batch(ks, n, workspace, w, nullptr, nullptr);
+  if (!workspace || workspace_bytes < total) return PSGD_ERR_WORKSPACE;
+  if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4 * (size_t)n, st), "memset"); if (rc) return rc; }
+  ChainIO io[KB_MAX];
+  for (int u = 0; u < n; ++u) {
+    if (!Xs[u] || !Hs[u]) return PSGD_ERR_INVALID_ARG;
+    io[u] = ChainIO{Xs[u], Hs[u], nullptr, nullptr, sumsq_out ? sumsq_out + u : nullptr};
+  }
+  return run_chain_batch(ctx, ks, n, w, io, st);
 }
 
 int psgd_kron_precond_grad(psgd_handle_t h, const psgd_kron_t* k, const void* X, void* H, float* sumsq_out, void* workspace,
                            size_t workspace_bytes, void* stream) {
-  Ctx* ctx = reinterpret_cast<Ctx*>(h);
-  if (!ctx || !X || !H) return PSGD_ERR_INVALID_ARG;
-  int rc = validate_kron(k); if (rc) return rc;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  KronWs w;
-  layout_kron(k, workspace, w);
-  if (!workspace || workspace_bytes < w.total) return PSGD_ERR_WORKSPACE;
-  if (sumsq_out) { rc = check_cuda(ctx, cudaMemsetAsync(sumsq_out, 0, 4, st), "memset"); if (rc) return rc; }
-  return run_chain(ctx, k, w, X, H, nullptr, nullptr, sumsq_out, st);
+  return psgd_kron_precond_grad_batched(h, k, 1, &X, &H, sumsq_out, workspace, workspace_bytes, stream);
 }
 
 int psgd_kron_balance(psgd_handle_t h, const psgd_kron_t* k, void* workspace, size_t workspace_bytes, void* stream) {

@@ -15,10 +15,12 @@
 //   finish    : the CTA that finishes last turns the norms into the bound and into what its consumer needs (Lipschitz update + step
 //               sizes of the dense factor, psgd.py:413-415; the Procrustes normaliser, psgd.py:118)
 //
-// Work unit = (matrix, 64-column slab): out[32 x 64] = V[32 x s] A[s x 64], K streamed in 128-row stages through a cp.async ring
-// (A stage 16 KB + V stage 8 KB, XOR-swizzled for ldmatrix), 8 warps each taking one k16 slice of every stage on mma.sync m16n8k16
-// (bf16 in, fp32 accumulate; 32 probes are far below a tcgen05 tile and the bound is L2 bandwidth), cross-warp reduction through
-// shared memory, epilogue: scale, round to bf16, store, per-probe sums of squares (atomics, 32 per unit).
+// Work unit = (matrix, 64-column slab): out[32 x 64] = V[32 x s] A[s x 64].  K is split over the 8 warps of the CTA in interleaved 16-row
+// slices; every warp streams ITS slices (A: 16 x 64, V: 32 x 16, XOR-swizzled for ldmatrix) through a warp-private cp.async ring and
+// multiplies them on mma.sync m16n8k16 (bf16 in, fp32 accumulate; 32 probes are far below a tcgen05 tile and the bound is L2 bandwidth) --
+// no block-wide barrier inside the K loop (a first version with block-wide 128-row stages spent its time in per-stage barriers and address
+// arithmetic: 92 us per pair of 4096 x 4096 matrices, profiles/r02_ncu_bounds_v1.txt).  Then a cross-warp reduction through shared memory
+// and the epilogue: scale, round to bf16, store, per-probe sums of squares (atomics, 32 per unit).
 #pragma once
 #include "common.cuh"
 #include "kron_kernels.cuh"
@@ -26,16 +28,18 @@
 namespace psgd {
 
 constexpr int NB_W = 64;          // columns of A per work unit
-constexpr int NB_KC = 128;        // k rows per pipeline stage (8 warps x 16)
-constexpr int NB_STAGES = 5;
+constexpr int NB_KS = 16;         // k rows per warp slice
+constexpr int NB_KC = 128;        // k rows all 8 warps cover together (padding granularity of the row kept in shared memory)
+constexpr int NB_STAGES = 6;      // slices in flight per warp
 constexpr int NB_THREADS = 256;
 constexpr int NB_MAX_JOBS = 16;
 constexpr int NB_MAX_S = 16384;   // the selected row of A is kept in shared memory (2 bytes per column)
-constexpr int NB_A_BYTES = NB_KC * NB_W * 2;
-constexpr int NB_V_BYTES = 32 * NB_KC * 2;
+constexpr int NB_A_BYTES = NB_KS * NB_W * 2;    // 2 KB: 16 rows x 128 B
+constexpr int NB_V_BYTES = 32 * NB_KS * 2;      // 1 KB: 32 probes x 32 B
 constexpr int NB_STAGE_BYTES = NB_A_BYTES + NB_V_BYTES;
+constexpr int NB_RING_BYTES = 8 * NB_STAGES * NB_STAGE_BYTES;
 constexpr int NB_RED_LD = 72;     // floats per row of the cross-warp reduction buffer (64 + 8: conflict-free float2 stores)
-static_assert(8 * 32 * NB_RED_LD * 4 <= NB_STAGES * NB_STAGE_BYTES, "reduction buffer aliases the pipeline stages");
+static_assert(8 * 32 * NB_RED_LD * 4 <= NB_RING_BYTES, "reduction buffer aliases the warp rings");
 
 struct NbJob {
   const bf16* A;          // s x s, row-major, ld = s
@@ -78,9 +82,8 @@ __device__ __forceinline__ void nb_grid_barrier(unsigned* counter, unsigned targ
     long long t0 = 0;
     unsigned spins = 0;
     while (nb_ld_acquire(counter) < target) {
-      __nanosleep(40);
-      if (++spins == 4096u) t0 = clock64();
-      if (spins > 4096u && (spins & 1023u) == 0u && clock64() - t0 > 8000000000LL) __trap();
+      if (++spins == 65536u) t0 = clock64();
+      if (spins > 65536u && (spins & 4095u) == 0u && clock64() - t0 > 8000000000LL) __trap();
     }
     __threadfence();
   }
@@ -162,17 +165,20 @@ __device__ __forceinline__ void nb_finish_job(const NbJob& J, int dtype, float t
 
 __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_constant__ NbParams P) {
   extern __shared__ __align__(128) uint8_t nb_smem[];
-  bf16* a_row = reinterpret_cast<bf16*>(nb_smem + NB_STAGES * NB_STAGE_BYTES);   // row j of A', zero beyond s (up to the stage boundary)
+  bf16* a_row = reinterpret_cast<bf16*>(nb_smem + NB_RING_BYTES);   // row j of A', zero beyond s (up to a multiple of NB_KC)
   float* red = reinterpret_cast<float*>(nb_smem);
   __shared__ float s_sgn[32];
   __shared__ float s_scale[32];
   __shared__ float s_sv[8];
   __shared__ int s_si[9];
   __shared__ int s_last;
+  __shared__ int s_jc[NB_MAX_JOBS];   // argmax row of the matrices this CTA has met (phase I -> step 0)
   const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(nb_smem));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned ncta = gridDim.x;
   unsigned nbar = 0;
+  if (tid < NB_MAX_JOBS) s_jc[tid] = -1;
+  __syncthreads();
 
   auto job_of = [&](int u) {
     int ji = 0;
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_cons
       const NbJob& J = P.job[ji];
       if (ji != cur) {
         j = nb_block_argmax(J.row_sumsq, J.s, s_sv, s_si);
+        if (tid == 0) s_jc[ji] = j;
         inv_nf = 1.f / (__ldcg(J.nf_src) + P.tiny);
         cur = ji;
       }
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_cons
         __syncthreads();                     // previous unit's readers of s_scale / a_row are done
         inv_nf = 1.f / (__ldcg(J.nf_src) + P.tiny);
         if (st == 0) {
-          const int j = nb_block_argmax(J.row_sumsq, s, s_sv, s_si);
+          const int j = s_jc[ji] >= 0 ? s_jc[ji] : nb_block_argmax(J.row_sumsq, s, s_sv, s_si);
           for (int k = tid; k < nkb * NB_KC; k += NB_THREADS)
             a_row[k] = k < s ? __float2bfloat16_rn(__bfloat162float(J.A[(size_t)j * s + k]) * inv_nf) : __float2bfloat16_rn(0.f);
           if (tid < 32) { const float d = __ldcg(J.dots + tid); s_sgn[tid] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
@@ -242,27 +249,56 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_cons
       bf16* Vdst = st == 1 ? J.Vb : J.Va;
       const int col0 = (u - J.unit0) * NB_W;
 
-      auto issue = [&](int kb) {
-        const uint32_t sa = smem_base + (uint32_t)(kb % NB_STAGES) * NB_STAGE_BYTES;
-        const uint32_t sv = sa + NB_A_BYTES;
-        const int c = tid & 7;
+      // ---- warp-private pipeline over this warp's k slices: slice index ks = warp + 8 i, rows [16 ks, 16 ks + 16) ----
+      const int nks = (s + NB_KS - 1) / NB_KS;
+      const int my_n = nks > warp ? (nks - warp + 7) / 8 : 0;         // slices of this warp
+      const uint32_t ring = smem_base + (uint32_t)warp * NB_STAGES * NB_STAGE_BYTES;
+      uint8_t* ring_gen = nb_smem + warp * NB_STAGES * NB_STAGE_BYTES;
+      // per-lane copy pattern (fixed for the unit): A slice = 16 rows x 8 chunks of 16 B -> 4 per lane; V slice = 32 probes x 2 chunks -> 2 per lane
+      const int ac = lane & 7, ar = lane >> 3;                         // chunk, first row (rows ar + 4 i)
+      const bool a_col_ok = col0 + ac * 8 < s;
+      const bf16* a_src = J.A + (size_t)(warp * NB_KS + ar) * s + col0 + ac * 8;
+      const bf16* v_src = Vsrc + (size_t)lane * s + warp * NB_KS;       // probe = lane
+      const size_t a_step = (size_t)8 * NB_KS * s;                     // elements between consecutive slices of this warp
+      uint32_t a_dst[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (tid >> 3) + 32 * i;
-          const int gk = kb * NB_KC + r, gn = col0 + c * 8;
-          const bool ok = gk < s && gn < s;
-          nb_cp_async16(sa + r * 128 + ((c ^ (r & 7)) << 4), ok ? (const void*)(J.A + (size_t)gk * s + gn) : (const void*)J.A, ok ? 16 : 0);
-        }
-        const int cv = tid & 15;
+      for (int i = 0; i < 4; ++i) { const int r = ar + 4 * i; a_dst[i] = (uint32_t)(r * 128 + ((ac ^ (r & 7)) << 4)); }
+      const uint32_t v_dst0 = NB_A_BYTES + lane * 32 + ((0 ^ ((lane >> 2) & 1)) << 4);
+      const uint32_t v_dst1 = NB_A_BYTES + lane * 32 + ((1 ^ ((lane >> 2) & 1)) << 4);
+
+      auto issue = [&](int it) {       // the it-th slice of this warp
+        const uint32_t st_base = ring + (uint32_t)(it % NB_STAGES) * NB_STAGE_BYTES;
+        const int k0 = (warp + 8 * it) * NB_KS;
+        const bf16* ap = a_src + (size_t)it * a_step;
+        const bf16* vp = v_src + (size_t)it * (8 * NB_KS);
+        if (k0 + NB_KS <= s && a_col_ok) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int p = (tid >> 4) + 16 * i;
-          const int gk = kb * NB_KC + cv * 8;
-          const bool ok = gk < s;
-          nb_cp_async16(sv + p * 256 + (((cv & 8) | ((cv ^ p) & 7)) << 4), ok ? (const void*)(Vsrc + (size_t)p * s + gk) : (const void*)Vsrc,
-                        ok ? 16 : 0);
+          for (int i = 0; i < 4; ++i) nb_cp_async16(st_base + a_dst[i], ap + (size_t)(4 * i) * s, 16);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = a_col_ok && k0 + ar + 4 * i < s;
+            nb_cp_async16(st_base + a_dst[i], ok ? (const void*)(ap + (size_t)(4 * i) * s) : (const void*)J.A, ok ? 16 : 0);
+          }
         }
+        const bool ok0 = k0 < s, ok1 = k0 + 8 < s;
+        nb_cp_async16(st_base + v_dst0, ok0 ? (const void*)vp : (const void*)Vsrc, ok0 ? 16 : 0);
+        nb_cp_async16(st_base + v_dst1, ok1 ? (const void*)(vp + 8) : (const void*)Vsrc, ok1 ? 16 : 0);
       };
+
+      // ldmatrix addresses (fixed): A-operand = V slice rows (probes) x k 16; B-operand = A slice k rows x 8 column chunks (transposed load)
+      uint32_t v_ld[2], a_ld[4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = mt * 16 + (lane & 15);
+        v_ld[mt] = NB_A_BYTES + row * 32 + (((lane >> 4) ^ ((row >> 2) & 1)) << 4);
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        const int krow = (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int nc = np * 2 + (lane >> 4);
+        a_ld[np] = krow * 128 + ((nc ^ (krow & 7)) << 4);
+      }
 
       float acc[2][8][4];
 #pragma unroll
@@ -273,49 +309,41 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_cons
           for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
 #pragma unroll 1
-      for (int kb = 0; kb < NB_STAGES - 1; ++kb) {
-        if (kb < nkb) issue(kb);
+      for (int it = 0; it < NB_STAGES - 1; ++it) {
+        if (it < my_n) issue(it);
         nb_cp_commit();
       }
 #pragma unroll 1
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int it = 0; it < my_n; ++it) {
         nb_cp_wait<NB_STAGES - 2>();
-        uint8_t* stg = nb_smem + (kb % NB_STAGES) * NB_STAGE_BYTES;
+        const uint32_t st_base = ring + (uint32_t)(it % NB_STAGES) * NB_STAGE_BYTES;
         if (st == 0) {
-          // rotated probes V = A'[j] + sgn V0 (psgd.py:63), formed in place on the chunks this thread itself copied
-          const int cv = tid & 15;
+          // rotated probes V = A'[j] + sgn V0 (psgd.py:63), formed in place on the two chunks this lane itself copied (probe = lane)
+          uint8_t* sg_base = ring_gen + (it % NB_STAGES) * NB_STAGE_BYTES;
+          const int k0 = (warp + 8 * it) * NB_KS;
+          const float sg = s_sgn[lane];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int p = (tid >> 4) + 16 * i;
-            bf16* vp = reinterpret_cast<bf16*>(stg + NB_A_BYTES + p * 256 + (((cv & 8) | ((cv ^ p) & 7)) << 4));
+          for (int h = 0; h < 2; ++h) {
+            bf16* vp = reinterpret_cast<bf16*>(sg_base + (h ? v_dst1 : v_dst0));
             float v[8], a[8], o[8];
             ld8(vp, v);
-            ld8(a_row + kb * NB_KC + cv * 8, a);
-            const float sg = s_sgn[p];
+            ld8(a_row + k0 + 8 * h, a);
 #pragma unroll
             for (int t = 0; t < 8; ++t) o[t] = a[t] + sg * v[t];
             st8(vp, o);
           }
         }
-        __syncthreads();
-        if (kb + NB_STAGES - 1 < nkb) issue(kb + NB_STAGES - 1);
+        __syncwarp();
+        // refill the slot consumed in the previous iteration (every lane of this warp is past its ldmatrix reads: __syncwarp above)
+        if (it + NB_STAGES - 1 < my_n) issue(it + NB_STAGES - 1);
         nb_cp_commit();
-        // this warp's k16 slice of the stage
-        const uint32_t sa = smem_base + (uint32_t)(kb % NB_STAGES) * NB_STAGE_BYTES;
-        const uint32_t sv = sa + NB_A_BYTES;
         uint32_t af[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const int row = mt * 16 + (lane & 15);
-          const int kc = 2 * warp + (lane >> 4);
-          nb_ldsm_x4(sv + row * 256 + (((kc & 8) | ((kc ^ row) & 7)) << 4), af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
-        }
+        nb_ldsm_x4(st_base + v_ld[0], af[0][0], af[0][1], af[0][2], af[0][3]);
+        nb_ldsm_x4(st_base + v_ld[1], af[1][0], af[1][1], af[1][2], af[1][3]);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
-          const int krow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const int nc = np * 2 + (lane >> 4);
           uint32_t b0, b1, b2, b3;
-          nb_ldsm_x4_t(sa + krow * 128 + ((nc ^ (krow & 7)) << 4), b0, b1, b2, b3);
+          nb_ldsm_x4_t(st_base + a_ld[np], b0, b1, b2, b3);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             nb_mma(acc[mt][2 * np], af[mt], b0, b1);
@@ -324,7 +352,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_cons
         }
       }
       nb_cp_wait<0>();
-      __syncthreads();                       // every warp is done with the stages: the reduction buffer aliases them
+      __syncthreads();                       // every warp is done with its ring: the reduction buffer aliases the rings
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll

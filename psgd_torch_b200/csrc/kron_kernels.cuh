@@ -54,6 +54,71 @@ __global__ void k_add_noise_bf16x8(const bf16* __restrict__ G, const bf16* __res
   }
 }
 
+// ------------------------------ batched forms: blockIdx.y = unit of a same-shape batch, pointers from a table ------------------------------
+constexpr int KB_MAX = 16;   // units per batched call
+struct PtrTab { void* p[KB_MAX]; };
+struct CPtrTab { const void* p[KB_MAX]; };
+
+template <typename T, bool VEC8>
+__global__ void k_add_noise_multi(CPtrTab G, CPtrTab Nz, PtrTab out, size_t numel, float damping, float eps) {
+  const T* g = reinterpret_cast<const T*>(G.p[blockIdx.y]);
+  const T* z = reinterpret_cast<const T*>(Nz.p[blockIdx.y]);
+  T* o = reinterpret_cast<T*>(out.p[blockIdx.y]);
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (VEC8) {   // bf16, numel % 8 == 0, 16-byte aligned pointers
+    const size_t nvec = numel / 8;
+    for (; i < nvec; i += stride) {
+      float a[8], b[8], r[8];
+      ld8(reinterpret_cast<const bf16*>(g) + i * 8, a); ld8(reinterpret_cast<const bf16*>(z) + i * 8, b);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { float d = rbf(damping + rbf(eps * fabsf(a[t]))); r[t] = a[t] + rbf(d * b[t]); }
+      st8(reinterpret_cast<bf16*>(o) + i * 8, r);
+    }
+  } else {
+    for (; i < numel; i += stride) {
+      float a = to_f<T>(g[i]);
+      float d = to_f<T>(from_f<T>(damping + to_f<T>(from_f<T>(eps * fabsf(a)))));
+      float dn = to_f<T>(from_f<T>(d * to_f<T>(z[i])));
+      o[i] = from_f<T>(a + dn);
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_square_to_f32_multi(CPtrTab q, PtrTab out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float v = to_f<T>(reinterpret_cast<const T*>(q.p[blockIdx.y])[i]); reinterpret_cast<float*>(out.p[blockIdx.y])[i] = v * v; }
+}
+
+// k_scale2d for a batch (1-D tensors / diag x diag: tiny, the atomics per element are fine)
+template <typename T>
+__global__ void k_scale2d_multi(CPtrTab X, PtrTab out, int m, int n, CPtrTab rs, CPtrTab cs, PtrTab row_sumsq, PtrTab col_sumsq, PtrTab total_sumsq) {
+  const int u = blockIdx.y;
+  const T* x = reinterpret_cast<const T*>(X.p[u]);
+  T* o = reinterpret_cast<T*>(out.p[u]);
+  const float* r_ = reinterpret_cast<const float*>(rs.p[u]);
+  const float* c_ = reinterpret_cast<const float*>(cs.p[u]);
+  float* rss = reinterpret_cast<float*>(row_sumsq.p[u]);
+  float* css = reinterpret_cast<float*>(col_sumsq.p[u]);
+  float* tss = reinterpret_cast<float*>(total_sumsq.p[u]);
+  const size_t numel = (size_t)m * n;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float tot = 0.f;
+  for (; i < numel; i += stride) {
+    const int r = (int)(i / n), c = (int)(i % n);
+    const float v = to_f<T>(x[i]) * (r_ ? r_[r] : 1.f) * (c_ ? c_[c] : 1.f);
+    const T ov = from_f<T>(v);
+    if (o) o[i] = ov;
+    const float f = to_f<T>(ov);
+    tot += f * f;
+    if (rss) atomicAdd(&rss[r], f * f);
+    if (css) atomicAdd(&css[c], f * f);
+  }
+  if (tss) { tot = warp_sum(tot); if ((threadIdx.x & 31) == 0) atomicAdd(tss, tot); }
+}
+
 // q2[i] = float(q[i])^2  (diagonal factor applied twice: Q^T Q)   psgd.py:327 with 1-D q
 template <typename T>
 __global__ void k_square_to_f32(const T* __restrict__ q, float* __restrict__ out, int n) {
@@ -281,6 +346,31 @@ __global__ void k_diag_update(T* __restrict__ q, const float* __restrict__ term1
                               float* L) {
   __shared__ float red[32];
   __shared__ float c_s;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) mx = fmaxf(mx, to_f<T>(from_f<T>(term1[i])));
+  mx = block_max(mx, red);
+  if (threadIdx.x == 0) {
+    float ell = to_f<T>(from_f<T>(mx + t2));
+    float Ln = fmaxf(betaL * (*L) + (1.f - betaL) * ell, ell);
+    *L = Ln;
+    c_s = lr / Ln;
+  }
+  __syncthreads();
+  const float c = c_s;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) {
+    float t1 = to_f<T>(from_f<T>(term1[i]));
+    q[i] = from_f<T>(to_f<T>(q[i]) * (1.f - c * (t1 - t2)));
+  }
+}
+
+// batched k_diag_update: one block per unit
+template <typename T>
+__global__ void k_diag_update_multi(PtrTab q_, CPtrTab term1_, int s, float t2, float lr, float betaL, PtrTab L_) {
+  __shared__ float red[32];
+  __shared__ float c_s;
+  T* q = reinterpret_cast<T*>(q_.p[blockIdx.x]);
+  const float* term1 = reinterpret_cast<const float*>(term1_.p[blockIdx.x]);
+  float* L = reinterpret_cast<float*>(L_.p[blockIdx.x]);
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < s; i += blockDim.x) mx = fmaxf(mx, to_f<T>(from_f<T>(term1[i])));
   mx = block_max(mx, red);

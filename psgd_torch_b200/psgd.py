@@ -317,6 +317,72 @@ def update_precond_kron_whiten_q0p5eq1p5(QL, exprs, G, lr=0.1, betaL=0.9, dampin
     _lib.check(h, rc, "psgd_kron_whiten_q0p5eq1p5_update")
 
 
+def _fill_noise(nz, noise, nfactors):
+    nz.N = noise["N"].data_ptr()
+    spd, skh = noise["spd"], noise["skh"]
+    nz.V0_spd_l = spd[0].data_ptr() if spd[0] is not None else None
+    nz.V0_skh_l = skh[0].data_ptr() if skh[0] is not None else None
+    if nfactors > 1:
+        nz.V0_spd_r = spd[1].data_ptr() if spd[1] is not None else None
+        nz.V0_skh_r = skh[1].data_ptr() if skh[1] is not None else None
+
+
+def _batch_descs(QLs, Gs, with_L):
+    n = len(QLs)
+    if not 1 <= n <= _lib.MAX_BATCH:
+        raise EngineError(f"a batched call takes 1..{_lib.MAX_BATCH} units, got {n}")
+    ks = (KronT * n)()
+    for u, (QL, G) in enumerate(zip(QLs, Gs)):
+        if G.dim() > 2 or not G.is_cuda or not G.is_contiguous():
+            raise EngineError("batched calls take contiguous CUDA tensors of order <= 2")
+        k = _kron_desc(QL[0], QL[1] if with_L else None, G)
+        if not with_L:
+            d = _dummy(G.device)
+            k.LL, k.LR = d.data_ptr(), d.data_ptr() + 4
+        ks[u] = k
+    return ks
+
+
+def update_precond_kron_whiten_q0p5eq1p5_batched(QLs, exprs, Gs, lr=0.1, betaL=0.9, damping=1e-9, noises=None):
+    """psgd.py:394-419 for a list of same-shape tensors in ONE engine call (psgd_kron_whiten_q0p5eq1p5_update_batched): what the reference's
+    per-parameter loop (ddp.py:112-161) does one tensor at a time.  QLs = [QL_0, QL_1, ...] (each as init_kron returns it), Gs = list of
+    gradients of one shape / dtype; `exprs` is accepted for symmetry with the single-tensor call and not used.  Random draws: per unit,
+    in list order, exactly the single-tensor call's draws (`noises` = list of dicts from draw_kron_noise replays them)."""
+    if noises is None:
+        noises = [draw_kron_noise(G, QL[0]) for QL, G in zip(QLs, Gs)]
+    n = len(QLs)
+    ks = _batch_descs(QLs, Gs, True)
+    nzs = (KronNoiseT * n)()
+    for u in range(n):
+        _fill_noise(nzs[u], noises[u], len(QLs[u][0]))
+    gp = (C.c_void_p * n)(*[G.data_ptr() for G in Gs])
+    bal = (C.c_int * n)(*[int(bool(nz.get("balance", False))) for nz in noises])
+    dev = Gs[0].device
+    h = _lib.handle_for(dev)
+    lib = _lib.load_library()
+    ws = _lib.workspace(dev, lib.psgd_kron_batch_workspace_bytes(h, ks, n))
+    rc = lib.psgd_kron_whiten_q0p5eq1p5_update_batched(h, ks, n, gp, float(lr), float(betaL), float(damping), nzs, bal, _lib.ptr(ws),
+                                                       ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(h, rc, "psgd_kron_whiten_q0p5eq1p5_update_batched")
+
+
+def precond_grad_kron_batched(QLs, exprs, Gs, sumsq_out=None):
+    """psgd.py:322-327 for a list of same-shape tensors in one engine call; returns the list of preconditioned gradients.  `sumsq_out`
+    (optional fp32 CUDA tensor with len(Gs) elements) receives sum(out_u^2) per unit."""
+    n = len(QLs)
+    ks = _batch_descs(QLs, Gs, False)
+    outs = [torch.empty_like(G) for G in Gs]
+    xp = (C.c_void_p * n)(*[G.data_ptr() for G in Gs])
+    hp = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    dev = Gs[0].device
+    h = _lib.handle_for(dev)
+    lib = _lib.load_library()
+    ws = _lib.workspace(dev, lib.psgd_kron_batch_workspace_bytes(h, ks, n))
+    rc = lib.psgd_kron_precond_grad_batched(h, ks, n, xp, hp, _lib.ptr(sumsq_out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(h, rc, "psgd_kron_precond_grad_batched")
+    return outs
+
+
 def balance_kron_precond(Q):
     """psgd.py:266-275, in place."""
     if len(Q) <= 1:

@@ -542,3 +542,57 @@ def test_fused_norm_bound_kernel_matches_oracle_and_the_unfused_form(s, kind):
     check(tag, "bound (fused kernel) vs unfused form", b_e, b_u, 2e-2)
     lam = float(torch.linalg.matrix_norm(A.double(), 2))
     assert 0.4 * lam <= float(b_e) <= 1.02 * lam
+
+
+@pytest.mark.parametrize("shape,dtype,nb", [
+    ((256, 384), torch.bfloat16, 4),     # dense x dense: 8 dense factors through grouped launches and one norm-bound launch
+    ((1024, 4096), torch.bfloat16, 5),   # k/v-like dense x diag: more units than one grouped launch carries
+    ((2048, 128), torch.bfloat16, 3),    # diag x dense
+    ((4096,), torch.bfloat16, 16),       # RMSNorm-like 1-D tensors: the all-diagonal batch path
+    ((40, 24), torch.float32, 3),        # fp32 (SIMT products)
+])
+def test_batched_update_and_apply_match_the_single_unit_calls_and_the_oracle(shape, dtype, nb):
+    """psgd_kron_whiten_q0p5eq1p5_update_batched / psgd_kron_precond_grad_batched: same-shape units in one call must give, unit by unit,
+    what the single-unit entry points give (same noise), and match the CPU oracle."""
+    from psgd_torch_b200 import psgd
+    from oracle import psgd_oracle as orc
+    dev = _dev()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = torch.Generator().manual_seed(sum(shape) + nb)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    QLb = [psgd.init_kron(torch.zeros(*shape, dtype=dtype, device=dev)) for _ in range(nb)]
+    QLs = [psgd.init_kron(torch.zeros(*shape, dtype=dtype, device=dev)) for _ in range(nb)]
+    exprs = QLb[0][1]
+    for step in range(2):
+        Gs = [(0.1 * (1 + u) * torch.randn(*shape, generator=g) * (1.0 + torch.arange(shape[-1]) % 3)).to(dtype) for u in range(nb)]
+        torch.manual_seed(77 + step)
+        noises = [orc.draw_kron_noise(G, [q.cpu() for q in QL[0][0]]) for G, QL in zip(Gs, QLb)]
+        for nz in noises:
+            nz["balance"] = (step == 1)
+        Qo = [[q.detach().cpu().clone() for q in QL[0][0]] for QL in QLb]
+        Lo = [[l.detach().cpu().clone() for l in QL[0][1]] for QL in QLb]
+        Gd = [G.to(dev) for G in Gs]
+        nzd = [_noise_to(nz, dev) for nz in noises]
+        psgd.update_precond_kron_whiten_q0p5eq1p5_batched([QL[0] for QL in QLb], exprs, Gd, lr=0.5, noises=nzd)
+        for u in range(nb):
+            psgd.update_precond_kron_whiten_q0p5eq1p5(QLs[u][0], exprs, Gd[u], lr=0.5, noise=nzd[u])
+            orc.update_precond_kron_whiten_q0p5eq1p5([Qo[u], Lo[u]], Gs[u], noises[u], lr=0.5)
+        ss = torch.zeros(nb, device=dev)
+        Hb = psgd.precond_grad_kron_batched([QL[0] for QL in QLb], exprs, Gd, sumsq_out=ss)
+        for u in range(nb):
+            tag = f"batched ({nb} units) {shape} {dtype} step {step} unit {u}"
+            for i, (qb, qs, qo) in enumerate(zip(QLb[u][0][0], QLs[u][0][0], Qo[u])):
+                check(tag, f"Q[{i}] batched vs single", qb, qs, 2e-3 if dtype == torch.bfloat16 else 1e-6)
+                # step 1 balances the factors (psgd.py:266-275): the reference rounds the ~1.00x balancing factor to bf16 (2^-7 steps), the
+                # engine keeps it in fp32 (k_balance_scale), so the two factors differ by up to 2^-8 in opposite directions
+                check(tag, f"Q[{i}] batched vs oracle", qb, qo, 2e-2 if (dtype == torch.bfloat16 and step == 1) else tol)
+            for i, (lb, lo) in enumerate(zip(QLb[u][0][1], Lo[u])):
+                check(tag, f"L[{i}] batched vs oracle", lb, lo, 1e-5 if dtype == torch.float32 else 3e-2)
+            Hs = psgd.precond_grad_kron(QLb[u][0], exprs, Gd[u])
+            check(tag, "precond_grad batched vs single", Hb[u], Hs, 2e-3 if dtype == torch.bfloat16 else 1e-6)
+            check(tag, "precond_grad batched vs oracle", Hb[u], orc.precond_grad_kron([q.detach().cpu() for q in QLb[u][0][0]], Gs[u]), tol)
+            assert abs(float(ss[u]) - float((Hb[u].float() ** 2).sum())) <= 2e-3 * float(ss[u]) + 1e-30
+            for qs, qb in zip(QLs[u][0][0], QLb[u][0][0]):      # keep the two copies of the state together for the next step
+                qs.copy_(qb)
+            for ls, lb in zip(QLs[u][0][1], QLb[u][0][1]):
+                ls.copy_(lb)
