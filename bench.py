@@ -357,82 +357,122 @@ def run_unit(u, G, psgd):
     return psgd.precond_grad_lra(u.UVd, G)
 
 
-def step_resident(units, psgd):
-    for u in units:
-        run_unit(u, u.G, psgd)
+# units per batched engine call (psgd.*_batched: same-shape units share grouped tcgen05 launches, one norm-bound launch and the
+# elementwise launches).  1024 x 4096 k/v projections fill a quarter of the machine each, RMSNorm vectors are launch-bound, a single
+# dense factor of a gate/up/down unit gives the norm-bound kernel 64 of 148 CTAs; q/o units fill the machine on their own.
+BATCH = {"k_v_proj": 8, "rmsnorm": 16, "gate_up_proj": 2, "down_proj": 2, "q_o_proj": 1, "lm_head": 1}
+
+
+def make_groups(units):
+    """Consecutive same-bucket Kron units -> lists of at most BATCH[bucket] unit indices; every other unit is its own group."""
+    groups, cur = [], []
+    for i, u in enumerate(units):
+        cap = BATCH.get(u.name, 1) if u.kind == "kron" else 1
+        if cur and (units[cur[0]].name != u.name or len(cur) >= cap):
+            groups.append(cur)
+            cur = []
+        cur.append(i)
+        if cap == 1:
+            groups.append(cur)
+            cur = []
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def run_group(units, idx, Gs, psgd):
+    """update + apply of one group; returns the list of preconditioned gradients."""
+    if len(idx) == 1:
+        return [run_unit(units[idx[0]], Gs[0], psgd)]
+    QLs = [units[i].QL for i in idx]
+    psgd.update_precond_kron_whiten_q0p5eq1p5_batched(QLs, None, Gs, lr=0.1, betaL=0.9, damping=1e-9)
+    return psgd.precond_grad_kron_batched(QLs, None, Gs)
+
+
+def step_resident(units, groups, psgd):
+    for idx in groups:
+        run_group(units, idx, [units[i].G for i in idx], psgd)
 
 
 class HostPipeline:
     """e2e leg: gradients start in pinned host memory, preconditioned gradients end there; every unit pays its own full H2D and D2H
     copy inside the timed region.  Copies run on their own streams (both PCIe directions at once) and are software-pipelined DEPTH
-    units ahead of the compute stream.  The step visits the units in an interleaved order (each shape bucket spread evenly over the
+    groups ahead of the compute stream.  The step visits the groups in an interleaved order (each shape bucket spread evenly over the
     step) so that transfer-heavy units (gate/up/down: 117 MB for 1.9 ms of compute) share the link with compute-heavy ones (q/o: 32 MB
     for 1.7 ms; the LRA unit: 1 GB for 75 ms) -- visiting bucket after bucket leaves PCIe idle half of the step and saturated the other
     half.  One pinned source/destination buffer per bucket (the data is synthetic; only the host allocation is shared)."""
 
     DEPTH = 3
 
-    def __init__(self, units, dev):
+    def __init__(self, units, groups, dev):
         self.dev = dev
+        self.groups = groups
         self.h2d = torch.cuda.Stream(dev)
         self.d2h = torch.cuda.Stream(dev)
         self.host_in, self.host_out, self.stage_in = {}, {}, {}
         self.bytes_in = self.bytes_out = 0
-        count = {}
-        for u in units:
+        count, gsize = {}, {}
+        for idx in groups:
+            u = units[idx[0]]
             key = (u.name, u.G.shape)
             count[key] = count.get(key, 0) + 1
+            gsize[key] = max(gsize.get(key, 0), len(idx))
         seen = {}
         pos = []
-        for idx, u in enumerate(units):
+        for gi, idx in enumerate(groups):
+            u = units[idx[0]]
             key = (u.name, u.G.shape)
             if key not in self.host_in:
                 self.host_in[key] = torch.empty(u.G.shape, dtype=u.G.dtype).pin_memory()
                 self.host_in[key].copy_(u.G)
                 self.host_out[key] = torch.empty(u.G.shape, dtype=u.G.dtype).pin_memory()
-                self.stage_in[key] = [torch.empty_like(u.G) for _ in range(min(count[key], self.DEPTH + 1))]
-            self.bytes_in += u.G.numel() * u.G.element_size()
-            self.bytes_out += u.G.numel() * u.G.element_size()
+                slots = min(count[key], self.DEPTH + 1)
+                self.stage_in[key] = [[torch.empty_like(u.G) for _ in range(gsize[key])] for _ in range(slots)]
+            nbytes = len(idx) * u.G.numel() * u.G.element_size()
+            self.bytes_in += nbytes
+            self.bytes_out += nbytes
             j = seen.get(key, 0)
             seen[key] = j + 1
-            pos.append(((j + 0.5) / count[key], idx))
-        self.order = [idx for _, idx in sorted(pos)]
-        coll = [i for i in self.order if units[i].sharded is not None]   # units with collectives go first on every rank: the ranks meet there
-        self.order = coll + [i for i in self.order if units[i].sharded is None]
+            pos.append(((j + 0.5) / count[key], gi))
+        self.order = [gi for _, gi in sorted(pos)]
+        coll = [gi for gi in self.order if units[groups[gi][0]].sharded is not None]   # groups with collectives go first on every rank
+        self.order = coll + [gi for gi in self.order if units[groups[gi][0]].sharded is None]
         self.slot = {k: 0 for k in self.host_in}
         self.in_free = {k: [None] * len(v) for k, v in self.stage_in.items()}   # event: compute finished reading stage_in[k][i]
-        self.out_done = {k: None for k in self.host_in}                         # event: last D2H into host_out[k] finished
 
     def step(self, units, psgd):
         cur = torch.cuda.current_stream(self.dev)
         order = self.order
         staged = {}
         for j in range(len(order) + self.DEPTH):
-            if j < len(order):     # host -> device copy of unit j's gradient, DEPTH units ahead of the compute
-                u = units[order[j]]
+            if j < len(order):     # host -> device copies of group j's gradients, DEPTH groups ahead of the compute
+                idx = self.groups[order[j]]
+                u = units[idx[0]]
                 key = (u.name, u.G.shape)
                 i = self.slot[key]
                 self.slot[key] = (i + 1) % len(self.stage_in[key])
-                stg = self.stage_in[key][i]
+                stg = self.stage_in[key][i][:len(idx)]
                 with torch.cuda.stream(self.h2d):
                     if self.in_free[key][i] is not None:
                         self.h2d.wait_event(self.in_free[key][i])
-                    stg.copy_(self.host_in[key], non_blocking=True)
+                    for t in stg:
+                        t.copy_(self.host_in[key], non_blocking=True)
                     ev_in = torch.cuda.Event(); ev_in.record(self.h2d)
                 staged[j] = (key, i, stg, ev_in)
             c = j - self.DEPTH
             if c < 0:
                 continue
-            u = units[order[c]]
+            idx = self.groups[order[c]]
             key, i, stg, ev_in = staged.pop(c)
             cur.wait_event(ev_in)
-            H = run_unit(u, stg, psgd)
+            Hs = run_group(units, idx, stg, psgd)
             ev_c = torch.cuda.Event(); ev_c.record(cur)
             self.in_free[key][i] = ev_c
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(ev_c)
-                self.host_out[key].copy_(H, non_blocking=True)   # the d2h stream is FIFO: copies into host_out[key] never overlap
-                H.record_stream(self.d2h)
+                for H in Hs:
+                    self.host_out[key].copy_(H, non_blocking=True)   # the d2h stream is FIFO: copies into host_out[key] never overlap
+                    H.record_stream(self.d2h)
         cur.wait_stream(self.d2h)
         cur.wait_stream(self.h2d)
 
@@ -512,15 +552,17 @@ def run_engine(args):
         lra = [u for u in all_units if u[2] == "lra"]
         lra_ms = sum(UNIT_MS[u[0]] for u in lra) / world
         parts = partition.lpt_partition([UNIT_MS[u[0]] for u in kron], world, initial_loads=[lra_ms] * world)
-        mine = lra + [kron[i] for i in parts[rank]]
+        mine = lra + [kron[i] for i in sorted(parts[rank])]    # bucket by bucket, so that same-shape units can share batched calls
         units = build_units(mine, dev, lra_rows=partition.row_shard(lra[0][1][0], world, rank) if lra else None)
     torch.cuda.synchronize(dev)
     h = _lib.handle_for(dev)
     lib = _lib.load_library()
+    groups = make_groups(units) if not args.no_batching else [[i] for i in range(len(units))]
+    psgd.set_noise_mode(args.noise)
 
     # ---------------- value: gradients resident in HBM ----------------
     for _ in range(args.warmup):
-        step_resident(units, psgd)
+        step_resident(units, groups, psgd)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -528,7 +570,7 @@ def run_engine(args):
     l0 = lib.psgd_launch_count(h)
     if args.profile_range:   # ncu --profile-from-start off: only the timed region of the `value` leg is captured
         torch.cuda.cudart().cudaProfilerStart()
-    ms_value = timed(lambda: step_resident(units, psgd), args.steps, dev, dist, world)
+    ms_value = timed(lambda: step_resident(units, groups, psgd), args.steps, dev, dist, world)
     if args.profile_range:
         torch.cuda.cudart().cudaProfilerStop()
     launches = lib.psgd_launch_count(h) - l0
@@ -540,7 +582,7 @@ def run_engine(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- e2e: host buffers through the public API ----------------
-    pipe = HostPipeline(units, dev)
+    pipe = HostPipeline(units, groups, dev)
     for _ in range(max(1, min(args.warmup, 2))):
         pipe.step(units, psgd)
     ms_e2e = timed(lambda: pipe.step(units, psgd), args.steps, dev, dist, world)
@@ -599,6 +641,9 @@ def run_engine(args):
                                    "(dense x dense) + 64 k/v 1024x4096 + 64 gate/up 14336x4096 + 32 down 4096x14336 + 65 RMSNorm "
                                    "4096 + lm_head 128256x4096 as Kron(diag,dense) + embed_tokens 128256x4096 as LRA r=32",
                        "preconditioner_dtype": "bf16", "geometry": "Q0.5EQ1.5 (dense Q, the path KWNS4 runs)",
+                       "noise": "in-kernel Philox4x32-10 (performance mode)" if args.noise == "philox" else "torch.randn, reference draw order",
+                       "batching": "one engine call per unit" if args.no_batching else
+                                   "same-shape units per engine call: " + ", ".join(f"{k} x{v}" for k, v in BATCH.items() if v > 1),
                        "partition": "single GPU" if world == 1 else f"Kron units: owner-computes LPT partition over {world} GPUs, no collective; "
                                     "the LRA unit is row-sharded over all ranks (5 all-reduces of <= 13 KB per update + apply, NCCL)",
                        "cache": "per-step working set (>16 GB of gradients + 7 GB of Q) exceeds the 126 MB L2; no explicit flush"},
@@ -649,6 +694,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--noise", default="philox", choices=["philox", "torch"],
+                    help="philox: damping noise and norm-bound probes drawn inside the engine's kernels (performance mode); torch: drawn by "
+                         "torch.randn on the host side in the reference's order (the parity mode the tests use)")
+    ap.add_argument("--no-batching", action="store_true", help="one engine call per unit (no psgd.*_batched calls)")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the torch-CUDA run of the reference's op graph (gpu_reference key)")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu launch lists)")
     args = ap.parse_args()

@@ -34,7 +34,7 @@ class KronT(C.Structure):
 
 class KronNoiseT(C.Structure):
     _fields_ = [("N", C.c_void_p), ("V0_spd_l", C.c_void_p), ("V0_skh_l", C.c_void_p), ("V0_spd_r", C.c_void_p),
-                ("V0_skh_r", C.c_void_p)]
+                ("V0_skh_r", C.c_void_p), ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64)]
 
 
 class LraT(C.Structure):
@@ -116,7 +116,7 @@ def load_library():
                 fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
                 fn.restype = res
                 fn.argtypes = args
-            if lib.psgd_abi_version() != 1:
+            if lib.psgd_abi_version() != 2:
                 raise EngineError("libpsgd_b200.so ABI version mismatch")
             _lib = lib
     return _lib

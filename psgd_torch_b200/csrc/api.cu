@@ -155,6 +155,7 @@ struct KronWs {
   void* B0; void* B1; void* B2;   // m x n
   void* S[2][4];    // per dense factor, s x s each: T (Gram, later R), Qn, RQ, RRQ   (the Qn slots double as P_L / P_R in the chain)
   void* Va[2]; void* Vb[2];       // per dense factor: 32 x s probe buffers
+  void* P0[2][2];                 // per dense factor: probe blocks drawn on the device (performance mode): [factor][spd, skh]
   size_t total;
 };
 
@@ -199,6 +200,7 @@ static void layout_kron_bufs(Bump& b, const psgd_kron_t* k, KronWs& w) {
     const size_t sd = dense[i] ? (size_t)sdim[i] : 0;
     for (int j = 0; j < 4; ++j) w.S[i][j] = b.take(sd * sd * es);
     w.Va[i] = b.take(32 * sd * es); w.Vb[i] = b.take(32 * sd * es);
+    w.P0[i][0] = b.take(32 * sd * es); w.P0[i][1] = b.take(32 * sd * es);
   }
 }
 
@@ -796,26 +798,65 @@ static int kron_update_batch(Ctx* ctx, const psgd_kron_t* ks, int n, const void*
   const int m = k0.m, nn = k0.has_r ? k0.n : 1;
   const size_t numel = (size_t)m * nn;
   const bool dense[2] = {k0.kind_l == PSGD_DENSE, k0.has_r && k0.kind_r == PSGD_DENSE};
+  // parity mode: the host supplies every random number; performance mode (NULL pointers): drawn on the device (Philox).  One mode per batch.
+  const bool dev_noise = noises[0].N == nullptr;
+  const void* probes[KB_MAX][2][2];   // [unit][factor][spd, skh]
+  bool gen_probes = false;
   for (int u = 0; u < n; ++u) {
-    if (!Gs[u] || !noises[u].N) return PSGD_ERR_INVALID_ARG;
-    if ((dense[0] && (!noises[u].V0_spd_l || !noises[u].V0_skh_l)) || (dense[1] && (!noises[u].V0_spd_r || !noises[u].V0_skh_r)))
-      return PSGD_ERR_INVALID_ARG;
+    if (!Gs[u] || (noises[u].N == nullptr) != dev_noise) return PSGD_ERR_INVALID_ARG;
+    const void* given[2][2] = {{noises[u].V0_spd_l, noises[u].V0_skh_l}, {noises[u].V0_spd_r, noises[u].V0_skh_r}};
+    for (int i = 0; i < 2; ++i)
+      for (int b = 0; b < 2; ++b) {
+        probes[u][i][b] = given[i][b];
+        if (dense[i] && !given[i][b]) { probes[u][i][b] = w[u].P0[i][b]; gen_probes = true; }
+      }
   }
   int rc = check_cuda(ctx, cudaMemsetAsync(zero_begin, 0, zero_bytes, st), "memset"); if (rc) return rc;
 
   // G' = G + (damping + eps|G|) N      psgd.py:402-403
   {
     CPtrTab G, N; PtrTab O;
+    U64Tab seeds, offs;
     bool vec = dt == PSGD_BF16 && numel % 8 == 0;
     for (int u = 0; u < n; ++u) {
       G.p[u] = Gs[u]; N.p[u] = noises[u].N; O.p[u] = w[u].B0;
+      seeds.v[u] = noises[u].philox_seed; offs.v[u] = noises[u].philox_offset;
       vec = vec && (reinterpret_cast<uintptr_t>(Gs[u]) & 15u) == 0 && (reinterpret_cast<uintptr_t>(noises[u].N) & 15u) == 0;
     }
     int bx = ew_blocks(ctx, vec ? numel / 8 : numel);
     if (n > 1) { bx = (bx + n - 1) / n; if (bx < 1) bx = 1; }
-    if (vec) k_add_noise_multi<bf16, true><<<dim3(bx, n), 256, 0, st>>>(G, N, O, numel, damping, dtype_eps(dt));
-    else DISPATCH_T(dt, (k_add_noise_multi<T, false><<<dim3(bx, n), 256, 0, st>>>(G, N, O, numel, damping, dtype_eps(dt))));
+    if (dev_noise) {
+      if (vec) k_add_noise_philox_multi<bf16, true><<<dim3(bx, n), 256, 0, st>>>(G, O, numel, damping, dtype_eps(dt), seeds, offs);
+      else DISPATCH_T(dt, (k_add_noise_philox_multi<T, false><<<dim3(bx, n), 256, 0, st>>>(G, O, numel, damping, dtype_eps(dt), seeds, offs)));
+    } else {
+      if (vec) k_add_noise_multi<bf16, true><<<dim3(bx, n), 256, 0, st>>>(G, N, O, numel, damping, dtype_eps(dt));
+      else DISPATCH_T(dt, (k_add_noise_multi<T, false><<<dim3(bx, n), 256, 0, st>>>(G, N, O, numel, damping, dtype_eps(dt))));
+    }
     LAUNCH_CHECK(ctx, "k_add_noise");
+  }
+  if (gen_probes) {   // the probe blocks the host did not supply: one launch for the whole batch
+    ProbeTab tab;
+    int ne = 0;
+    for (int u = 0; u < n; ++u)
+      for (int i = 0; i < 2; ++i)
+        for (int b = 0; b < 2; ++b)
+          if (dense[i] && probes[u][i][b] == w[u].P0[i][b]) {
+            tab.p[ne] = w[u].P0[i][b]; tab.seed[ne] = noises[u].philox_seed; tab.off[ne] = noises[u].philox_offset;
+            tab.strm[ne] = 1u + 2u * i + b;
+            ++ne;
+          }
+    // all entries of one call have the same size only if m == n or one factor is dense; generate per factor size otherwise
+    for (int i = 0; i < 2; ++i) {
+      if (!dense[i]) continue;
+      ProbeTab t2; int c = 0;
+      for (int e = 0; e < ne; ++e)
+        if ((int)((tab.strm[e] - 1u) / 2u) == i) { t2.p[c] = tab.p[e]; t2.seed[c] = tab.seed[e]; t2.off[c] = tab.off[e]; t2.strm[c] = tab.strm[e]; ++c; }
+      if (!c) continue;
+      const size_t pn = (size_t)32 * (i == 0 ? m : nn);
+      int bx = (int)((pn / 4 + 255) / 256); if (bx < 1) bx = 1; if (bx > 64) bx = 64;
+      DISPATCH_T(dt, (k_philox_probes<T><<<dim3(bx, c), 256, 0, st>>>(t2, pn)));
+      LAUNCH_CHECK(ctx, "k_philox_probes");
+    }
   }
   // Pg = P G'  with the sums of squares the diagonal factors need fused into the last product
   ChainIO io[KB_MAX];
@@ -859,8 +900,8 @@ static int kron_update_batch(Ctx* ctx, const psgd_kron_t* ks, int n, const void*
       FactorWs& f = w[u].f[i];
       d.s = s; d.q = i == 0 ? ks[u].QL : ks[u].QR; d.L = i == 0 ? ks[u].LL : ks[u].LR; d.t2 = t2;
       d.T = w[u].S[i][0]; d.Qn = w[u].S[i][1]; d.RQ = w[u].S[i][2]; d.RRQ = w[u].S[i][3]; d.Va = w[u].Va[i]; d.Vb = w[u].Vb[i];
-      d.v_spd = i == 0 ? noises[u].V0_spd_l : noises[u].V0_spd_r;
-      d.v_skh = i == 0 ? noises[u].V0_skh_l : noises[u].V0_skh_r;
+      d.v_spd = probes[u][i][0];
+      d.v_skh = probes[u][i][1];
       d.f = &f;
     }
   }

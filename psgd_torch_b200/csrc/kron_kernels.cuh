@@ -54,6 +54,32 @@ __global__ void k_add_noise_bf16x8(const bf16* __restrict__ G, const bf16* __res
   }
 }
 
+// ------------------------------ in-kernel noise (performance mode: psgd_kron_noise_t pointers == NULL) ------------------------------
+// Philox4x32-10 (Salmon et al., SC'11; the generator behind torch's CUDA randn), counter-based: element group g of stream `strm` of a call
+// with (seed, offset) always gets the same four 32-bit words, whatever the launch geometry.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// four standard normals from one Philox block (Box-Muller on two pairs of uniforms; fast-math log / sincos: this is damping noise)
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, uint32_t strm, uint64_t group, float* z) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), strm, (uint32_t)offset),
+                                make_uint2((uint32_t)seed ^ (uint32_t)(offset >> 32), (uint32_t)(seed >> 32)));
+  const float u0 = ((float)r.x + 1.0f) * 2.3283064365386963e-10f, u1 = (float)r.y * 2.3283064365386963e-10f;
+  const float u2 = ((float)r.z + 1.0f) * 2.3283064365386963e-10f, u3 = (float)r.w * 2.3283064365386963e-10f;
+  const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+  float sa, ca, sb, cb;
+  __sincosf(6.283185307179586f * u1, &sa, &ca);
+  __sincosf(6.283185307179586f * u3, &sb, &cb);
+  z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
+}
+
 // ------------------------------ batched forms: blockIdx.y = unit of a same-shape batch, pointers from a table ------------------------------
 constexpr int KB_MAX = 16;   // units per batched call
 struct PtrTab { void* p[KB_MAX]; };
@@ -82,6 +108,62 @@ __global__ void k_add_noise_multi(CPtrTab G, CPtrTab Nz, PtrTab out, size_t nume
       float dn = to_f<T>(from_f<T>(d * to_f<T>(z[i])));
       o[i] = from_f<T>(a + dn);
     }
+  }
+}
+
+// G' = G + (damping + eps|G|) N with N drawn in the kernel (stream 0 of the unit's Philox sequence): one read and one write of G instead of
+// torch's randn kernel + a three-pass add.  seeds[u] / offsets[u] per unit.
+struct U64Tab { uint64_t v[KB_MAX]; };
+template <typename T, bool VEC8>
+__global__ void k_add_noise_philox_multi(CPtrTab G, PtrTab out, size_t numel, float damping, float eps, U64Tab seeds, U64Tab offsets) {
+  const T* g = reinterpret_cast<const T*>(G.p[blockIdx.y]);
+  T* o = reinterpret_cast<T*>(out.p[blockIdx.y]);
+  const uint64_t seed = seeds.v[blockIdx.y], off = offsets.v[blockIdx.y];
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (VEC8) {
+    const size_t nvec = numel / 8;
+    for (; i < nvec; i += stride) {
+      float a[8], z[8], r[8];
+      ld8(reinterpret_cast<const bf16*>(g) + i * 8, a);
+      philox_normal4(seed, off, 0u, 2 * i, z);
+      philox_normal4(seed, off, 0u, 2 * i + 1, z + 4);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const float d = rbf(damping + rbf(eps * fabsf(a[t]))); r[t] = a[t] + rbf(d * rbf(z[t])); }
+      st8(reinterpret_cast<bf16*>(o) + i * 8, r);
+    }
+  } else {
+    const size_t ngrp = (numel + 3) / 4;
+    for (; i < ngrp; i += stride) {
+      float z[4];
+      philox_normal4(seed, off, 0u, i, z);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const size_t e = 4 * i + t;
+        if (e < numel) {
+          const float a = to_f<T>(g[e]);
+          const float d = to_f<T>(from_f<T>(damping + to_f<T>(from_f<T>(eps * fabsf(a)))));
+          o[e] = from_f<T>(a + to_f<T>(from_f<T>(d * to_f<T>(from_f<T>(z[t])))));
+        }
+      }
+    }
+  }
+}
+
+// probe blocks (32 x s standard normals each) of a batch: table entry e = (buffer, stream id of its unit's sequence); blockIdx.y = entry
+struct ProbeTab { void* p[4 * KB_MAX]; uint64_t seed[4 * KB_MAX]; uint64_t off[4 * KB_MAX]; uint32_t strm[4 * KB_MAX]; };
+template <typename T>
+__global__ void k_philox_probes(const __grid_constant__ ProbeTab tab, size_t numel) {
+  T* o = reinterpret_cast<T*>(tab.p[blockIdx.y]);
+  const uint64_t seed = tab.seed[blockIdx.y], off = tab.off[blockIdx.y];
+  const uint32_t strm = tab.strm[blockIdx.y];
+  const size_t ngrp = (numel + 3) / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ngrp; i += (size_t)gridDim.x * blockDim.x) {
+    float z[4];
+    philox_normal4(seed, off, strm, i, z);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (4 * i + t < numel) o[4 * i + t] = from_f<T>(z[t]);
   }
 }
 

@@ -295,18 +295,12 @@ def update_precond_kron_whiten_q0p5eq1p5(QL, exprs, G, lr=0.1, betaL=0.9, dampin
         raise EngineError("psgd_torch_b200 runs on CUDA (sm_100a) tensors only")
     G = G.contiguous()
     if noise is None:
-        noise = draw_kron_noise(G, Q)
+        noise = draw_kron_noise_philox(G, Q) if (_NOISE_MODE == "philox" and G.dim() <= 2) else draw_kron_noise(G, Q)
     if G.dim() > 2:
         return _update_kron_nd(Q, L, G, lr, betaL, damping, noise)
     k = _kron_desc(Q, L, G)
     nz = KronNoiseT()
-    nz.N = noise["N"].data_ptr()
-    spd, skh = noise["spd"], noise["skh"]
-    nz.V0_spd_l = spd[0].data_ptr() if spd[0] is not None else None
-    nz.V0_skh_l = skh[0].data_ptr() if skh[0] is not None else None
-    if len(Q) > 1:
-        nz.V0_spd_r = spd[1].data_ptr() if spd[1] is not None else None
-        nz.V0_skh_r = skh[1].data_ptr() if skh[1] is not None else None
+    _fill_noise(nz, noise, len(Q))
     h = _lib.handle_for(G.device)
     lib = _lib.load_library()
     nbytes = lib.psgd_kron_workspace_bytes(h, C.byref(k))
@@ -317,8 +311,32 @@ def update_precond_kron_whiten_q0p5eq1p5(QL, exprs, G, lr=0.1, betaL=0.9, dampin
     _lib.check(h, rc, "psgd_kron_whiten_q0p5eq1p5_update")
 
 
+_NOISE_MODE = "torch"
+_philox_calls = 0
+
+
+def set_noise_mode(mode):
+    """"torch" (default): every random number of an update is drawn by torch on the host side, in the reference's order (parity with the
+    reference's RNG streams; SURVEY.md 8b "RNG contract").  "philox": performance mode -- the damping noise and the norm-bound probes are
+    drawn inside the engine's kernels (counter-based Philox4x32-10); the host only draws a 62-bit seed per update and the balancing coin
+    from torch's CPU generator, so DDP replicas whose CPU generators are synchronised (KWNS4 does that) still see identical noise."""
+    global _NOISE_MODE
+    if mode not in ("torch", "philox"):
+        raise ValueError("noise mode must be 'torch' or 'philox'")
+    _NOISE_MODE = mode
+
+
+def draw_kron_noise_philox(G, Q):
+    """Performance-mode counterpart of draw_kron_noise: no tensors, a seed for the in-kernel generator + the CPU coin of psgd.py:418."""
+    global _philox_calls
+    _philox_calls += 1
+    return {"N": None, "spd": [None] * len(Q), "skh": [None] * len(Q), "seed": int(torch.randint(0, 1 << 62, (1,))),
+            "offset": _philox_calls, "balance": bool(torch.rand([]) < 0.01)}
+
+
 def _fill_noise(nz, noise, nfactors):
-    nz.N = noise["N"].data_ptr()
+    nz.N = noise["N"].data_ptr() if noise["N"] is not None else None
+    nz.philox_seed, nz.philox_offset = int(noise.get("seed", 0)), int(noise.get("offset", 0))
     spd, skh = noise["spd"], noise["skh"]
     nz.V0_spd_l = spd[0].data_ptr() if spd[0] is not None else None
     nz.V0_skh_l = skh[0].data_ptr() if skh[0] is not None else None
@@ -349,7 +367,8 @@ def update_precond_kron_whiten_q0p5eq1p5_batched(QLs, exprs, Gs, lr=0.1, betaL=0
     gradients of one shape / dtype; `exprs` is accepted for symmetry with the single-tensor call and not used.  Random draws: per unit,
     in list order, exactly the single-tensor call's draws (`noises` = list of dicts from draw_kron_noise replays them)."""
     if noises is None:
-        noises = [draw_kron_noise(G, QL[0]) for QL, G in zip(QLs, Gs)]
+        draw = draw_kron_noise_philox if _NOISE_MODE == "philox" else draw_kron_noise
+        noises = [draw(G, QL[0]) for QL, G in zip(QLs, Gs)]
     n = len(QLs)
     ks = _batch_descs(QLs, Gs, True)
     nzs = (KronNoiseT * n)()

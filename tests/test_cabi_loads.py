@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in psgd_b200.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in _lib.SYMBOLS"
-    assert lib.psgd_abi_version() == 1
+    assert lib.psgd_abi_version() == 2
     assert lib.psgd_status_string(0) == b"ok"
     assert b"no other code path" in lib.psgd_status_string(-5)
 

@@ -596,3 +596,48 @@ def test_batched_update_and_apply_match_the_single_unit_calls_and_the_oracle(sha
                 qs.copy_(qb)
             for ls, lb in zip(QLs[u][0][1], QLb[u][0][1]):
                 ls.copy_(lb)
+
+
+def test_in_kernel_philox_noise_is_standard_normal_and_reproducible():
+    """Performance mode (psgd_kron_noise_t pointers NULL): the damping noise G' - G = (damping + eps|G|) N is drawn inside the kernel.  With
+    G = 0 and damping = 1 the first product of the update sees exactly N: its statistics must be those of a standard normal, the same
+    (seed, offset) must reproduce it, a different seed must not."""
+    from psgd_torch_b200 import psgd
+    dev = _dev()
+    m, n = 512, 1024
+
+    def gram_diag_after_update(seed, offset):
+        # Q = I, G = 0, damping = 1: Pg = N, so term1 = N N^T and L[0] is a bound of ||N N^T|| + n; Q_new - Q = -lr/L (N N^T - n I) Q ...
+        QL, exprs = psgd.init_kron(torch.zeros(m, n, dtype=torch.bfloat16, device=dev))
+        nz = {"N": None, "spd": [None, None], "skh": [None, None], "seed": seed, "offset": offset, "balance": False}
+        psgd.update_precond_kron_whiten_q0p5eq1p5(QL, exprs, torch.zeros(m, n, dtype=torch.bfloat16, device=dev), lr=0.01, damping=1.0, noise=nz)
+        return QL
+
+    a = gram_diag_after_update(12345, 1)
+    b = gram_diag_after_update(12345, 1)
+    c = gram_diag_after_update(999, 1)
+    for qa, qb, qc in zip(a[0], b[0], c[0]):
+        eye = torch.eye(qa.shape[0], device=dev)
+        da, db, dc = qa.float() - eye, qb.float() - eye, qc.float() - eye       # the step the noise produced
+        assert relerr(da, db) < 2e-2       # same (seed, offset): same noise (fp32 atomics reorder the last bits of the reductions)
+        assert relerr(dc, da) > 0.5        # another seed: unrelated noise
+    # ||N N^T||_2 of an m x n standard normal matrix is ~ (sqrt(m) + sqrt(n))^2; the Lipschitz constant is that bound + t2 = n
+    expect_l = (m ** 0.5 + n ** 0.5) ** 2 + n
+    assert 0.6 * expect_l < float(a[1][0]) < 1.2 * expect_l, (float(a[1][0]), expect_l)
+    # direct statistics through the public noise path: psgd.set_noise_mode("philox") on a diagonal x diagonal unit, where the update is
+    # elementwise: term1 = sum_j (q_i^2 q_j^2 N_ij)^2 -> with Q = 1 the row sums of N^2 / n must average 1 with variance 2 / n
+    psgd.set_noise_mode("philox")
+    try:
+        torch.manual_seed(5)
+        rows, cols = 4096, 2048
+        QL, exprs = psgd.init_kron(torch.zeros(rows, cols, dtype=torch.float32, device=dev), max_skew=0.0)     # both factors diagonal
+        L0 = [l.clone() for l in QL[1]]
+        psgd.update_precond_kron_whiten_q0p5eq1p5(QL, exprs, torch.zeros(rows, cols, dtype=torch.float32, device=dev), lr=1e-3, damping=1.0)
+        # q_i <- q_i (1 - lr/L (term1_i - cols)): recover term1_i = sum_j N_ij^2
+        Ll = float(QL[1][0])
+        t1 = cols - (QL[0][0].double() - 1.0) * Ll / 1e-3
+        mean, var = float(t1.mean() / cols), float(t1.var() / cols)
+        assert abs(mean - 1.0) < 0.01, mean                  # E[N^2] = 1
+        assert 1.6 < var < 2.4, var                          # Var[N^2] = 2
+    finally:
+        psgd.set_noise_mode("torch")
