@@ -359,8 +359,9 @@ def run_unit(u, G, psgd):
 
 # units per batched engine call (psgd.*_batched: same-shape units share grouped tcgen05 launches, one norm-bound launch and the
 # elementwise launches).  1024 x 4096 k/v projections fill a quarter of the machine each, RMSNorm vectors are launch-bound, a single
-# dense factor of a gate/up/down unit gives the norm-bound kernel 64 of 148 CTAs; q/o units fill the machine on their own.
-BATCH = {"k_v_proj": 8, "rmsnorm": 16, "gate_up_proj": 2, "down_proj": 2, "q_o_proj": 1, "lm_head": 1}
+# dense factor of a gate/up/down unit gives the norm-bound kernel 64 of 148 CTAs; the big units gain from grouped launches too: four
+# 4096^3 products are 13.8 waves of pair tiles instead of four times 3.46 -> 4.
+BATCH = {"k_v_proj": 16, "rmsnorm": 16, "gate_up_proj": 4, "down_proj": 4, "q_o_proj": 4, "lm_head": 1}
 
 
 def make_groups(units):
@@ -664,6 +665,99 @@ def run_engine(args):
         dist.destroy_process_group()
 
 
+def run_kwns4(args):
+    """--mode kwns4: BASELINE.json configs[3] -- the same parameter set driven through the torch.optim wrapper, KWNS4.step() (head: weight decay
+    + cast + EMA, update, apply, tail: clip + parameter update), preconditioners sharded per parameter over the ranks
+    (shard_preconditioners=True at N > 1): the owner of a parameter computes its step and broadcasts the updated parameter (NCCL), all
+    inside the timed region.  Every parameter takes the Kron path here (KWNS4 has no LRA form: embed_tokens is Kron(diag, dense) like
+    lm_head).  Gradients are identical on every rank (as after DDP's all-reduce)."""
+    from psgd_torch_b200 import KWNS4, psgd, _lib
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
+    psgd.set_noise_mode(args.noise)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    shapes = []
+    for name, count, shape, kind in LLAMA3_8B_SET:
+        shp = (128256, 4096) if kind == "lra" else shape
+        shapes += [shp] * count
+    params = []
+    for shp in shapes:
+        p = torch.nn.Parameter((0.02 * torch.randn(*shp, device=dev, generator=gen)).bfloat16())
+        p.grad = (0.01 * torch.randn(*shp, device=dev, generator=gen)).bfloat16()
+        params.append(p)
+    opt = KWNS4(params, lr_params=2e-4, lr_preconditioner=0.1, preconditioner_dtype=torch.bfloat16, shard_preconditioners=world > 1,
+                batch_same_shape=not args.no_batching)
+    h = _lib.handle_for(dev)
+    lib = _lib.load_library()
+    for _ in range(args.warmup):
+        opt.step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.psgd_launch_count(h)
+    ms_value = timed(opt.step, args.steps, dev, dist, world)
+    launches = lib.psgd_launch_count(h) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: the gradients of the parameters this rank OWNS arrive from pinned host memory every step (the owner is the only rank that
+    # reads a parameter's gradient), a checksum of the updated parameters is read back
+    owned = [p for p in params if (world == 1 or opt._owner[id(p)] == rank)]
+    host = {}
+    bytes_in = 0
+    for p in owned:
+        key = tuple(p.shape)
+        if key not in host:
+            host[key] = torch.empty(p.shape, dtype=p.dtype).pin_memory()
+            host[key].copy_(p.grad)
+        bytes_in += p.numel() * p.element_size()
+    chk = torch.zeros(1, device=dev)
+    chk_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        for p in owned:
+            p.grad.copy_(host[tuple(p.shape)], non_blocking=True)
+        opt.step()
+        chk.copy_(params[0].detach().float().abs().sum().reshape(1))
+        chk_host.copy_(chk, non_blocking=True)
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps, dev, dist, world)
+    tot = torch.tensor([float(launches), float(bytes_in)], device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    n_units = len(params)
+    if rank == 0:
+        bcast = sum(p.numel() * p.element_size() for p in params) if world > 1 else 0
+        line = {"metric": METRIC, "value": n_units / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "mode": "kwns4",
+                "config": {"workload": "Llama-3-8B param-shape set through KWNS4.step() (BASELINE.json configs[3]): 291 parameters, all Kron "
+                                       "(embed_tokens as Kron(diag, dense)), bf16 parameters / gradients / preconditioners, momentum 0.9, "
+                                       "weight decay, clipping, parameter update; "
+                                       + ("single GPU" if world == 1 else f"preconditioners sharded per parameter over {world} GPUs "
+                                          "(owner computes, NCCL broadcast of the updated parameter inside the timed region)"),
+                           "noise": args.noise, "batch_same_shape": not args.no_batching,
+                           "nccl_broadcast_bytes_per_step": bcast},
+                "clocks": clocks,
+                "e2e": {"value": n_units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(tot[1].item()),
+                        "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": int(tot[0].item())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU arithmetic (oracle port; the reference is pure Python, so there is no oracle/_ref build) on the
     box's host cores.  Every step is one bounded sample pass (one unit per Kron bucket + the LRA unit at 2^22 rows); W warm-up passes and
@@ -693,6 +787,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--mode", default="functional", choices=["functional", "kwns4"],
+                    help="functional (default): update + apply per unit through the psgd.* functions (BASELINE configs[2]); kwns4: the same "
+                         "set through KWNS4.step(), preconditioners sharded per parameter at N > 1 (BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--noise", default="philox", choices=["philox", "torch"],
                     help="philox: damping noise and norm-bound probes drawn inside the engine's kernels (performance mode); torch: drawn by "
@@ -703,6 +800,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "kwns4":
+        run_kwns4(args)
     else:
         run_engine(args)
 

@@ -47,6 +47,7 @@ class KWNS4(torch.optim.Optimizer):
             update_preconditioner_first=True,
             resync_every=1000_000,
             shard_preconditioners=False,
+            batch_same_shape=False,
     ):
         # ddp.py:45-62, verbatim
         assert whiten_grad in (False, True)
@@ -93,6 +94,11 @@ class KWNS4(torch.optim.Optimizer):
         # which alone keeps its (Q, L, ema) and runs its update + apply; the updated parameter is then broadcast to the other ranks
         # (NCCL).  Off by default so that the class stays a drop-in with the reference's replicated semantics.
         self.shard_preconditioners = bool(shard_preconditioners)
+        # Not in the reference either: parameters of one shape share batched engine calls (psgd.*_batched: grouped tcgen05 launches, one
+        # norm-bound launch per batch).  The random draws then happen batch by batch instead of parameter by parameter, so it is off by
+        # default; a transformer's repeated layers are where it pays (64 k/v projections, 65 norm vectors, pairs of MLP matrices).
+        self.batch_same_shape = bool(batch_same_shape)
+        self.batch_numel_cap = 128 * 1024 * 1024     # elements of gradient per batched call (workspace grows with it)
         self._owner = None
         self.dQ = "Q0.5EQ1.5"  # ddp.py:84-86
         self.update_precond = psgd.update_precond_kron_whiten_q0p5eq1p5
@@ -306,11 +312,89 @@ class KWNS4(torch.optim.Optimizer):
                 st["ema"] = None if raw.get("ema") is None else raw["ema"].detach().to(device=lp.device, dtype=dt).contiguous().clone()
                 st["exprs"] = psgd.exprs_for_state(st["QL"][0], self.dQ)
 
+    # ---- one parameter's share of the loop body (ddp.py:117-143): state creation, weight decay + cast + EMA (one engine pass) ----
+    def _head(self, p, group):
+        lib = _lib.load_library()
+        momentum = group["momentum"]
+        wd, lr_params = group["weight_decay"], group["lr_params"]
+        local_p = self._local(p)
+        grad = self._local(p.grad)
+        if not local_p.is_contiguous():
+            raise _lib.EngineError("KWNS4 (B200 engine) needs contiguous parameters")
+        grad = grad.contiguous()
+        pre_dtype = group["preconditioner_dtype"] or grad.dtype
+        sq_shape = grad.squeeze().shape  # ddp.py:124
+        dev = grad.device
+        h = _lib.handle_for(dev)
+        state = self.state[p]
+        if len(state) == 0:  # ddp.py:130-137
+            QL, exprs = psgd.init_kron(torch.empty(sq_shape, dtype=pre_dtype, device=dev),
+                                       Scale=group["preconditioner_init_scale"],
+                                       max_size=group["preconditioner_max_size"],
+                                       max_skew=group["preconditioner_max_skew"], dQ=self.dQ)
+            state["QL"], state["exprs"] = QL, exprs
+            state["step"] = 0
+            state["ema"] = None if momentum == 0.0 else torch.zeros(sq_shape, dtype=pre_dtype, device=dev)
+        t = state["step"]
+        beta = min(t / (t + 1), momentum) if momentum > 0.0 else 0.0  # ddp.py:141
+        need_g = group["whiten_grad"] or momentum == 0.0
+        coupled = wd > 0.0 and not group["decoupled_weight_decay"]
+        g_cast = torch.empty(sq_shape, dtype=pre_dtype, device=dev) if (need_g and (grad.dtype != pre_dtype or coupled)) else None
+        # head: weight decay (ddp.py:117-122) + cast (125-127) + EMA (139-143), one pass
+        rc = lib.psgd_kwns4_head(h, grad.numel(), _lib.ptr(local_p), _lib.dtype_code(local_p), _lib.ptr(grad),
+                                 _lib.dtype_code(grad), float(wd), float(lr_params), int(group["decoupled_weight_decay"]),
+                                 _lib.ptr(state["ema"]), _lib.ptr(g_cast), _lib._DTYPES[pre_dtype], float(beta),
+                                 _lib.stream_ptr(dev))
+        _lib.check(h, rc, "psgd_kwns4_head")
+        state["step"] += 1
+        g_pre = g_cast if g_cast is not None else grad.view(sq_shape)
+        return {"p": p, "local_p": local_p, "state": state, "dev": dev, "h": h,
+                "whiten": g_pre if group["whiten_grad"] else state["ema"],       # ddp.py:145
+                "precond": g_pre if momentum == 0.0 else state["ema"]}           # ddp.py:150
+
+    def _tail(self, job, hh, sumsq, group):
+        """clip (ddp.py:153-156) + p -= lr*h (157), one pass, device-side branch"""
+        lib = _lib.load_library()
+        max_avg_amp, max_element_amp = group["grad_clip_max_amps"]
+        lp = job["local_p"]
+        rc = lib.psgd_kwns4_tail(job["h"], hh.numel(), hh.numel(), _lib.ptr(lp), _lib.dtype_code(lp), _lib.ptr(hh), _lib.dtype_code(hh),
+                                 _lib.ptr(sumsq), float(max_avg_amp), float(max_element_amp), float(group["lr_params"]),
+                                 _lib.stream_ptr(job["dev"]))
+        _lib.check(job["h"], rc, "psgd_kwns4_tail")
+
+    def _process(self, jobs, group, updateP_first, updateP_last):
+        """update (if due) -> apply -> tail -> update (if due last) for one parameter or one same-shape batch of parameters."""
+        kw = dict(lr=group["lr_preconditioner"], betaL=group["betaL"], damping=group["damping"])
+        if len(jobs) == 1:
+            job = jobs[0]
+            st = job["state"]
+            if updateP_first:  # ddp.py:146-148
+                self.update_precond(st["QL"], st["exprs"], job["whiten"], **kw)
+            sumsq = self._sumsq_buf(job["dev"])
+            hh = self.precond_grad(st["QL"], st["exprs"], job["precond"], sumsq_out=sumsq)  # ddp.py:150-151
+            self._tail(job, hh, sumsq, group)
+            if updateP_last:  # ddp.py:159-161
+                self.update_precond(st["QL"], st["exprs"], job["whiten"], **kw)
+            return
+        QLs = [j["state"]["QL"] for j in jobs]
+        if updateP_first:
+            psgd.update_precond_kron_whiten_q0p5eq1p5_batched(QLs, None, [j["whiten"] for j in jobs], **kw)
+        sumsq = torch.empty(len(jobs), dtype=torch.float32, device=jobs[0]["dev"])
+        hs = psgd.precond_grad_kron_batched(QLs, None, [j["precond"] for j in jobs], sumsq_out=sumsq)
+        for i, (job, hh) in enumerate(zip(jobs, hs)):
+            self._tail(job, hh, sumsq[i:i + 1], group)
+        if updateP_last:
+            psgd.update_precond_kron_whiten_q0p5eq1p5_batched(QLs, None, [j["whiten"] for j in jobs], **kw)
+
+    @staticmethod
+    def _batch_key(job):
+        st = job["state"]
+        g = job["whiten"]
+        return (tuple(g.shape), g.dtype, tuple(q.dim() for q in st["QL"][0])) if g.dim() <= 2 else None
+
     @torch.no_grad()
     def step(self):
         external = self._rng_enter()
-
-        lib = _lib.load_library()
         sharded = self._sharding_active()
         if sharded and self._owner is None:
             self._assign_owners()
@@ -318,93 +402,90 @@ class KWNS4(torch.optim.Optimizer):
         pending = []
         for group in self.param_groups:
             momentum = group["momentum"]
-            max_avg_amp, max_element_amp = group["grad_clip_max_amps"]
             coin = torch.rand([], generator=self._coin_gen) if sharded else torch.rand([])
             updateP_first, updateP_last = ((group["update_preconditioner_first"], not group["update_preconditioner_first"])
                                            if coin < group["preconditioner_update_probability"] else (False, False))
-            wd, lr_params = group["weight_decay"], group["lr_params"]
+            # the parameters this rank works on, in parameter order, and (sharded) the order in which every rank meets the broadcasts
+            mine, recv = [], []
             for p in group["params"]:
-                grad = p.grad
                 local_p = self._local(p)
                 if sharded:
-                    # owner and receivers must take the same decision or the broadcast below dead-locks: the skip tests use what
-                    # every rank sees alike (the parameter), never the local gradient, and a missing gradient on the owner is an error
+                    # owner and receivers must take the same decision or the broadcasts dead-lock: the skip tests use what every rank
+                    # sees alike (the parameter), never the local gradient, and a missing gradient on the owner is an error
                     if local_p.numel() == 0:
                         continue
                     owner = self._owner[id(p)]
-                    if owner != my_rank:   # the owner computes; this rank only receives the updated parameter
-                        pending.append(torch.distributed.broadcast(local_p, src=owner, async_op=True))
+                    if owner != my_rank:
+                        recv.append((p, owner))
                         continue
-                    if grad is None:
+                    if p.grad is None:
                         raise _lib.EngineError("shard_preconditioners=True: the owner rank has no gradient for a parameter the other ranks "
                                                "are waiting for (every parameter handed to KWNS4 must receive a gradient on every step)")
-                if grad is None:
+                if p.grad is None or self._local(p.grad).numel() == 0:  # ddp.py:114-115, dtensor.py:124-125
                     continue
-                grad = self._local(grad)
-                if grad.numel() == 0:  # dtensor.py:124-125
-                    continue
-                if not local_p.is_contiguous():
-                    raise _lib.EngineError("KWNS4 (B200 engine) needs contiguous parameters")
-                grad = grad.contiguous()
-                pre_dtype = group["preconditioner_dtype"] or grad.dtype
-                sq_shape = grad.squeeze().shape  # ddp.py:124
-                dev = grad.device
-                h = _lib.handle_for(dev)
-
-                state = self.state[p]
-                if len(state) == 0:  # ddp.py:130-137
-                    QL, exprs = psgd.init_kron(torch.empty(sq_shape, dtype=pre_dtype, device=dev),
-                                               Scale=group["preconditioner_init_scale"],
-                                               max_size=group["preconditioner_max_size"],
-                                               max_skew=group["preconditioner_max_skew"], dQ=self.dQ)
-                    state["QL"], state["exprs"] = QL, exprs
-                    state["step"] = 0
-                    state["ema"] = None if momentum == 0.0 else torch.zeros(sq_shape, dtype=pre_dtype, device=dev)
-
-                t = state["step"]
-                beta = min(t / (t + 1), momentum) if momentum > 0.0 else 0.0  # ddp.py:141
-                need_g = group["whiten_grad"] or momentum == 0.0
-                coupled = wd > 0.0 and not group["decoupled_weight_decay"]
-                if need_g and (grad.dtype != pre_dtype or coupled):
-                    g_cast = torch.empty(sq_shape, dtype=pre_dtype, device=dev)
-                else:
-                    g_cast = None
-                # head: weight decay (ddp.py:117-122) + cast (125-127) + EMA (139-143), one pass
-                rc = lib.psgd_kwns4_head(h, grad.numel(), _lib.ptr(local_p), _lib.dtype_code(local_p), _lib.ptr(grad),
-                                         _lib.dtype_code(grad), float(wd), float(lr_params), int(group["decoupled_weight_decay"]),
-                                         _lib.ptr(state["ema"]), _lib.ptr(g_cast), _lib._DTYPES[pre_dtype], float(beta),
-                                         _lib.stream_ptr(dev))
-                _lib.check(h, rc, "psgd_kwns4_head")
-                state["step"] += 1
-                g_pre = g_cast if g_cast is not None else grad.view(sq_shape)
-
-                to_be_whitened = g_pre if group["whiten_grad"] else state["ema"]
-                if updateP_first:  # ddp.py:146-148
-                    self.update_precond(state["QL"], state["exprs"], to_be_whitened,
-                                        lr=group["lr_preconditioner"], betaL=group["betaL"], damping=group["damping"])
-
-                to_be_preconded = g_pre if momentum == 0.0 else state["ema"]
-                sumsq = self._sumsq_buf(dev)
-                hh = self.precond_grad(state["QL"], state["exprs"], to_be_preconded, sumsq_out=sumsq)  # ddp.py:150-151
-
-                # tail: clip (ddp.py:153-156) + p -= lr*h (157), one pass, device-side branch
-                rc = lib.psgd_kwns4_tail(h, hh.numel(), hh.numel(), _lib.ptr(local_p), _lib.dtype_code(local_p), _lib.ptr(hh),
-                                         _lib.dtype_code(hh), _lib.ptr(sumsq), float(max_avg_amp), float(max_element_amp),
-                                         float(lr_params), _lib.stream_ptr(dev))
-                _lib.check(h, rc, "psgd_kwns4_tail")
-
-                if updateP_last:  # ddp.py:159-161
-                    self.update_precond(state["QL"], state["exprs"], to_be_whitened,
-                                        lr=group["lr_preconditioner"], betaL=group["betaL"], damping=group["damping"])
-
+                mine.append(p)
+            if not self.batch_same_shape:
+                # the reference's order: one parameter at a time (ddp.py:112-161)
                 if sharded:
-                    pending.append(torch.distributed.broadcast(local_p, src=my_rank, async_op=True))
+                    order = [p for p in group["params"] if self._local(p).numel() > 0]
+                    mine_set = set(id(p) for p in mine)
+                    for p in order:
+                        if id(p) in mine_set:
+                            self._process([self._head(p, group)], group, updateP_first, updateP_last)
+                        pending.append(torch.distributed.broadcast(self._local(p), src=self._owner[id(p)], async_op=True))
                 else:
-                    self._resync(p, state, group, momentum)
+                    for p in mine:
+                        job = self._head(p, group)
+                        self._process([job], group, updateP_first, updateP_last)
+                        self._resync(p, job["state"], group, momentum)
+                continue
+            # batched: same-shape parameters share engine calls (psgd.*_batched); not the reference's draw order
+            batches = self._make_batches(mine)
+            if not sharded:
+                for plist in batches:
+                    jobs = [self._head(p, group) for p in plist]
+                    self._process(jobs, group, updateP_first, updateP_last)
+                    for p, job in zip(plist, jobs):
+                        self._resync(p, job["state"], group, momentum)
+                continue
+            # sharded + batched: every rank derives every rank's batch list from the shapes and walks the same global sequence
+            # (round-robin over the owners' lists), computing its own batches and posting the broadcasts of all of them in that order
+            world = torch.distributed.get_world_size()
+            all_params = [p for p in group["params"] if self._local(p).numel() > 0]
+            per_rank = [self._make_batches([p for p in all_params if self._owner[id(p)] == r]) for r in range(world)]
+            for i in range(max(len(b) for b in per_rank)):
+                for r in range(world):
+                    if i >= len(per_rank[r]):
+                        continue
+                    plist = per_rank[r][i]
+                    if r == my_rank:
+                        self._process([self._head(p, group) for p in plist], group, updateP_first, updateP_last)
+                    for p in plist:
+                        pending.append(torch.distributed.broadcast(self._local(p), src=r, async_op=True))
         for w in pending:
             w.wait()
-
         self._rng_exit(external)
+
+    def _make_batches(self, plist):
+        """Consecutive-in-bucket grouping of parameters by (squeezed shape, dtype, dense/diagonal pattern), at most _lib.MAX_BATCH per
+        batch and at most ~1.5 GB of gradients per batch; order-3+ tensors stay alone.  Depends on shapes only: identical on every rank."""
+        buckets, order = {}, []
+        for p in plist:
+            lp = self._local(p)
+            shp = tuple(lp.squeeze().shape)
+            key = (shp, lp.dtype) if len(shp) <= 2 else ("single", id(p))
+            if key not in buckets:
+                buckets[key] = []
+                order.append(key)
+            buckets[key].append(p)
+        out = []
+        for key in order:
+            ps = buckets[key]
+            numel = max(1, self._local(ps[0]).numel())
+            cap = 1 if key[0] == "single" else max(1, min(_lib.MAX_BATCH, int(self.batch_numel_cap // numel)))
+            for i in range(0, len(ps), cap):
+                out.append(ps[i:i + cap])
+        return out
 
 
 class KWNS4DTensor(KWNS4):
