@@ -290,15 +290,56 @@ static int run_bounds_fused(Ctx* ctx, int dt, const BoundJob* jb, int n, const B
   return check_cuda(ctx, e == cudaSuccess ? cudaGetLastError() : e, "k_norm_bounds");
 }
 
+// tcgen05 form (bounds.cuh: k_norm_bounds_tc): matrices whose size is a multiple of 64
+static bool bound_fusable_tc(const Ctx* ctx, int dt, const BoundJob& J) {
+  return bound_fusable(ctx, dt, J) && (J.s % 64) == 0 && ctx->encode_tiled && !(ctx->debug_flags & 512);
+}
+
+static int run_bounds_fused_tc(Ctx* ctx, int dt, const BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st) {
+  NbTcParams P;
+  memset(&P, 0, sizeof(P));
+  int units = 0;
+  for (int j = 0; j < n; ++j) {
+    const BoundJob& J = jb[j];
+    NbTcJob& T = P.job[j];
+    int rc = make_tmap_mn3(ctx, &T.map_a, J.A, J.s, J.s, J.s, NT_BM / 64); if (rc) return rc;
+    rc = make_tmap(ctx, &T.map_va, J.Va, 32, J.s, J.s, 32); if (rc) return rc;
+    rc = make_tmap(ctx, &T.map_vb, J.Vb, 32, J.s, J.s, 32); if (rc) return rc;
+    NbJob& o = T.j;
+    o.A = (const bf16*)J.A; o.V0 = (const bf16*)J.V0; o.row_sumsq = J.row_sumsq; o.nf_src = J.nf_src;
+    o.Va = (bf16*)J.Va; o.Vb = (bf16*)J.Vb; o.scal = J.w->scal; o.rn1 = J.w->rn1; o.rn3 = J.w->rn3; o.rn4 = J.w->rn4; o.dots = J.w->sc1;
+    o.s = J.s; o.unit0 = units; o.nunits = (J.s + NT_BM - 1) / NT_BM;
+    units += o.nunits;
+    const BoundFinish f = fin ? fin[j] : BoundFinish{2, 0.f, 0.f, 0.f, nullptr, nullptr};
+    o.mode = f.mode; o.t2 = f.t2; o.lr = f.lr; o.betaL = f.betaL; o.L = f.L; o.fs = f.fs;
+  }
+  P.njobs = n; P.total_units = units; P.dtype = dt; P.tiny = dtype_tiny(dt);
+  P.barrier = ctx->nb_sync; P.done = ctx->nb_sync + 1;
+  P.mn_lbo = ctx->mn_lbo; P.mn_sbo = ctx->mn_sbo;
+  static PerDeviceOnce attr;
+  if (attr.need(ctx->device)) {
+    cudaError_t e = cudaFuncSetAttribute(k_norm_bounds_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "cudaFuncSetAttribute(k_norm_bounds_tc)");
+  }
+  const int grid = units < ctx->num_sms ? units : ctx->num_sms;
+  void* args[1] = {&P};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_norm_bounds_tc, dim3(grid), dim3(NT_THREADS), args, (size_t)NT_SMEM_BYTES, st);
+  ctx->launches++;
+  return check_cuda(ctx, e == cudaSuccess ? cudaGetLastError() : e, "k_norm_bounds_tc");
+}
+
 static int run_bounds_unfused(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st);
 
 static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* fin, cudaStream_t st) {
-  BoundJob fj[NB_MAX_JOBS];
-  BoundFinish ff[NB_MAX_JOBS];
-  int nf = 0;
+  BoundJob fj[NB_MAX_JOBS], tj[NT_MAX_JOBS];
+  BoundFinish ff[NB_MAX_JOBS], tf[NT_MAX_JOBS];
+  int nf = 0, nt = 0;
   for (int j = 0; j < n; ++j) {
     const BoundFinish f = fin ? fin[j] : BoundFinish{2, 0.f, 0.f, 0.f, nullptr, nullptr};
-    if (bound_fusable(ctx, dt, jb[j])) {
+    if (bound_fusable_tc(ctx, dt, jb[j])) {
+      tj[nt] = jb[j]; tf[nt++] = f;
+      if (nt == NT_MAX_JOBS) { int rc = run_bounds_fused_tc(ctx, dt, tj, nt, tf, st); if (rc) return rc; nt = 0; }
+    } else if (bound_fusable(ctx, dt, jb[j])) {
       fj[nf] = jb[j]; ff[nf++] = f;
       if (nf == NB_MAX_JOBS) { int rc = run_bounds_fused(ctx, dt, fj, nf, ff, st); if (rc) return rc; nf = 0; }
     } else {
@@ -306,6 +347,7 @@ static int run_bounds(Ctx* ctx, int dt, BoundJob* jb, int n, const BoundFinish* 
       int rc = run_bounds_unfused(ctx, dt, &one, 1, &f, st); if (rc) return rc;
     }
   }
+  if (nt) { int rc = run_bounds_fused_tc(ctx, dt, tj, nt, tf, st); if (rc) return rc; }
   if (nf) { int rc = run_bounds_fused(ctx, dt, fj, nf, ff, st); if (rc) return rc; }
   return PSGD_OK;
 }

@@ -24,6 +24,7 @@
 #pragma once
 #include "common.cuh"
 #include "kron_kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace psgd {
 
@@ -404,6 +405,282 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_cons
   if (s_last) {
     __threadfence();
     if (tid < P.njobs) nb_finish_job(P.job[tid], P.dtype, P.tiny);
+    __syncthreads();
+    if (tid == 0) { *P.barrier = 0u; *P.done = 0u; __threadfence(); }
+  }
+}
+
+
+// =====================================================================================================================================
+// tcgen05 form of the same kernel (matrices whose size is a multiple of 64).  mma.sync m16n8k16 turned out to issue only once per ~32
+// cycles per SM sub-partition on this part (profiles/r02_ncu_bounds_hmma.txt: the mma.sync kernel above is bound by exactly that: 4096 HMMA
+// per unit and step = 33 k cycles), so the products move to the 5th-generation tensor cores:
+//   unit = 128 columns of A:  D[128 x 32] (TMEM, fp32) = A[:, slab]^T (MN-major operand, 3-D TMA box) x V^T (K-major operand, 32 rows)
+//   warp 0: TMA producer (8-stage mbarrier ring: A tile 16 KB + V tile 4 KB per 64-row k block), warp 1: single-thread tcgen05.mma issuer
+//   (M = 128, N = 32, K = 16 x 4 per block), warps 2-5: epilogue (tcgen05.ld: thread = column of A, registers = probes -> scale, round, per-probe
+//   sums of squares by a warp transpose-reduce, coalesced 2-byte stores V_new[p][col]).
+// Phase I writes the rotated probes V = A'[j] + sgn V0 to global memory (one more grid barrier than the mma.sync form, whose probes
+// are rotated in shared memory) so that step 0 is fed by TMA like the other steps.
+// =====================================================================================================================================
+constexpr int NT_BM = 128;
+constexpr int NT_BK = 64;
+constexpr int NT_STAGES = 8;
+constexpr int NT_THREADS = 192;
+constexpr int NT_MAX_JOBS = 8;
+constexpr int NT_A_BYTES = NT_BM * NT_BK * 2;
+constexpr int NT_V_BYTES = 32 * NT_BK * 2;
+constexpr int NT_STAGE_BYTES = NT_A_BYTES + NT_V_BYTES;
+constexpr int NT_SMEM_BYTES = NT_STAGES * NT_STAGE_BYTES + 1024 + 256;
+
+struct alignas(64) NbTcJob {
+  CUtensorMap map_a;    // A as MN-major operand: 3-D {64, s, s / 64}, box {64, 64, 2}
+  CUtensorMap map_va;   // Va / Vb as K-major operand: 2-D {s, 32}, box {64, 32}
+  CUtensorMap map_vb;
+  NbJob j;              // unit0 / nunits count 128-column units here
+};
+struct alignas(64) NbTcParams {
+  NbTcJob job[NT_MAX_JOBS];
+  int njobs, total_units, dtype;
+  float tiny;
+  unsigned* barrier;
+  unsigned* done;
+  int mn_lbo, mn_sbo;
+};
+
+__device__ __forceinline__ void nb_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NT_THREADS, 1) k_norm_bounds_tc(const __grid_constant__ NbTcParams P) {
+  extern __shared__ uint8_t nt_smem_raw[];
+  const uint32_t smem_base = (smem_u32(nt_smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = nt_smem_raw + (smem_base - smem_u32(nt_smem_raw));
+  const uint32_t bar_base = smem_base + NT_STAGES * NT_STAGE_BYTES;
+  auto full_bar = [&](int st_) { return bar_base + 8u * st_; };
+  auto empty_bar = [&](int st_) { return bar_base + 8u * (NT_STAGES + st_); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * NT_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NT_STAGES + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + NT_STAGES * NT_STAGE_BYTES + 8 * (2 * NT_STAGES + 1));
+  __shared__ float s_scale[32];
+  __shared__ float s_dots[32];
+  __shared__ float s_sv[8];
+  __shared__ int s_si[9];
+  __shared__ int s_last;
+  __shared__ int s_jc[NT_MAX_JOBS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned ncta = gridDim.x;
+  unsigned nbar = 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < NT_STAGES; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+    for (int i = 0; i < P.njobs; ++i) { prefetch_tmap(&P.job[i].map_a); prefetch_tmap(&P.job[i].map_va); prefetch_tmap(&P.job[i].map_vb); }
+  }
+  if (tid < NT_MAX_JOBS) s_jc[tid] = -1;
+  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  auto job_of = [&](int u) {
+    int ji = 0;
+    for (int i = 1; i < P.njobs; ++i)
+      if (u >= P.job[i].j.unit0) ji = i;
+    return ji;
+  };
+  // block-wide argmax of the squared row norms (first maximal index), any block size up to 8 warps
+  auto block_argmax = [&](const float* x, int s) {
+    float best = -1.f;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < s; i += NT_THREADS) {
+      const float v = __ldcg(x + i);
+      if (v > best) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_sv[warp] = best; s_si[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < NT_THREADS / 32; ++w)
+        if (s_sv[w] > best || (s_sv[w] == best && s_si[w] < bi)) { best = s_sv[w]; bi = s_si[w]; }
+      s_si[8] = (bi == 0x7fffffff) ? 0 : bi;
+    }
+    __syncthreads();
+    return s_si[8];
+  };
+
+  // ------------------------------ phase I-a: signs of the probe rotation (psgd.py:63) ------------------------------
+  for (int u = blockIdx.x; u < P.total_units; u += ncta) {
+    const int ji = job_of(u);
+    const NbJob& J = P.job[ji].j;
+    int j = s_jc[ji];
+    if (j < 0) { j = block_argmax(J.row_sumsq, J.s); if (tid == 0) s_jc[ji] = j; }
+    const float inv_nf = 1.f / (__ldcg(J.nf_src) + P.tiny);
+    if (tid < 32) s_dots[tid] = 0.f;
+    __syncthreads();
+    for (int idx = tid; idx < 32 * 16; idx += NT_THREADS) {
+      const int p = idx >> 4, c0 = (u - J.unit0) * NT_BM + (idx & 15) * 8;
+      if (c0 < J.s) {
+        float a[8], v[8], part = 0.f;
+        ld8(J.A + (size_t)j * J.s + c0, a);
+        ld8(J.V0 + (size_t)p * J.s + c0, v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) part += rbf(rbf(a[t] * inv_nf) * v[t]);
+        atomicAdd(&s_dots[p], part);
+      }
+    }
+    __syncthreads();
+    if (tid < 32 && s_dots[tid] != 0.f) atomicAdd(J.dots + tid, s_dots[tid]);
+    __syncthreads();
+  }
+  nb_grid_barrier(P.barrier, ncta * (++nbar));
+  // ------------------------------ phase I-b: V = A'[j] + sgn V0 -> Va ------------------------------
+  for (int u = blockIdx.x; u < P.total_units; u += ncta) {
+    const int ji = job_of(u);
+    const NbJob& J = P.job[ji].j;
+    const int j = s_jc[ji];
+    const float inv_nf = 1.f / (__ldcg(J.nf_src) + P.tiny);
+    if (u == J.unit0 && tid == 0) reinterpret_cast<int*>(J.scal)[SC_J] = j;
+    for (int idx = tid; idx < 32 * 16; idx += NT_THREADS) {
+      const int p = idx >> 4, c0 = (u - J.unit0) * NT_BM + (idx & 15) * 8;
+      if (c0 < J.s) {
+        const float d = __ldcg(J.dots + p);
+        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        float a[8], v[8], o[8];
+        ld8(J.A + (size_t)j * J.s + c0, a);
+        ld8(J.V0 + (size_t)p * J.s + c0, v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = rbf(a[t] * inv_nf) + sg * v[t];
+        st8(J.Va + (size_t)p * J.s + c0, o);
+      }
+    }
+  }
+  nb_fence_proxy_async();        // generic-proxy stores of Va -> async-proxy (TMA) reads by every CTA after the barrier
+  nb_grid_barrier(P.barrier, ncta * (++nbar));
+  nb_fence_proxy_async();
+
+  // ------------------------------ the four products ------------------------------
+  int p_stage = 0; uint32_t p_phase = 0;     // producer's ring position
+  int c_stage = 0; uint32_t c_phase = 0;     // MMA issuer's ring position
+  uint32_t t_phase = 0;                      // accumulator-full barrier phase (every warp counts the units)
+  for (int st = 0; st < 4; ++st) {
+    for (int u = blockIdx.x; u < P.total_units; u += ncta) {
+      const int ji = job_of(u);
+      const NbTcJob& TJ = P.job[ji];
+      const NbJob& J = TJ.j;
+      const int s = J.s;
+      const int nkb = s / NT_BK;
+      const int slab = u - J.unit0;
+      if (tid < 32) {
+        float sc = 1.f / (__ldcg(J.nf_src) + P.tiny);
+        if (st == 1) sc *= fminf(1.f / (sqrtf(__ldcg(J.rn1 + tid)) + P.tiny), 3.0e38f);
+        if (st == 3) sc *= fminf(1.f / (sqrtf(__ldcg(J.rn3 + tid)) + P.tiny), 3.0e38f);
+        s_scale[tid] = fminf(sc, 3.0e38f);
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (warp == 0) {
+        // ===================== TMA producer =====================
+        const CUtensorMap* mv = (st & 1) ? &TJ.map_vb : &TJ.map_va;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(p_stage), p_phase ^ 1u, nullptr);
+          if (elect_one()) {
+            const uint32_t sa = smem_base + p_stage * NT_STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(p_stage), NT_STAGE_BYTES);
+            tma_load_3d(&TJ.map_a, full_bar(p_stage), sa, 0, kb * NT_BK, slab * (NT_BM / 64));
+            tma_load_2d(mv, full_bar(p_stage), sa + NT_A_BYTES, kb * NT_BK, 0);
+          }
+          __syncwarp();
+          if (++p_stage == NT_STAGES) { p_stage = 0; p_phase ^= 1u; }
+        }
+      } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // instruction descriptor: D = f32 (bit 4), A = bf16 (bit 7), B = bf16 (bit 10), A MN-major (bit 15), N >> 3 at bits 17-22, M >> 4 at 24-28
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (uint32_t(32 >> 3) << 17) | (uint32_t(NT_BM >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(c_stage), c_phase, nullptr);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_base + c_stage * NT_STAGE_BYTES;
+            const uint32_t sv = sa + NT_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < NT_BK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * (16u * 128u), (uint32_t)P.mn_lbo, (uint32_t)P.mn_sbo);
+              const uint64_t bdesc = make_smem_desc(sv + k * 32u, 0u, 1024u);
+              umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(c_stage));
+            if (kb + 1 == nkb) umma_commit(tfull_bar);
+          }
+          __syncwarp();
+          if (++c_stage == NT_STAGES) { c_stage = 0; c_phase ^= 1u; }
+        }
+      } else {
+        // ===================== epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 = columns of A =====================
+        const int quarter = warp & 3;
+        mbar_wait_relaxed(tfull_bar, t_phase, nullptr);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16), raw);
+        tmem_ld_wait();
+        const int col = slab * NT_BM + quarter * 32 + lane;
+        const bool ok = col < s;
+        float v[32];
+#pragma unroll
+        for (int jx = 0; jx < 32; ++jx) v[jx] = ok ? rbf(__uint_as_float(raw[jx]) * s_scale[jx]) : 0.f;
+        if (st < 3 && ok) {
+          bf16* dst = ((st & 1) ? J.Va : J.Vb) + col;
+#pragma unroll
+          for (int jx = 0; jx < 32; ++jx) dst[(size_t)jx * s] = __float2bfloat16_rn(v[jx]);
+        }
+        float* rn = st == 0 ? J.rn1 : (st == 2 ? J.rn3 : (st == 3 ? J.rn4 : nullptr));
+        if (rn) {
+          // transpose-reduce: after the 5 halving steps lane l holds the sum over the warp's 32 columns of probe l
+#pragma unroll
+          for (int jx = 0; jx < 32; ++jx) v[jx] = v[jx] * v[jx];
+#define NB_TR_STEP(OFF)                                                \
+          {                                                            \
+            const bool upper = (lane & (OFF)) != 0;                    \
+            _Pragma("unroll") for (int i = 0; i < (OFF); ++i) {        \
+              const float send = upper ? v[i] : v[i + (OFF)];          \
+              const float keep = upper ? v[i + (OFF)] : v[i];          \
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, (OFF)); \
+            }                                                          \
+          }
+          NB_TR_STEP(16) NB_TR_STEP(8) NB_TR_STEP(4) NB_TR_STEP(2) NB_TR_STEP(1)
+#undef NB_TR_STEP
+          if (v[0] != 0.f) atomicAdd(rn + lane, v[0]);
+        }
+      }
+      t_phase ^= 1u;
+      tc_fence_before();
+      __syncthreads();       // the accumulator is drained and every role is done with this unit
+    }
+    if (st < 3) {
+      nb_fence_proxy_async();
+      nb_grid_barrier(P.barrier, ncta * (++nbar));
+      nb_fence_proxy_async();
+    }
+  }
+
+  // ------------------------------ finish: the CTA that arrives last ------------------------------
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+  if (tid == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(P.done, 1u);
+    s_last = (old == ncta - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (tid < P.njobs) nb_finish_job(P.job[tid].j, P.dtype, P.tiny);
     __syncthreads();
     if (tid == 0) { *P.barrier = 0u; *P.done = 0u; __threadfence(); }
   }

@@ -216,9 +216,10 @@ class KWNS4(torch.optim.Optimizer):
                 has[i] = 1 + self.state[p]["step"]
         dist.all_reduce(has, op=dist.ReduceOp.MAX)
         has = has.tolist()
+        index_of = {id(p): i for i, p in enumerate(plist)}
         for group in self.param_groups:
             for p in group["params"]:
-                i = plist.index(p)
+                i = index_of[id(p)]
                 if has[i] == 0:
                     continue
                 owner = self._owner[id(p)]

@@ -66,7 +66,19 @@ def _stand_ins(log):
             sumsq_out.copy_((out.float() ** 2).sum().reshape(sumsq_out.shape))
         return out
 
+    def update_batched(QLs, exprs, Gs, lr=0.1, betaL=0.9, damping=1e-9):
+        for QL, G in zip(QLs, Gs):
+            update(QL, None, G, lr=lr, betaL=betaL, damping=damping)
+
+    def apply_batched(QLs, exprs, Gs, sumsq_out=None):
+        outs = [apply(QL, None, G) for QL, G in zip(QLs, Gs)]
+        if sumsq_out is not None:
+            sumsq_out.copy_(torch.stack([(o.float() ** 2).sum() for o in outs]))
+        return outs
+
+    lib.MAX_BATCH = 16
     ps = types.SimpleNamespace(init_kron=real_psgd.init_kron, update_precond_kron_whiten_q0p5eq1p5=update, precond_grad_kron=apply,
+                               update_precond_kron_whiten_q0p5eq1p5_batched=update_batched, precond_grad_kron_batched=apply_batched,
                                exprs_for_state=real_psgd.exprs_for_state)
     return lib, ps
 

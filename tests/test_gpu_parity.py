@@ -504,9 +504,9 @@ def test_kwns4_continues_from_a_reference_written_checkpoint(fname, monkeypatch)
     assert not queue
 
 
-@pytest.mark.parametrize("s", [128, 264, 1000, 2048, 4096])
+@pytest.mark.parametrize("s,form_flags", [(128, 0), (192, 0), (264, 0), (1000, 0), (2048, 0), (4096, 0), (2048, 512), (4096, 512)])
 @pytest.mark.parametrize("kind", ["spd", "skh"])
-def test_fused_norm_bound_kernel_matches_oracle_and_the_unfused_form(s, kind):
+def test_fused_norm_bound_kernel_matches_oracle_and_the_unfused_form(s, kind, form_flags):
     """psgd.py:46-93 in bf16: the persistent cooperative kernel (bounds.cuh: probe rotation, four L2-resident products with grid barriers,
     finish) against the bf16 oracle, an fp64 evaluation, and the round-1 form (separate GEMM launches, debug flag bit 8)."""
     from psgd_torch_b200 import psgd, _lib
@@ -526,6 +526,8 @@ def test_fused_norm_bound_kernel_matches_oracle_and_the_unfused_form(s, kind):
     b_o = f_o(A, V0).float()
     b_64 = f_o(A.double(), V0.double())
     lib, h = _lib.load_library(), _lib.handle_for(dev)
+    # form_flags 0: the tcgen05 form where s is a multiple of 64, else the mma.sync form; 512: the mma.sync form everywhere
+    lib.psgd_debug_set_flags(h, form_flags)
     l0 = _lib.launch_count(dev)
     b_e = f_e(A.to(dev), V0=V0.to(dev)).float()
     fused_launches = _lib.launch_count(dev) - l0
@@ -536,7 +538,7 @@ def test_fused_norm_bound_kernel_matches_oracle_and_the_unfused_form(s, kind):
         unfused_launches = _lib.launch_count(dev) - l0
     finally:
         lib.psgd_debug_set_flags(h, 0)
-    tag = f"norm_lower_bound_{kind} bf16 s={s}"
+    tag = f"norm_lower_bound_{kind} bf16 s={s} ({'mma.sync form' if (form_flags or s % 64) else 'tcgen05 form'})"
     assert fused_launches < unfused_launches and fused_launches <= 3, (fused_launches, unfused_launches)   # row stats + fused kernel + copy
     check(tag, "bound (fused kernel) vs bf16 oracle", b_e, b_o, 2e-2, yard=b_64, floor=1e-2)
     check(tag, "bound (fused kernel) vs unfused form", b_e, b_u, 2e-2)

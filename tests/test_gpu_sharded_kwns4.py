@@ -19,6 +19,16 @@ SHAPES = [(256, 384), (384,), (128, 2048), (64, 64), (128, 2048), (1, 96, 1, 40)
 
 
 def _worker(rank, world, port, q):
+    import faulthandler
+    import traceback
+    faulthandler.dump_traceback_later(240, exit=True)      # a dead-locked collective must not eat the GPU lease
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception:
+        q.put((rank, {"error": traceback.format_exc()}))
+
+
+def _worker_body(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -95,10 +105,15 @@ def test_sharded_kwns4_two_ranks_on_one_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=600) for _ in range(2))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = dict(q.get(timeout=300) for _ in range(2))
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for r in (0, 1):
+        assert "error" not in res[r], res[r]["error"]
     rep = res[0]["rep"]
     assert rep[-1] < 0.2 * rep[0]
     for name in ("sharded", "sharded_batched"):

@@ -354,3 +354,85 @@ def test_lra_optimizer_checkpoint_round_trip():
     for a, b in zip(opt2._UVd + opt2._Luvd + [opt2._m], opt._UVd + opt._Luvd + [opt._m]):
         assert torch.equal(a, b)
     assert opt2._counter_m == 11
+
+
+# ---- KWNS4(shard_preconditioners=True): schedule, ownership, collective checkpoint -- world_size 2 over gloo, oracle-backed engine stand-in ----
+def _sharded_kwns4_worker(rank, world, port, q):
+    import traceback
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from psgd_torch_b200 import kwns4
+        from test_dtensor_host_logic import _stand_ins
+        kwns4._lib, kwns4.psgd = _stand_ins([])
+        shapes = [(12, 16), (16,), (6, 40), (8, 8), (6, 40), (1, 5, 1, 4), (16,), (12, 16)]
+        g0 = torch.Generator().manual_seed(3)
+        targets = [torch.randn(*s, generator=g0) for s in shapes]
+        out = {}
+        for name, batched in (("plain", False), ("batched", True)):
+            torch.manual_seed(11)
+            ps = [torch.nn.Parameter(torch.zeros(*s)) for s in shapes]
+            opt = kwns4.KWNS4(ps, lr_params=0.05, lr_preconditioner=0.3, weight_decay=0.0, preconditioner_dtype=torch.float32,
+                              shard_preconditioners=True, batch_same_shape=batched)
+
+            def steps(ps, opt, n):
+                losses = []
+                for _ in range(n):
+                    loss = sum(((p - t) ** 2).sum() for p, t in zip(ps, targets))
+                    losses.append(float(loss.detach()))
+                    for p, g in zip(ps, torch.autograd.grad(loss, ps)):
+                        p.grad = g
+                    opt.step()
+                return losses
+
+            losses = steps(ps, opt, 12)
+            owned = [i for i, p in enumerate(ps) if len(opt.state[p]) > 0]
+            sd = opt.state_dict()                       # collective
+            ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+            torch.manual_seed(999 + rank)
+            opt2 = kwns4.KWNS4(ps2, lr_params=0.05, lr_preconditioner=0.3, weight_decay=0.0, preconditioner_dtype=torch.float32,
+                               shard_preconditioners=True, batch_same_shape=batched)
+            opt2.load_state_dict(sd)
+            owned2 = [i for i, p in enumerate(ps2) if len(opt2.state[p]) > 0]
+            more = steps(ps2, opt2, 3)
+            diffs = []
+            for p in list(ps) + list(ps2):
+                ref = p.detach().clone()
+                dist.broadcast(ref, src=0)
+                diffs.append(float((p.detach() - ref).abs().max()))
+            out[name] = dict(losses=losses, owned=owned, owned2=owned2, n_saved=len(sd["state"]), more=more, diff=max(diffs),
+                             coin=float(torch.rand([], generator=opt2._coin_gen)))
+        q.put((rank, out))
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, {"error": traceback.format_exc()}))
+
+
+def test_world_size_2_gloo_sharded_kwns4_schedule_and_checkpoint():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 37500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sharded_kwns4_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        res = dict(q.get(timeout=180) for _ in range(2))
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for r in (0, 1):
+        assert "error" not in res[r], res[r]["error"]
+    for name in ("plain", "batched"):
+        a, b = res[0][name], res[1][name]
+        assert a["diff"] == 0.0 and b["diff"] == 0.0, "parameters must be bit-identical on every rank"
+        assert sorted(a["owned"] + b["owned"]) == list(range(8)) and a["owned"] and b["owned"]
+        assert a["n_saved"] == 8 and b["n_saved"] == 8, "the collective state_dict() holds every parameter's state on every rank"
+        assert a["owned2"] == a["owned"] and b["owned2"] == b["owned"]
+        assert a["losses"][-1] < 0.5 * a["losses"][0] and a["more"][-1] < a["more"][0]
+        assert a["coin"] == b["coin"], "the resumed update-coin generators must agree across ranks"
