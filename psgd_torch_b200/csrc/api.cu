@@ -302,7 +302,7 @@ static int run_bounds_fused_tc(Ctx* ctx, int dt, const BoundJob* jb, int n, cons
   for (int j = 0; j < n; ++j) {
     const BoundJob& J = jb[j];
     NbTcJob& T = P.job[j];
-    int rc = make_tmap_mn3(ctx, &T.map_a, J.A, J.s, J.s, J.s, NT_BM / 64); if (rc) return rc;
+    int rc = make_tmap_mn3(ctx, &T.map_a, J.A, J.s, J.s, J.s, NT_BM / 64, NT_BK); if (rc) return rc;
     rc = make_tmap(ctx, &T.map_va, J.Va, 32, J.s, J.s, 32); if (rc) return rc;
     rc = make_tmap(ctx, &T.map_vb, J.Vb, 32, J.s, J.s, 32); if (rc) return rc;
     NbJob& o = T.j;

@@ -423,8 +423,8 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_norm_bounds(const __grid_cons
 // are rotated in shared memory) so that step 0 is fed by TMA like the other steps.
 // =====================================================================================================================================
 constexpr int NT_BM = 128;
-constexpr int NT_BK = 64;
-constexpr int NT_STAGES = 8;
+constexpr int NT_BK = 256;      // k rows per stage: the issue loops of the single producer / MMA threads cost ~500 cycles per stage whatever its
+constexpr int NT_STAGES = 2;    // size (dependent-issue latency of one warp), so stages are big: 80 KB each (64-row stages: 62 GB/s per SM)
 constexpr int NT_THREADS = 192;
 constexpr int NT_MAX_JOBS = 8;
 constexpr int NT_A_BYTES = NT_BM * NT_BK * 2;
@@ -433,8 +433,8 @@ constexpr int NT_STAGE_BYTES = NT_A_BYTES + NT_V_BYTES;
 constexpr int NT_SMEM_BYTES = NT_STAGES * NT_STAGE_BYTES + 1024 + 256;
 
 struct alignas(64) NbTcJob {
-  CUtensorMap map_a;    // A as MN-major operand: 3-D {64, s, s / 64}, box {64, 64, 2}
-  CUtensorMap map_va;   // Va / Vb as K-major operand: 2-D {s, 32}, box {64, 32}
+  CUtensorMap map_a;    // A as MN-major operand: 3-D {64, s, s / 64}, box {64, NT_BK, 2}
+  CUtensorMap map_va;   // Va / Vb as K-major operand: 2-D {s, 32}, box {64, 32} (NT_BK / 64 boxes per stage)
   CUtensorMap map_vb;
   NbJob j;              // unit0 / nunits count 128-column units here
 };
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_norm_bounds_tc(const __grid_c
   }
   nb_fence_proxy_async();        // generic-proxy stores of Va -> async-proxy (TMA) reads by every CTA after the barrier
   nb_grid_barrier(P.barrier, ncta * (++nbar));
-  nb_fence_proxy_async();
+  if (warp == 0) nb_fence_proxy_async();
 
   // ------------------------------ the four products ------------------------------
   int p_stage = 0; uint32_t p_phase = 0;     // producer's ring position
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_norm_bounds_tc(const __grid_c
       const NbTcJob& TJ = P.job[ji];
       const NbJob& J = TJ.j;
       const int s = J.s;
-      const int nkb = s / NT_BK;
+      const int nkb = (s + NT_BK - 1) / NT_BK;      // the last block may be partial: TMA zero-fills rows / columns beyond s
       const int slab = u - J.unit0;
       if (tid < 32) {
         float sc = 1.f / (__ldcg(J.nf_src) + P.tiny);
@@ -594,7 +594,8 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_norm_bounds_tc(const __grid_c
             const uint32_t sa = smem_base + p_stage * NT_STAGE_BYTES;
             mbar_arrive_expect_tx(full_bar(p_stage), NT_STAGE_BYTES);
             tma_load_3d(&TJ.map_a, full_bar(p_stage), sa, 0, kb * NT_BK, slab * (NT_BM / 64));
-            tma_load_2d(mv, full_bar(p_stage), sa + NT_A_BYTES, kb * NT_BK, 0);
+#pragma unroll
+            for (int c = 0; c < NT_BK / 64; ++c) tma_load_2d(mv, full_bar(p_stage), sa + NT_A_BYTES + c * 4096, kb * NT_BK + c * 64, 0);
           }
           __syncwarp();
           if (++p_stage == NT_STAGES) { p_stage = 0; p_phase ^= 1u; }
@@ -603,16 +604,19 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_norm_bounds_tc(const __grid_c
         // ===================== MMA issuer =====================
         // instruction descriptor: D = f32 (bit 4), A = bf16 (bit 7), B = bf16 (bit 10), A MN-major (bit 15), N >> 3 at bits 17-22, M >> 4 at 24-28
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (uint32_t(32 >> 3) << 17) | (uint32_t(NT_BM >> 4) << 24);
+        // descriptors of stage 0, k step 0; the others differ in the 14-bit start-address field only (16-byte units, no carry: smem < 256 KB).
+        // MN-major A tile = [2 chunks][NT_BK k rows][128 B]: LBO = chunk stride, SBO = 8 k rows; K-major V tile = NT_BK / 64 boxes of [32 rows][128 B]
+        const uint64_t adesc0 = make_smem_desc(smem_base, (uint32_t)(NT_BK * 128), (uint32_t)P.mn_sbo);
+        const uint64_t bdesc0 = make_smem_desc(smem_base + NT_A_BYTES, 0u, 1024u);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(c_stage), c_phase, nullptr);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t sa = smem_base + c_stage * NT_STAGE_BYTES;
-            const uint32_t sv = sa + NT_A_BYTES;
+            const uint64_t so = (uint64_t)((c_stage * NT_STAGE_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < NT_BK / 16; ++k) {
-              const uint64_t adesc = make_smem_desc(sa + k * (16u * 128u), (uint32_t)P.mn_lbo, (uint32_t)P.mn_sbo);
-              const uint64_t bdesc = make_smem_desc(sv + k * 32u, 0u, 1024u);
+              const uint64_t adesc = adesc0 + so + (uint64_t)((k * 16 * 128) >> 4);
+              const uint64_t bdesc = bdesc0 + so + (uint64_t)(((k >> 2) * 4096 + (k & 3) * 32) >> 4);
               umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(empty_bar(c_stage));
@@ -657,15 +661,15 @@ __global__ void __launch_bounds__(NT_THREADS, 1) k_norm_bounds_tc(const __grid_c
 #undef NB_TR_STEP
           if (v[0] != 0.f) atomicAdd(rn + lane, v[0]);
         }
+        if (st < 3) nb_fence_proxy_async();   // this thread's stores of V_new are read through TMA (async proxy) after the grid barrier
       }
       t_phase ^= 1u;
       tc_fence_before();
       __syncthreads();       // the accumulator is drained and every role is done with this unit
     }
     if (st < 3) {
-      nb_fence_proxy_async();
       nb_grid_barrier(P.barrier, ncta * (++nbar));
-      nb_fence_proxy_async();
+      if (warp == 0) nb_fence_proxy_async();
     }
   }
 

@@ -847,12 +847,12 @@ int make_tmap(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, i
 
 // MN-major operand (rows = K, cols = MN, cols % 64 == 0) as a 3-D tensor {64 elems, rows, cols/64}: box {64, 64, chunks} lands in smem as
 // [chunk][k row][64 elems] -- the same layout the per-chunk 2-D boxes produce -- with a single TMA operation
-int make_tmap_mn3(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int chunks) {
+int make_tmap_mn3(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int chunks, int k_rows) {
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
   if (!fn) return PSGD_ERR_CUDA;
   cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
-  cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, (cuuint32_t)chunks};
+  cuuint32_t box[3] = {64, (cuuint32_t)(k_rows > 0 ? k_rows : TC_BK), (cuuint32_t)chunks};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -151,8 +151,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 
 // host side (gemm_tc.cu): tensor maps of a row-major bf16 matrix
 //   make_tmap: 2-D {cols, rows}, box {64 cols, box_rows}, 128-byte swizzle (K-major operand tiles)
-//   make_tmap_mn3: MN-major operand (rows = K, cols = MN, cols % 64 == 0) as 3-D {64, rows, cols / 64}, box {64, 64 k-rows, chunks}
+//   make_tmap_mn3: MN-major operand (rows = K, cols = MN, cols % 64 == 0) as 3-D {64, rows, cols / 64}, box {64, k_rows (default 64), chunks}
 int make_tmap(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows);
-int make_tmap_mn3(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int chunks);
+int make_tmap_mn3(Ctx* ctx, CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int chunks, int k_rows = 0);
 
 }  // namespace psgd

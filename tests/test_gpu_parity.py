@@ -606,7 +606,7 @@ def test_in_kernel_philox_noise_is_standard_normal_and_reproducible():
     (seed, offset) must reproduce it, a different seed must not."""
     from psgd_torch_b200 import psgd
     dev = _dev()
-    m, n = 512, 1024
+    m, n = 512, 512          # both factors dense
 
     def gram_diag_after_update(seed, offset):
         # Q = I, G = 0, damping = 1: Pg = N, so term1 = N N^T and L[0] is a bound of ||N N^T|| + n; Q_new - Q = -lr/L (N N^T - n I) Q ...
