@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # headers each translation unit includes (directly or through common.cuh); the public header reaches all of them
 DEPS = {"api.cu": ["common.cuh", "kron_kernels.cuh", "kron_geom.cuh", "bounds.cuh", "tc_ptx.cuh"], "gemm_simt.cu": ["common.cuh"],
         "gemm_tc.cu": ["common.cuh", "tc_ptx.cuh"],
-        "lra.cu": ["common.cuh", "lra_mma.cuh"]}
+        "lra.cu": ["common.cuh", "lra_mma.cuh", "lra_tc.cuh", "tc_ptx.cuh"]}
 
 
 def _headers(src):

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "lra_mma.cuh"
+#include "lra_tc.cuh"
 
 namespace psgd {
 
@@ -680,8 +681,52 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   // tensor-core sweeps: bf16, rank exactly 16 or 32 (rows are whole 16-byte pieces); everything else takes the CUDA-core sweeps
   const bool mma_path = dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && al16(l->d) && al16(hv) && al16(v) && ctx->gemm_path != 1;
   const int smem_mma = 8 * LRA_STAGES * (r == 32 ? LraTile<32>::BYTES : LraTile<16>::BYTES);
-  if (!(stages & LRA_ST_SWEEP1)) {
-    // sums of sweep 1 already in w.acc (all-reduced by the caller)
+  // sweep 1 on tcgen05 (lra_tc.cuh): bf16, rank 16 / 32 / 64, whole 128 * (64 / r)-row blocks; the remainder (< one block) goes through
+  // the kernels below on offset pointers and adds into the same accumulators
+  const bool tc_rank = r == 16 || r == 32 || r == 64;
+  const int tc_rows = tc_rank ? LT_KR * (64 / r) : 1;
+  const bool tc_path = dt == PSGD_BF16 && tc_rank && al16(l->U) && al16(l->V) && al16(l->d) && al16(hv) && al16(v) && ctx->gemm_path != 1 &&
+                       ctx->encode_tiled && !(ctx->debug_flags & 1024) && n >= tc_rows;
+  long long n_done = 0;     // rows already covered by the tcgen05 kernel
+  if ((stages & LRA_ST_SWEEP1) && tc_path) {
+    LtParams P;
+    memset(&P, 0, sizeof(P));
+    P.nblocks = n / tc_rows;
+    n_done = P.nblocks * tc_rows;
+    const long long prow = n_done / (64 / r);      // 128-byte lines
+    if (prow < (1LL << 31)) {
+      rc = make_tmap(ctx, &P.map_u, l->U, (int)prow, 64, 64, LT_KR); if (rc) return rc;
+      rc = make_tmap(ctx, &P.map_v, l->V, (int)prow, 64, 64, LT_KR); if (rc) return rc;
+      P.d = (const bf16*)l->d; P.h = (const bf16*)hv; P.v = (const bf16*)v; P.acc_out = w.acc;
+      const int grid = (int)(P.nblocks < (long long)ctx->num_sms ? P.nblocks : (long long)ctx->num_sms);
+      static PerDeviceOnce attr_t;
+      if (attr_t.need(ctx->device)) {
+        cudaFuncSetAttribute(k_lra_gram_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LtCfg<16>::SMEM_BYTES);
+        cudaFuncSetAttribute(k_lra_gram_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LtCfg<32>::SMEM_BYTES);
+        cudaFuncSetAttribute(k_lra_gram_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, LtCfg<64>::SMEM_BYTES);
+      }
+      if (r == 16) k_lra_gram_tc<16><<<grid, LT_THREADS, LtCfg<16>::SMEM_BYTES, st>>>(P);
+      else if (r == 32) k_lra_gram_tc<32><<<grid, LT_THREADS, LtCfg<32>::SMEM_BYTES, st>>>(P);
+      else k_lra_gram_tc<64><<<grid, LT_THREADS, LtCfg<64>::SMEM_BYTES, st>>>(P);
+      ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_gram_tc"); if (rc) return rc;
+    } else {
+      n_done = 0;
+    }
+  }
+  if ((stages & LRA_ST_SWEEP1) && n_done > 0 && n_done < n) {
+    // remainder rows: the mma.sync / CUDA-core sweep on the tail slice
+    const long long nr = n - n_done;
+    const size_t es = dtype_size(dt);
+    const char* Ut = (const char*)l->U + (size_t)n_done * r * es; const char* Vt = (const char*)l->V + (size_t)n_done * r * es;
+    const char* dt_ = (const char*)l->d + (size_t)n_done * es; const char* ht = (const char*)hv + (size_t)n_done * es;
+    const char* vt = (const char*)v + (size_t)n_done * es;
+    long long tiles = (nr + 63) / 64;
+    int grid1 = (int)(tiles < (long long)ctx->num_sms * 2 ? tiles : (long long)ctx->num_sms * 2);
+    LRA_DISPATCH(dt, RP, (k_lra_sweep1<T, R_><<<grid1, 256, 0, st>>>((const T*)Ut, (const T*)Vt, (const T*)dt_, (const T*)ht, (const T*)vt, nr, r, w.acc)));
+    ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep1(tail)"); if (rc) return rc;
+  }
+  if (!(stages & LRA_ST_SWEEP1) || n_done > 0) {
+    // sums of sweep 1 already in w.acc (all-reduced by the caller), or formed above
   } else if (mma_path) {
     long long chunks = (n + 15) / 16;
     int grid1 = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
