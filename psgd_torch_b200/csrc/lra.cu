@@ -681,6 +681,15 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   // tensor-core sweeps: bf16, rank exactly 16 or 32 (rows are whole 16-byte pieces); everything else takes the CUDA-core sweeps
   const bool mma_path = dt == PSGD_BF16 && (r == 16 || r == 32) && al16(l->U) && al16(l->V) && al16(l->d) && al16(hv) && al16(v) && ctx->gemm_path != 1;
   const int smem_mma = 8 * LRA_STAGES * (r == 32 ? LraTile<32>::BYTES : LraTile<16>::BYTES);
+  if (mma_path) {
+    static PerDeviceOnce attr_g;
+    if (attr_g.need(ctx->device)) {
+      cudaFuncSetAttribute(k_lra_gram_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
+      cudaFuncSetAttribute(k_lra_gram_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
+      cudaFuncSetAttribute(k_lra_rotate_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
+      cudaFuncSetAttribute(k_lra_rotate_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
+    }
+  }
   // sweep 1 on tcgen05 (lra_tc.cuh): bf16, rank 16 / 32 / 64, whole 128 * (64 / r)-row blocks; the remainder (< one block) goes through
   // the kernels below on offset pointers and adds into the same accumulators
   const bool tc_rank = r == 16 || r == 32 || r == 64;
@@ -730,13 +739,6 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   } else if (mma_path) {
     long long chunks = (n + 15) / 16;
     int grid1 = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
-    static PerDeviceOnce attr_g;
-    if (attr_g.need(ctx->device)) {
-      cudaFuncSetAttribute(k_lra_gram_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
-      cudaFuncSetAttribute(k_lra_gram_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
-      cudaFuncSetAttribute(k_lra_rotate_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<32>::BYTES);
-      cudaFuncSetAttribute(k_lra_rotate_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * LRA_STAGES * LraTile<16>::BYTES);
-    }
     if (r == 32) k_lra_gram_mma<32><<<grid1, 256, smem_mma, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.acc);
     else k_lra_gram_mma<16><<<grid1, 256, smem_mma, st>>>((const bf16*)l->U, (const bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.acc);
     ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_gram_mma"); if (rc) return rc;
@@ -762,17 +764,55 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
   long long rows_blocks = (n + 127) / 128;
   int grid2 = (int)(rows_blocks < (long long)ctx->num_sms * 8 ? rows_blocks : (long long)ctx->num_sms * 8);
   size_t smem2 = ((size_t)2 * RP * RP + LV_NVEC * RP) * 4;
-  if (mma_path) {
-    long long chunks = (n + 15) / 16;
-    int gridr = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
-    if (r == 32) k_lra_rotate_mma<32><<<gridr, 256, smem_mma, st>>>((bf16*)l->U, (bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.par, update_U, w.dd, scal);
-    else k_lra_rotate_mma<16><<<gridr, 256, smem_mma, st>>>((bf16*)l->U, (bf16*)l->V, (const bf16*)l->d, (const bf16*)hv, (const bf16*)v, n, w.par, update_U, w.dd, scal);
-  } else LRA_DISPATCH(dt, RP, {
-    static PerDeviceOnce attr;
-    if (attr.need(ctx->device)) cudaFuncSetAttribute(k_lra_sweep2<T, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    k_lra_sweep2<T, R_><<<grid2, 128, smem2, st>>>((T*)l->U, (T*)l->V, (const T*)l->d, (const T*)hv, (const T*)v, n, r, w.par, update_U, w.dd, scal);
-  });
+  // tcgen05 form (lra_tc.cuh) for the whole blocks, the kernels below for the remainder rows
+  long long n2_done = 0;
+  if (tc_path && !(ctx->debug_flags & 2048)) {
+    const long long blocks = n / tc_rows;
+    const long long prow = blocks * LT_KR;
+    if (prow < (1LL << 31)) {
+      LrParams P;
+      memset(&P, 0, sizeof(P));
+      rc = make_tmap(ctx, &P.map_u, l->U, (int)prow, 64, 64, LT_KR); if (rc) return rc;
+      rc = make_tmap(ctx, &P.map_v, l->V, (int)prow, 64, 64, LT_KR); if (rc) return rc;
+      P.U = (bf16*)l->U; P.V = (bf16*)l->V; P.d = (const bf16*)l->d; P.h = (const bf16*)hv; P.v = (const bf16*)v;
+      P.nblocks = blocks; P.par = w.par; P.update_U = update_U; P.dd_out = w.dd; P.scal_out = scal;
+      const int grid = (int)(blocks < (long long)ctx->num_sms ? blocks : (long long)ctx->num_sms);
+      static PerDeviceOnce attr_r;
+      if (attr_r.need(ctx->device)) {
+        cudaFuncSetAttribute(k_lra_rotate_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LrCfg<16>::SMEM_BYTES);
+        cudaFuncSetAttribute(k_lra_rotate_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LrCfg<32>::SMEM_BYTES);
+        cudaFuncSetAttribute(k_lra_rotate_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, LrCfg<64>::SMEM_BYTES);
+      }
+      if (r == 16) k_lra_rotate_tc<16><<<grid, LT_THREADS, LrCfg<16>::SMEM_BYTES, st>>>(P);
+      else if (r == 32) k_lra_rotate_tc<32><<<grid, LT_THREADS, LrCfg<32>::SMEM_BYTES, st>>>(P);
+      else k_lra_rotate_tc<64><<<grid, LT_THREADS, LrCfg<64>::SMEM_BYTES, st>>>(P);
+      ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_rotate_tc"); if (rc) return rc;
+      n2_done = blocks * tc_rows;
+    }
+  }
+  const long long nr2 = n - n2_done;
+  if (nr2 > 0) {
+    const size_t es = dtype_size(dt);
+    char* Ut = (char*)l->U + (size_t)n2_done * r * es; char* Vt = (char*)l->V + (size_t)n2_done * r * es;
+    const char* dtl = (const char*)l->d + (size_t)n2_done * es; const char* ht = (const char*)hv + (size_t)n2_done * es;
+    const char* vt = (const char*)v + (size_t)n2_done * es;
+    float* ddt = w.dd + n2_done;
+    if (mma_path) {
+      long long chunks = (nr2 + 15) / 16;
+      int gridr = (int)((chunks + 7) / 8 < (long long)ctx->num_sms ? (chunks + 7) / 8 : (long long)ctx->num_sms);
+      if (r == 32) k_lra_rotate_mma<32><<<gridr, 256, smem_mma, st>>>((bf16*)Ut, (bf16*)Vt, (const bf16*)dtl, (const bf16*)ht, (const bf16*)vt, nr2, w.par, update_U, ddt, scal);
+      else k_lra_rotate_mma<16><<<gridr, 256, smem_mma, st>>>((bf16*)Ut, (bf16*)Vt, (const bf16*)dtl, (const bf16*)ht, (const bf16*)vt, nr2, w.par, update_U, ddt, scal);
+    } else {
+      long long rb2 = (nr2 + 127) / 128;
+      int grid2t = (int)(rb2 < (long long)ctx->num_sms * 8 ? rb2 : (long long)ctx->num_sms * 8);
+      LRA_DISPATCH(dt, RP, {
+        static PerDeviceOnce attr;
+        if (attr.need(ctx->device)) cudaFuncSetAttribute(k_lra_sweep2<T, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        k_lra_sweep2<T, R_><<<grid2t, 128, smem2, st>>>((T*)Ut, (T*)Vt, (const T*)dtl, (const T*)ht, (const T*)vt, nr2, r, w.par, update_U, ddt, scal);
+      });
+    }
   ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_sweep2"); if (rc) return rc;
+  }
   }
   if (!(stages & LRA_ST_FINISH)) return PSGD_OK;
   k_lra_Ld<<<1, 32, 0, st>>>(scal, lr, betaL, l->Ld, dt);

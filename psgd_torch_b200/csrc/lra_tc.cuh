@@ -206,3 +206,255 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lra_gram_tc(const __grid_cons
 }
 
 }  // namespace psgd
+
+namespace psgd {
+
+// =====================================================================================================================================
+// sweep 2 of the LRA update on tcgen05: balancing rotation U' = (U - U Eu) / rho, V' = (V + V Ev) rho (psgd.py:1012-1015), the per-row terms
+// of the d update (psgd.py:1017-1029) and the rank-2 update of U or V (psgd.py:1036-1052), written back in place.
+//   packed lines as in sweep 1; per tile of 128 lines:  D_U[128 x 80] = Upk_tile (K-major, K = 64) x B_U,  D_V[128 x 80 / 96] = Vpk_tile x B_V
+//   B_U = [blockdiag(Eu, .., Eu) | hi / lo bf16 columns of the vectors whose row dot products are needed (Au c1, Au s2), one set per
+//   sub-row] -- K-major operands built once per CTA from the parameter block of k_lra_small.  The identity part of the rotation is
+//   applied exactly in fp32 by the epilogue (thread = line: original line from the shared-memory tile, correction and dots from TMEM).
+//   TMEM holds two accumulator sets so that the products of tile t + 1 overlap the epilogue of tile t.
+//   warp 0: producer, warp 1: MMA issuer, warps 2-5: epilogue (16-byte stores of whole 128-byte lines).
+// =====================================================================================================================================
+constexpr int LR_STAGES = 4;
+
+template <int RP> struct LrCfg {
+  static constexpr int PACK = 64 / RP;
+  static constexpr int ROWS = LT_KR * PACK;
+  static constexpr int VEC_BYTES = ROWS * 2;
+  static constexpr int NU = 80;                           // 64 rotation columns + 4 PACK dot columns, padded to a multiple of 16
+  static constexpr int NV = PACK == 4 ? 96 : 80;          // 64 + 8 PACK
+  static constexpr int BU_BYTES = NU * 128, BV_BYTES = NV * 128;
+  static constexpr int SMEM_BYTES = LR_STAGES * (2 * LT_TILE + 3 * VEC_BYTES) + BU_BYTES + BV_BYTES + 1024 + 512;
+};
+
+struct alignas(64) LrParams {
+  CUtensorMap map_u;
+  CUtensorMap map_v;
+  bf16* U; bf16* V;
+  const bf16* d; const bf16* h; const bf16* v;
+  long long nblocks;
+  const float* par;
+  int update_U;
+  float* dd_out;
+  float* scal_out;
+};
+
+template <int RP>
+__global__ void __launch_bounds__(LT_THREADS, 1) k_lra_rotate_tc(const __grid_constant__ LrParams P) {
+  using Cfg = LrCfg<RP>;
+  constexpr int PACK = Cfg::PACK;
+  extern __shared__ uint8_t lr_smem_raw[];
+  const uint32_t smem_base = (smem_u32(lr_smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = lr_smem_raw + (smem_base - smem_u32(lr_smem_raw));
+  // layout: [U tile | V tile] x S, B_U, B_V (all 1024-aligned), vectors [d | h | v] x S, barriers
+  const uint32_t bu_base = smem_base + LR_STAGES * 2 * LT_TILE;
+  const uint32_t bv_base = bu_base + Cfg::BU_BYTES;
+  const uint32_t vec_base = bv_base + Cfg::BV_BYTES;
+  const uint32_t bar_base = vec_base + LR_STAGES * 3 * Cfg::VEC_BYTES;
+  uint8_t* bu_gen = smem_gen + LR_STAGES * 2 * LT_TILE;
+  uint8_t* bv_gen = bu_gen + Cfg::BU_BYTES;
+  uint8_t* vec_gen = bv_gen + Cfg::BV_BYTES;
+  auto full_bar = [&](int s_) { return bar_base + 8u * s_; };
+  auto empty_bar = [&](int s_) { return bar_base + 8u * (LR_STAGES + s_); };
+  auto tfull_bar = [&](int a_) { return bar_base + 8u * (2 * LR_STAGES + a_); };
+  auto tempty_bar = [&](int a_) { return bar_base + 8u * (2 * LR_STAGES + 2 + a_); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * LR_STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(vec_gen + LR_STAGES * 3 * Cfg::VEC_BYTES + 8 * (2 * LR_STAGES + 4));
+  __shared__ float wvec[2][RP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* pvec = P.par + lra_par_vec_off(RP);
+  const float* pscal = P.par + lra_par_scal_off(RP);
+  const bf16* EuT = reinterpret_cast<const bf16*>(P.par + lra_par_et_off(RP));
+  const bf16* EvT = EuT + RP * RP;
+  const int update_U = P.update_U;
+
+  if (tid == 0) {
+    for (int i = 0; i < LR_STAGES; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 5); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    fence_barrier_init();
+    prefetch_tmap(&P.map_u); prefetch_tmap(&P.map_v);
+  }
+  for (int e = tid; e < RP; e += LT_THREADS) {
+    wvec[0][e] = update_U ? pvec[LV_WA * RP + e] : pvec[LV_ATU * RP + e];
+    wvec[1][e] = update_U ? pvec[LV_WB * RP + e] : pvec[LV_BTU * RP + e];
+  }
+  // K-major operand tiles B_U / B_V: row n (output column), 64 k elements, 128-byte swizzle: element (n, k) at n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2
+  auto b_put = [&](uint8_t* base, int n, int k, float val) {
+    *reinterpret_cast<bf16*>(base + n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(val);
+  };
+  for (int e = tid; e < (Cfg::NU + Cfg::NV) * 64; e += LT_THREADS) {
+    const bool isv = e >= Cfg::NU * 64;
+    const int ee = isv ? e - Cfg::NU * 64 : e;
+    const int n = ee >> 6, k = ee & 63;
+    const int kc = k / RP, kk = k % RP;            // sub-row and column of the contraction index
+    float val = 0.f;
+    if (n < 64) {
+      const int nc = n / RP, nn = n % RP;
+      if (nc == kc) val = __bfloat162float((isv ? EvT : EuT)[nn * RP + kk]);
+    } else {
+      const int idx = n - 64;
+      const int nvec = isv ? 4 : 2;
+      const int c = idx / (2 * nvec), vi = (idx / 2) % nvec, part = idx & 1;
+      if (c < PACK && c == kc) {
+        const int id = isv ? (vi == 0 ? LV_AVC2 : (vi == 1 ? LV_AVS1 : (vi == 2 ? LV_AVATU : LV_AVBTU))) : (vi == 0 ? LV_AUC1 : LV_AUS2);
+        const float x = (isv && vi >= 2 && update_U) ? 0.f : pvec[id * RP + kk];
+        const float hi = lt_rbf(x);
+        val = part ? x - hi : hi;
+      }
+    }
+    b_put(isv ? bv_gen : bu_gen, n, k, val);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  lt_fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const long long nblk = P.nblocks;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      mbar_wait(empty_bar(stage), phase ^ 1u, nullptr);
+      if (elect_one()) {
+        const uint32_t su = smem_base + stage * 2 * LT_TILE, fb = full_bar(stage);
+        const uint32_t sv = vec_base + stage * 3 * Cfg::VEC_BYTES;
+        const long long r0 = blk * Cfg::ROWS;
+        mbar_arrive_expect_tx(fb, 2 * LT_TILE + 3 * Cfg::VEC_BYTES);
+        tma_load_2d(&P.map_u, fb, su, 0, (int)(blk * LT_KR));
+        tma_load_2d(&P.map_v, fb, su + LT_TILE, 0, (int)(blk * LT_KR));
+        lt_bulk_g2s(sv, P.d + r0, Cfg::VEC_BYTES, fb);
+        lt_bulk_g2s(sv + Cfg::VEC_BYTES, P.h + r0, Cfg::VEC_BYTES, fb);
+        lt_bulk_g2s(sv + 2 * Cfg::VEC_BYTES, P.v + r0, Cfg::VEC_BYTES, fb);
+      }
+      __syncwarp();
+      if (++stage == LR_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: both operands K-major, M = 128 lines, K = 64 =====================
+    const uint32_t idesc_u = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(Cfg::NU >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const uint32_t idesc_v = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(Cfg::NV >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    const uint64_t adesc0 = make_smem_desc(smem_base, 0u, 1024u);
+    const uint64_t budesc = make_smem_desc(bu_base, 0u, 1024u), bvdesc = make_smem_desc(bv_base, 0u, 1024u);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, nullptr);
+      mbar_wait(full_bar(stage), phase, nullptr);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((stage * 2 * LT_TILE) >> 4);
+        const uint32_t du = tmem_base + uint32_t(acc * 256), dv = du + 96u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16(du, adesc0 + so + (uint64_t)((k * 32) >> 4), budesc + (uint64_t)((k * 32) >> 4), idesc_u, k != 0 ? 1u : 0u);
+          umma_bf16(dv, adesc0 + so + (uint64_t)((LT_TILE + k * 32) >> 4), bvdesc + (uint64_t)((k * 32) >> 4), idesc_v, k != 0 ? 1u : 0u);
+        }
+        umma_commit(tfull_bar(acc));
+        umma_commit(empty_bar(stage));
+      }
+      __syncwarp();
+      if (++stage == LR_STAGES) { stage = 0; phase ^= 1u; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 = lines of the tile =====================
+    const int quarter = warp & 3;
+    const int ln = quarter * 32 + lane;
+    const float step = pscal[LS_STEP], inv_rho = pscal[LS_INV_RHO], rho = pscal[LS_RHO];
+    float mx1 = 0.f, mx2 = 0.f;
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      mbar_wait(full_bar(stage), phase, nullptr);                // the tile and the vectors (read below through the generic proxy)
+      mbar_wait_relaxed(tfull_bar(acc), acc_phase, nullptr);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * 256);
+      const uint8_t* tile_u = smem_gen + stage * 2 * LT_TILE + ln * 128;
+      const uint8_t* tile_v = tile_u + LT_TILE;
+      const bf16* dvp = reinterpret_cast<const bf16*>(vec_gen + stage * 3 * Cfg::VEC_BYTES);
+      const bf16* hvp = dvp + Cfg::ROWS;
+      const bf16* vvp = hvp + Cfg::ROWS;
+      // dot columns
+      uint32_t du_raw[32], dv_raw[32];
+      tmem_ld_32x32(trow + 64u, du_raw);
+      tmem_ld_32x32(trow + 96u + 64u, dv_raw);
+      tmem_ld_wait();
+      float ca[PACK], cb[PACK];
+      const long long row0 = blk * Cfg::ROWS + (long long)PACK * ln;
+#pragma unroll
+      for (int c = 0; c < PACK; ++c) {
+        const float duc1 = __uint_as_float(du_raw[(c * 2 + 0) * 2]) + __uint_as_float(du_raw[(c * 2 + 0) * 2 + 1]);
+        const float dus2 = __uint_as_float(du_raw[(c * 2 + 1) * 2]) + __uint_as_float(du_raw[(c * 2 + 1) * 2 + 1]);
+        const float dvc2 = __uint_as_float(dv_raw[(c * 4 + 0) * 2]) + __uint_as_float(dv_raw[(c * 4 + 0) * 2 + 1]);
+        const float dvs1 = __uint_as_float(dv_raw[(c * 4 + 1) * 2]) + __uint_as_float(dv_raw[(c * 4 + 1) * 2 + 1]);
+        const float dva = __uint_as_float(dv_raw[(c * 4 + 2) * 2]) + __uint_as_float(dv_raw[(c * 4 + 2) * 2 + 1]);
+        const float dvb = __uint_as_float(dv_raw[(c * 4 + 3) * 2]) + __uint_as_float(dv_raw[(c * 4 + 3) * 2 + 1]);
+        const float dd = __bfloat162float(dvp[PACK * ln + c]), hh = __bfloat162float(hvp[PACK * ln + c]), vv = __bfloat162float(vvp[PACK * ln + c]);
+        const float x1 = lt_rbf(dd * hh), x2 = lt_rbf(vv / dd);
+        const float a = x1 + duc1;                    // Qh_i          psgd.py:1017
+        const float Ph = dd * (a + dvc2);             // Ph_i          psgd.py:1018
+        const float b = x2 - dvs1;                    // invQtv_i      psgd.py:1024
+        const float invPv = (b - dus2) / dd;          // invPv_i       psgd.py:1025-1026
+        const float Phh = Ph * hh, vinv = vv * invPv;
+        mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
+        P.dd_out[row0 + c] = Phh - vinv;
+        ca[c] = update_U ? step * a : step * (a + dva);
+        cb[c] = update_U ? step * b : step * (b + dvb);
+      }
+      // rotation (identity part exact, correction from the MMA) + rank-2 update, 32 columns at a time; whole 16-byte pieces of the line
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {      // 0: U, 1: V
+        const uint8_t* tl = side ? tile_v : tile_u;
+        bf16* gl = (side ? P.V : P.U) + (size_t)(blk * LT_KR + ln) * 64;
+        const bool upd = side ? !update_U : (update_U != 0);
+        const float scale = side ? rho : inv_rho;
+        const float sgn = side ? 1.f : -1.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t raw[32];
+          tmem_ld_32x32(trow + (side ? 96u : 0u) + uint32_t(half * 32), raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {            // 16-byte piece j = 4 half + q of the line: columns 8 j .. 8 j + 7
+            const int j = half * 4 + q;
+            const uint4 ow = *reinterpret_cast<const uint4*>(tl + ((j ^ (ln & 7)) << 4));
+            const uint32_t w[4] = {ow.x, ow.y, ow.z, ow.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16(w[e]);
+              const int col = 8 * j + 2 * e;        // column of the line; sub-row c = col / RP, rank index nn = col % RP
+              const int c = col / RP, nn = col % RP;
+              float y0 = (x.x + sgn * __uint_as_float(raw[8 * q + 2 * e])) * scale;
+              float y1 = (x.y + sgn * __uint_as_float(raw[8 * q + 2 * e + 1])) * scale;
+              if (upd) {
+                y0 -= ca[c] * wvec[0][nn] - cb[c] * wvec[1][nn];
+                y1 -= ca[c] * wvec[0][nn + 1] - cb[c] * wvec[1][nn + 1];
+              }
+              o[e] = pack_bf16(y0, y1);
+            }
+            *reinterpret_cast<uint4*>(gl + 8 * j) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(tempty_bar(acc)); mbar_arrive(empty_bar(stage)); }
+      if (++stage == LR_STAGES) { stage = 0; phase ^= 1u; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    mx1 = warp_max(mx1); mx2 = warp_max(mx2);
+    if (lane == 0) { atomic_max_nonneg(&P.scal_out[LS_MAX_PHH], mx1); atomic_max_nonneg(&P.scal_out[LS_MAX_VINV], mx2); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace psgd
