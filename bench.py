@@ -680,6 +680,8 @@ def run_kwns4(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
+        if args.comm_sms > 0:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.comm_sms))      # one CTA per channel: the broadcasts fit the SMs left free
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -697,7 +699,7 @@ def run_kwns4(args):
         p.grad = (0.01 * torch.randn(*shp, device=dev, generator=gen)).bfloat16()
         params.append(p)
     opt = KWNS4(params, lr_params=2e-4, lr_preconditioner=0.1, preconditioner_dtype=torch.bfloat16, shard_preconditioners=world > 1,
-                batch_same_shape=not args.no_batching)
+                batch_same_shape=not args.no_batching, comm_sms=args.comm_sms if world > 1 else 0)
     h = _lib.handle_for(dev)
     lib = _lib.load_library()
     for _ in range(args.warmup):
@@ -746,7 +748,7 @@ def run_kwns4(args):
                                        "weight decay, clipping, parameter update; "
                                        + ("single GPU" if world == 1 else f"preconditioners sharded per parameter over {world} GPUs "
                                           "(owner computes, NCCL broadcast of the updated parameter inside the timed region)"),
-                           "noise": args.noise, "batch_same_shape": not args.no_batching,
+                           "noise": args.noise, "batch_same_shape": not args.no_batching, "comm_sms": args.comm_sms if world > 1 else 0,
                            "nccl_broadcast_bytes_per_step": bcast},
                 "clocks": clocks,
                 "e2e": {"value": n_units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(tot[1].item()),
@@ -790,6 +792,7 @@ def main():
     ap.add_argument("--mode", default="functional", choices=["functional", "kwns4"],
                     help="functional (default): update + apply per unit through the psgd.* functions (BASELINE configs[2]); kwns4: the same "
                          "set through KWNS4.step(), preconditioners sharded per parameter at N > 1 (BASELINE configs[3])")
+    ap.add_argument("--comm-sms", type=int, default=8, help="--mode kwns4 at N > 1: SMs left free for the NCCL broadcast kernels (0: none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--noise", default="philox", choices=["philox", "torch"],
                     help="philox: damping noise and norm-bound probes drawn inside the engine's kernels (performance mode); torch: drawn by "

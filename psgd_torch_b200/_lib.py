@@ -52,6 +52,7 @@ SYMBOLS = {
     "psgd_destroy": (None, [_vp]),
     "psgd_set_gemm_path": (_i, [_vp, _i]),
     "psgd_launch_count": (_i64, [_vp]),
+    "psgd_set_sm_limit": (_i, [_vp, _i]),
     "psgd_set_fp32_tensor_cores": (_i, [_vp, _i]),
     "psgd_kron_workspace_bytes": (_sz, [_vp, C.POINTER(KronT)]),
     "psgd_kron_whiten_q0p5eq1p5_update": (_i, [_vp, C.POINTER(KronT), _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),
@@ -158,6 +159,8 @@ def handle_for(device):
                 rc = lib.psgd_create(C.byref(out), idx)
                 check(None, rc, f"psgd_create(device={idx})")
                 h = out
+                if idx in _sm_limit:
+                    check(h, lib.psgd_set_sm_limit(h, _sm_limit[idx]), "psgd_set_sm_limit")
                 _handles[key] = h
     return h
 
@@ -202,6 +205,21 @@ def set_fp32_tensor_cores(on, device=None):
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     h = handle_for(dev)
     check(h, load_library().psgd_set_fp32_tensor_cores(h, int(bool(on))), "psgd_set_fp32_tensor_cores")
+
+
+_sm_limit = {}
+
+
+def set_sm_limit(sms, device=None):
+    """Leave SMs free for concurrent kernels of other streams (NCCL): the engine's persistent kernels size their grids for `sms` SMs
+    (<= 0: all).  Applies to every context of the device, present and future (include/psgd_b200.h: psgd_set_sm_limit)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = _dev_index(dev)
+    _sm_limit[idx] = int(sms)
+    lib = load_library()
+    for (i, _), h in _handles.items():
+        if i == idx:
+            check(h, lib.psgd_set_sm_limit(h, int(sms)), "psgd_set_sm_limit")
 
 
 def launch_count(device=None):

@@ -688,6 +688,7 @@ int psgd_create(psgd_handle_t* out, int device) {
   memset(ctx, 0, sizeof(Ctx));
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  ctx->num_sms_hw = prop.multiProcessorCount;
   ctx->gemm_path = 0;
   ctx->mn_lbo = 8192;
   ctx->mn_sbo = 1024;
@@ -739,6 +740,13 @@ void psgd_destroy(psgd_handle_t h) {
 int psgd_set_gemm_path(psgd_handle_t h, int p) {
   if (!h || p < 0 || p > 2) return PSGD_ERR_INVALID_ARG;
   reinterpret_cast<Ctx*>(h)->gemm_path = p;
+  return PSGD_OK;
+}
+
+int psgd_set_sm_limit(psgd_handle_t h, int sms) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(h);
+  if (!ctx) return PSGD_ERR_INVALID_ARG;
+  ctx->num_sms = (sms <= 0 || sms > ctx->num_sms_hw) ? ctx->num_sms_hw : (sms < 2 ? 2 : sms & ~1);   // even: the 2-CTA GEMM runs CTA pairs
   return PSGD_OK;
 }
 

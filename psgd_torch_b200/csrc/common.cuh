@@ -166,7 +166,8 @@ __device__ __forceinline__ float block_max(float v, float* smem32) {
 // ---------------------------------------------------------------------------------------------
 struct Ctx {
   int device;
-  int num_sms;
+  int num_sms;         // SMs the persistent kernels size their grids for (psgd_set_sm_limit; default: all)
+  int num_sms_hw;
   int gemm_path;       // 0 auto, 1 simt, 2 tc
   int mn_lbo, mn_sbo;  // MN-major UMMA descriptor byte offsets
   int force_bn;        // debug: 0 = automatic tile width, else 128 / 256

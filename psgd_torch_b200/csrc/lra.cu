@@ -783,9 +783,9 @@ static int lra_update_impl(Ctx* ctx, const psgd_lra_t* l, const void* v, const v
         cudaFuncSetAttribute(k_lra_rotate_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LrCfg<32>::SMEM_BYTES);
         cudaFuncSetAttribute(k_lra_rotate_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, LrCfg<64>::SMEM_BYTES);
       }
-      if (r == 16) k_lra_rotate_tc<16><<<grid, LT_THREADS, LrCfg<16>::SMEM_BYTES, st>>>(P);
-      else if (r == 32) k_lra_rotate_tc<32><<<grid, LT_THREADS, LrCfg<32>::SMEM_BYTES, st>>>(P);
-      else k_lra_rotate_tc<64><<<grid, LT_THREADS, LrCfg<64>::SMEM_BYTES, st>>>(P);
+      if (r == 16) k_lra_rotate_tc<16><<<grid, LR_THREADS, LrCfg<16>::SMEM_BYTES, st>>>(P);
+      else if (r == 32) k_lra_rotate_tc<32><<<grid, LR_THREADS, LrCfg<32>::SMEM_BYTES, st>>>(P);
+      else k_lra_rotate_tc<64><<<grid, LR_THREADS, LrCfg<64>::SMEM_BYTES, st>>>(P);
       ctx->launches++; rc = check_cuda(ctx, cudaGetLastError(), "k_lra_rotate_tc"); if (rc) return rc;
       n2_done = blocks * tc_rows;
     }

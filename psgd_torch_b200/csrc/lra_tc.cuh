@@ -45,6 +45,12 @@ struct alignas(64) LtParams {
 __device__ __forceinline__ void lt_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void lt_tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void lt_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void lt_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float lt_rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ void lt_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -217,9 +223,14 @@ namespace psgd {
 //   sub-row] -- K-major operands built once per CTA from the parameter block of k_lra_small.  The identity part of the rotation is
 //   applied exactly in fp32 by the epilogue (thread = line: original line from the shared-memory tile, correction and dots from TMEM).
 //   TMEM holds two accumulator sets so that the products of tile t + 1 overlap the epilogue of tile t.
-//   warp 0: producer, warp 1: MMA issuer, warps 2-5: epilogue (16-byte stores of whole 128-byte lines).
+//   warp 0: producer, warp 1: MMA issuer, warps 2-9 / 10-17: two epilogue groups that take alternate tiles (group g owns accumulator set
+//   g); inside a group four warps (one per TMEM lane quarter) do the U side and four the V side.  The epilogue is ~6000 warp
+//   instructions per tile (ncu: issue 29 % active with one group, 5300 cycles per tile against 2800 at the HBM rate), so it needs
+//   warps, not bandwidth.  The new lines are written back INTO the shared-memory tile (each thread owns its line) and leave through one
+//   TMA store per factor and tile.
 // =====================================================================================================================================
-constexpr int LR_STAGES = 4;
+constexpr int LR_STAGES = 5;
+constexpr int LR_THREADS = 576;      // warp 0 producer, warp 1 MMA, then two epilogue groups of 8 warps (4 for the U side, 4 for the V side)
 
 template <int RP> struct LrCfg {
   static constexpr int PACK = 64 / RP;
@@ -244,7 +255,7 @@ struct alignas(64) LrParams {
 };
 
 template <int RP>
-__global__ void __launch_bounds__(LT_THREADS, 1) k_lra_rotate_tc(const __grid_constant__ LrParams P) {
+__global__ void __launch_bounds__(LR_THREADS, 1) k_lra_rotate_tc(const __grid_constant__ LrParams P) {
   using Cfg = LrCfg<RP>;
   constexpr int PACK = Cfg::PACK;
   extern __shared__ uint8_t lr_smem_raw[];
@@ -273,12 +284,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lra_rotate_tc(const __grid_co
   const int update_U = P.update_U;
 
   if (tid == 0) {
-    for (int i = 0; i < LR_STAGES; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 5); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    for (int i = 0; i < LR_STAGES; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 2); }   // MMA commit + the storing thread
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }     // 8 warps of the group that owns set i
     fence_barrier_init();
     prefetch_tmap(&P.map_u); prefetch_tmap(&P.map_v);
   }
-  for (int e = tid; e < RP; e += LT_THREADS) {
+  for (int e = tid; e < RP; e += LR_THREADS) {
     wvec[0][e] = update_U ? pvec[LV_WA * RP + e] : pvec[LV_ATU * RP + e];
     wvec[1][e] = update_U ? pvec[LV_WB * RP + e] : pvec[LV_BTU * RP + e];
   }
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lra_rotate_tc(const __grid_co
   auto b_put = [&](uint8_t* base, int n, int k, float val) {
     *reinterpret_cast<bf16*>(base + n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(val);
   };
-  for (int e = tid; e < (Cfg::NU + Cfg::NV) * 64; e += LT_THREADS) {
+  for (int e = tid; e < (Cfg::NU + Cfg::NV) * 64; e += LR_THREADS) {
     const bool isv = e >= Cfg::NU * 64;
     const int ee = isv ? e - Cfg::NU * 64 : e;
     const int n = ee >> 6, k = ee & 63;
@@ -365,18 +376,24 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lra_rotate_tc(const __grid_co
   } else {
     // ===================== epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 = lines of the tile =====================
     const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 3;                 // epilogue group: tiles it = grp, grp + 2, ... of this CTA; accumulator set = grp
+    const int side = ((warp - 2) >> 2) & 1;          // 0: U, 1: V
     const int ln = quarter * 32 + lane;
     const float step = pscal[LS_STEP], inv_rho = pscal[LS_INV_RHO], rho = pscal[LS_RHO];
     float mx1 = 0.f, mx2 = 0.f;
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int acc = grp;
+    int prev_stage = -1;                                         // stage whose TMA stores are still reading shared memory (storing thread)
+    long long it = grp;
+    for (long long blk = blockIdx.x + (long long)grp * gridDim.x; blk < nblk; blk += 2LL * gridDim.x, it += 2) {
+      const int stage = (int)(it % LR_STAGES);
+      const uint32_t phase = (uint32_t)((it / LR_STAGES) & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       mbar_wait(full_bar(stage), phase, nullptr);                // the tile and the vectors (read below through the generic proxy)
       mbar_wait_relaxed(tfull_bar(acc), acc_phase, nullptr);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * 256);
-      const uint8_t* tile_u = smem_gen + stage * 2 * LT_TILE + ln * 128;
-      const uint8_t* tile_v = tile_u + LT_TILE;
+      uint8_t* tile_u = smem_gen + stage * 2 * LT_TILE + ln * 128;
+      uint8_t* tile_v = tile_u + LT_TILE;
       const bf16* dvp = reinterpret_cast<const bf16*>(vec_gen + stage * 3 * Cfg::VEC_BYTES);
       const bf16* hvp = dvp + Cfg::ROWS;
       const bf16* vvp = hvp + Cfg::ROWS;
@@ -402,16 +419,16 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lra_rotate_tc(const __grid_co
         const float b = x2 - dvs1;                    // invQtv_i      psgd.py:1024
         const float invPv = (b - dus2) / dd;          // invPv_i       psgd.py:1025-1026
         const float Phh = Ph * hh, vinv = vv * invPv;
-        mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
-        P.dd_out[row0 + c] = Phh - vinv;
+        if (side == 0) {
+          mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
+          P.dd_out[row0 + c] = Phh - vinv;
+        }
         ca[c] = update_U ? step * a : step * (a + dva);
         cb[c] = update_U ? step * b : step * (b + dvb);
       }
       // rotation (identity part exact, correction from the MMA) + rank-2 update, 32 columns at a time; whole 16-byte pieces of the line
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {      // 0: U, 1: V
-        const uint8_t* tl = side ? tile_v : tile_u;
-        bf16* gl = (side ? P.V : P.U) + (size_t)(blk * LT_KR + ln) * 64;
+      {
+        uint8_t* tl = side ? tile_v : tile_u;
         const bool upd = side ? !update_U : (update_U != 0);
         const float scale = side ? rho : inv_rho;
         const float sgn = side ? 1.f : -1.f;
@@ -439,18 +456,28 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lra_rotate_tc(const __grid_co
               }
               o[e] = pack_bf16(y0, y1);
             }
-            *reinterpret_cast<uint4*>(gl + 8 * j) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(tl + ((j ^ (ln & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);   // in place: this thread owns the line
           }
         }
       }
       tc_fence_before();
+      lt_fence_async_smem();                                      // the rewritten lines -> TMA store (async proxy)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(tempty_bar(acc)); mbar_arrive(empty_bar(stage)); }
-      if (++stage == LR_STAGES) { stage = 0; phase ^= 1u; }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // all eight warps of the group are done with the tile and its vectors
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (tid == 64 + grp * 256) {
+        const uint32_t su = smem_base + stage * 2 * LT_TILE;
+        lt_tma_store_2d(&P.map_u, su, 0, (int)(blk * LT_KR));
+        lt_tma_store_2d(&P.map_v, su + LT_TILE, 0, (int)(blk * LT_KR));
+        lt_bulk_commit();
+        if (prev_stage >= 0) { lt_bulk_wait_read<1>(); mbar_arrive(empty_bar(prev_stage)); }   // the previous tile's stores have left shared memory
+        prev_stage = stage;
+      }
     }
+    if (tid == 64 + grp * 256 && prev_stage >= 0) { lt_bulk_wait_read<0>(); mbar_arrive(empty_bar(prev_stage)); }
     mx1 = warp_max(mx1); mx2 = warp_max(mx2);
-    if (lane == 0) { atomic_max_nonneg(&P.scal_out[LS_MAX_PHH], mx1); atomic_max_nonneg(&P.scal_out[LS_MAX_VINV], mx2); }
+    if (lane == 0 && side == 0) { atomic_max_nonneg(&P.scal_out[LS_MAX_PHH], mx1); atomic_max_nonneg(&P.scal_out[LS_MAX_VINV], mx2); }
   }
   tc_fence_before();
   __syncthreads();

@@ -48,6 +48,7 @@ class KWNS4(torch.optim.Optimizer):
             resync_every=1000_000,
             shard_preconditioners=False,
             batch_same_shape=False,
+            comm_sms=0,
     ):
         # ddp.py:45-62, verbatim
         assert whiten_grad in (False, True)
@@ -99,6 +100,9 @@ class KWNS4(torch.optim.Optimizer):
         # default; a transformer's repeated layers are where it pays (64 k/v projections, 65 norm vectors, pairs of MLP matrices).
         self.batch_same_shape = bool(batch_same_shape)
         self.batch_numel_cap = 128 * 1024 * 1024     # elements of gradient per batched call (workspace grows with it)
+        # sharded mode: SMs left free for the NCCL broadcast kernels that run beside the engine's persistent kernels (_lib.set_sm_limit)
+        self.comm_sms = int(comm_sms)
+        self._comm_sms_applied = False
         self._owner = None
         self.dQ = "Q0.5EQ1.5"  # ddp.py:84-86
         self.update_precond = psgd.update_precond_kron_whiten_q0p5eq1p5
@@ -399,6 +403,10 @@ class KWNS4(torch.optim.Optimizer):
         sharded = self._sharding_active()
         if sharded and self._owner is None:
             self._assign_owners()
+        if sharded and self.comm_sms > 0 and not self._comm_sms_applied:
+            total = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            _lib.set_sm_limit(total - self.comm_sms)
+            self._comm_sms_applied = True
         my_rank = torch.distributed.get_rank() if sharded else 0
         pending = []
         for group in self.param_groups:
