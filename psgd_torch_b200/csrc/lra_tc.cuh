@@ -229,17 +229,24 @@ namespace psgd {
 //   warps, not bandwidth.  The new lines are written back INTO the shared-memory tile (each thread owns its line) and leave through one
 //   TMA store per factor and tile.
 // =====================================================================================================================================
-constexpr int LR_STAGES = 5;
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100a): the rotate epilogue is instruction-bound, these halve its FMA count
+typedef unsigned long long lt_f2;
+__device__ __forceinline__ lt_f2 lt_pack2(float a, float b) { lt_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float2 lt_unpack2(lt_f2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ lt_f2 lt_fma2(lt_f2 a, lt_f2 b, lt_f2 c) { lt_f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ lt_f2 lt_mul2(lt_f2 a, lt_f2 b) { lt_f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 constexpr int LR_THREADS = 576;      // warp 0 producer, warp 1 MMA, then two epilogue groups of 8 warps (4 for the U side, 4 for the V side)
 
 template <int RP> struct LrCfg {
   static constexpr int PACK = 64 / RP;
   static constexpr int ROWS = LT_KR * PACK;
   static constexpr int VEC_BYTES = ROWS * 2;
+  static constexpr int STAGES = RP == 16 ? 5 : 6;         // a stage lives for load latency + up to two tile times of epilogue + the store drain
   static constexpr int NU = 80;                           // 64 rotation columns + 4 PACK dot columns, padded to a multiple of 16
   static constexpr int NV = PACK == 4 ? 96 : 80;          // 64 + 8 PACK
   static constexpr int BU_BYTES = NU * 128, BV_BYTES = NV * 128;
-  static constexpr int SMEM_BYTES = LR_STAGES * (2 * LT_TILE + 3 * VEC_BYTES) + BU_BYTES + BV_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * (2 * LT_TILE + 3 * VEC_BYTES) + BU_BYTES + BV_BYTES + 1024 + 512;
 };
 
 struct alignas(64) LrParams {
@@ -258,6 +265,7 @@ template <int RP>
 __global__ void __launch_bounds__(LR_THREADS, 1) k_lra_rotate_tc(const __grid_constant__ LrParams P) {
   using Cfg = LrCfg<RP>;
   constexpr int PACK = Cfg::PACK;
+  constexpr int LR_STAGES = Cfg::STAGES;
   extern __shared__ uint8_t lr_smem_raw[];
   const uint32_t smem_base = (smem_u32(lr_smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = lr_smem_raw + (smem_base - smem_u32(lr_smem_raw));
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) k_lra_rotate_tc(const __grid_co
   auto tempty_bar = [&](int a_) { return bar_base + 8u * (2 * LR_STAGES + 2 + a_); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * LR_STAGES + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(vec_gen + LR_STAGES * 3 * Cfg::VEC_BYTES + 8 * (2 * LR_STAGES + 4));
-  __shared__ float wvec[2][RP];
+  __shared__ __align__(16) float wvec[2][RP];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* pvec = P.par + lra_par_vec_off(RP);
   const float* pscal = P.par + lra_par_scal_off(RP);
@@ -397,41 +405,45 @@ __global__ void __launch_bounds__(LR_THREADS, 1) k_lra_rotate_tc(const __grid_co
       const bf16* dvp = reinterpret_cast<const bf16*>(vec_gen + stage * 3 * Cfg::VEC_BYTES);
       const bf16* hvp = dvp + Cfg::ROWS;
       const bf16* vvp = hvp + Cfg::ROWS;
-      // dot columns
-      uint32_t du_raw[32], dv_raw[32];
-      tmem_ld_32x32(trow + 64u, du_raw);
-      tmem_ld_32x32(trow + 96u + 64u, dv_raw);
-      tmem_ld_wait();
-      float ca[PACK], cb[PACK];
-      const long long row0 = blk * Cfg::ROWS + (long long)PACK * ln;
+      const bool upd = side ? !update_U : (update_U != 0);        // does this side get the rank-2 update?
+      lt_f2 nca2[PACK], cb2[PACK];
+      if (side == 0 || upd) {                                      // dot columns: the U side writes dd_out, the updated side needs ca / cb
+        uint32_t du_raw[32], dv_raw[32];
+        tmem_ld_32x32(trow + 64u, du_raw);
+        tmem_ld_32x32(trow + 96u + 64u, dv_raw);
+        tmem_ld_wait();
+        const long long row0 = blk * Cfg::ROWS + (long long)PACK * ln;
 #pragma unroll
-      for (int c = 0; c < PACK; ++c) {
-        const float duc1 = __uint_as_float(du_raw[(c * 2 + 0) * 2]) + __uint_as_float(du_raw[(c * 2 + 0) * 2 + 1]);
-        const float dus2 = __uint_as_float(du_raw[(c * 2 + 1) * 2]) + __uint_as_float(du_raw[(c * 2 + 1) * 2 + 1]);
-        const float dvc2 = __uint_as_float(dv_raw[(c * 4 + 0) * 2]) + __uint_as_float(dv_raw[(c * 4 + 0) * 2 + 1]);
-        const float dvs1 = __uint_as_float(dv_raw[(c * 4 + 1) * 2]) + __uint_as_float(dv_raw[(c * 4 + 1) * 2 + 1]);
-        const float dva = __uint_as_float(dv_raw[(c * 4 + 2) * 2]) + __uint_as_float(dv_raw[(c * 4 + 2) * 2 + 1]);
-        const float dvb = __uint_as_float(dv_raw[(c * 4 + 3) * 2]) + __uint_as_float(dv_raw[(c * 4 + 3) * 2 + 1]);
-        const float dd = __bfloat162float(dvp[PACK * ln + c]), hh = __bfloat162float(hvp[PACK * ln + c]), vv = __bfloat162float(vvp[PACK * ln + c]);
-        const float x1 = lt_rbf(dd * hh), x2 = lt_rbf(vv / dd);
-        const float a = x1 + duc1;                    // Qh_i          psgd.py:1017
-        const float Ph = dd * (a + dvc2);             // Ph_i          psgd.py:1018
-        const float b = x2 - dvs1;                    // invQtv_i      psgd.py:1024
-        const float invPv = (b - dus2) / dd;          // invPv_i       psgd.py:1025-1026
-        const float Phh = Ph * hh, vinv = vv * invPv;
-        if (side == 0) {
-          mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
-          P.dd_out[row0 + c] = Phh - vinv;
+        for (int c = 0; c < PACK; ++c) {
+          const float duc1 = __uint_as_float(du_raw[(c * 2 + 0) * 2]) + __uint_as_float(du_raw[(c * 2 + 0) * 2 + 1]);
+          const float dus2 = __uint_as_float(du_raw[(c * 2 + 1) * 2]) + __uint_as_float(du_raw[(c * 2 + 1) * 2 + 1]);
+          const float dvc2 = __uint_as_float(dv_raw[(c * 4 + 0) * 2]) + __uint_as_float(dv_raw[(c * 4 + 0) * 2 + 1]);
+          const float dvs1 = __uint_as_float(dv_raw[(c * 4 + 1) * 2]) + __uint_as_float(dv_raw[(c * 4 + 1) * 2 + 1]);
+          const float dva = __uint_as_float(dv_raw[(c * 4 + 2) * 2]) + __uint_as_float(dv_raw[(c * 4 + 2) * 2 + 1]);
+          const float dvb = __uint_as_float(dv_raw[(c * 4 + 3) * 2]) + __uint_as_float(dv_raw[(c * 4 + 3) * 2 + 1]);
+          const float dd = __bfloat162float(dvp[PACK * ln + c]), hh = __bfloat162float(hvp[PACK * ln + c]), vv = __bfloat162float(vvp[PACK * ln + c]);
+          const float x1 = lt_rbf(dd * hh), x2 = lt_rbf(vv / dd);
+          const float a = x1 + duc1;                    // Qh_i          psgd.py:1017
+          const float b = x2 - dvs1;                    // invQtv_i      psgd.py:1024
+          if (side == 0) {
+            const float Ph = dd * (a + dvc2);           // Ph_i          psgd.py:1018
+            const float invPv = __fdividef(b - dus2, dd);   // invPv_i   psgd.py:1025-1026
+            const float Phh = Ph * hh, vinv = vv * invPv;
+            mx1 = fmaxf(mx1, fabsf(Phh)); mx2 = fmaxf(mx2, fabsf(vinv));
+            P.dd_out[row0 + c] = Phh - vinv;
+          }
+          const float ca = update_U ? step * a : step * (a + dva);
+          const float cb = update_U ? step * b : step * (b + dvb);
+          nca2[c] = lt_pack2(-ca, -ca);
+          cb2[c] = lt_pack2(cb, cb);
         }
-        ca[c] = update_U ? step * a : step * (a + dva);
-        cb[c] = update_U ? step * b : step * (b + dvb);
       }
-      // rotation (identity part exact, correction from the MMA) + rank-2 update, 32 columns at a time; whole 16-byte pieces of the line
+      // rotation (identity part exact, correction from the MMA) + rank-2 update, 32 columns at a time; whole 16-byte pieces of the line;
+      // two columns per FFMA2
       {
         uint8_t* tl = side ? tile_v : tile_u;
-        const bool upd = side ? !update_U : (update_U != 0);
-        const float scale = side ? rho : inv_rho;
-        const float sgn = side ? 1.f : -1.f;
+        const lt_f2 scale2 = side ? lt_pack2(rho, rho) : lt_pack2(inv_rho, inv_rho);
+        const lt_f2 sgn2 = side ? lt_pack2(1.f, 1.f) : lt_pack2(-1.f, -1.f);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t raw[32];
@@ -445,16 +457,21 @@ __global__ void __launch_bounds__(LR_THREADS, 1) k_lra_rotate_tc(const __grid_co
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 x = unpack_bf16(w[e]);
               const int col = 8 * j + 2 * e;        // column of the line; sub-row c = col / RP, rank index nn = col % RP
               const int c = col / RP, nn = col % RP;
-              float y0 = (x.x + sgn * __uint_as_float(raw[8 * q + 2 * e])) * scale;
-              float y1 = (x.y + sgn * __uint_as_float(raw[8 * q + 2 * e + 1])) * scale;
+              const lt_f2 x2 = lt_pack2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+              const lt_f2 r2 = lt_pack2(__uint_as_float(raw[8 * q + 2 * e]), __uint_as_float(raw[8 * q + 2 * e + 1]));
+              const lt_f2 t = lt_fma2(sgn2, r2, x2);
+              lt_f2 y;
               if (upd) {
-                y0 -= ca[c] * wvec[0][nn] - cb[c] * wvec[1][nn];
-                y1 -= ca[c] * wvec[0][nn + 1] - cb[c] * wvec[1][nn + 1];
+                lt_f2 z = lt_mul2(cb2[c], *reinterpret_cast<const lt_f2*>(&wvec[1][nn]));
+                z = lt_fma2(nca2[c], *reinterpret_cast<const lt_f2*>(&wvec[0][nn]), z);
+                y = lt_fma2(t, scale2, z);          // (x + sgn raw) scale - (ca wa - cb wb)
+              } else {
+                y = lt_mul2(t, scale2);
               }
-              o[e] = pack_bf16(y0, y1);
+              const float2 yy = lt_unpack2(y);
+              o[e] = pack_bf16(yy.x, yy.y);
             }
             *reinterpret_cast<uint4*>(tl + ((j ^ (ln & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);   // in place: this thread owns the line
           }

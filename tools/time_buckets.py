@@ -6,7 +6,8 @@ import bench
 from psgd_torch_b200 import psgd
 
 dev = torch.device("cuda:0")
-only = sys.argv[1:]  # optional bucket names
+only = [a for a in sys.argv[1:] if not a.startswith("--")]  # optional bucket names
+BATCHED = "--batched" in sys.argv     # time the groups bench.py runs: same-shape units per engine call, in-kernel Philox noise
 
 
 def timeit(fn, iters):
@@ -21,6 +22,17 @@ def timeit(fn, iters):
 tot = 0.0
 for name, count, shape, kind in bench.LLAMA3_8B_SET:
     if only and name not in only: continue
+    if BATCHED:
+        nb = min(count, bench.BATCH.get(name, 1))
+        units = bench.build_units([(name, shape, kind)] * nb, dev)
+        groups = bench.make_groups(units)
+        psgd.set_noise_mode("philox")
+        t = timeit(lambda: bench.step_resident(units, groups, psgd), 5) / nb
+        print(f"{name:22s} x{count:3d} shape={shape}: batch of {nb:2d}: {t:8.3f} ms per unit  -> bucket {t*count:8.1f} ms")
+        tot += t * count
+        del units
+        torch.cuda.empty_cache()
+        continue
     u = bench.build_units([(name, shape, kind)], dev)[0]
     iters = 3 if u.numel > 1e8 else 10
     if kind == "kron":
