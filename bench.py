@@ -50,9 +50,10 @@ LLAMA3_8B_SET = [
 ]
 
 
-# measured update + apply time per unit on one B200 (ms; profiles/r01_bucket_times_v2.log, v3): the weights of the LPT partition
-UNIT_MS = {"q_o_proj": 1.68, "k_v_proj": 0.40, "gate_up_proj": 1.86, "down_proj": 1.89, "rmsnorm": 0.05, "lm_head": 10.5,
-           "embed_tokens_lra32": 69.0}
+# measured update + apply time per unit on one B200, batched as the bench runs them, Philox noise (ms;
+# profiles/r02_buckets_batched.log): the weights of the LPT partition
+UNIT_MS = {"q_o_proj": 1.53, "k_v_proj": 0.135, "gate_up_proj": 1.52, "down_proj": 1.70, "rmsnorm": 0.019, "lm_head": 10.7,
+           "embed_tokens_lra32": 62.0}
 
 
 def unit_list():
@@ -699,7 +700,7 @@ def run_kwns4(args):
         p.grad = (0.01 * torch.randn(*shp, device=dev, generator=gen)).bfloat16()
         params.append(p)
     opt = KWNS4(params, lr_params=2e-4, lr_preconditioner=0.1, preconditioner_dtype=torch.bfloat16, shard_preconditioners=world > 1,
-                batch_same_shape=not args.no_batching, comm_sms=args.comm_sms if world > 1 else 0)
+                batch_same_shape=not args.no_batching, comm_sms=args.comm_sms if world > 1 else 0, exchange=args.exchange)
     h = _lib.handle_for(dev)
     lib = _lib.load_library()
     for _ in range(args.warmup):
@@ -747,9 +748,13 @@ def run_kwns4(args):
                                        "(embed_tokens as Kron(diag, dense)), bf16 parameters / gradients / preconditioners, momentum 0.9, "
                                        "weight decay, clipping, parameter update; "
                                        + ("single GPU" if world == 1 else f"preconditioners sharded per parameter over {world} GPUs "
-                                          "(owner computes, NCCL broadcast of the updated parameter inside the timed region)"),
+                                          "(owner computes; the updated parameters reach the other ranks inside the timed region: "
+                                          + ("one NCCL all-gather per round of batches" if args.exchange == "all_gather" and not args.no_batching
+                                             else "one NCCL broadcast per parameter") + ")"),
                            "noise": args.noise, "batch_same_shape": not args.no_batching, "comm_sms": args.comm_sms if world > 1 else 0,
-                           "nccl_broadcast_bytes_per_step": bcast},
+                           "exchange": args.exchange if world > 1 else None,
+                           "nccl_parameter_bytes_per_step": bcast,
+                           "nccl_all_gather_buffer_bytes_per_step": getattr(opt, "_xbytes_step", 0)},
                 "clocks": clocks,
                 "e2e": {"value": n_units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(tot[1].item()),
                         "d2h_bytes_per_step": 4 * world},
@@ -792,7 +797,9 @@ def main():
     ap.add_argument("--mode", default="functional", choices=["functional", "kwns4"],
                     help="functional (default): update + apply per unit through the psgd.* functions (BASELINE configs[2]); kwns4: the same "
                          "set through KWNS4.step(), preconditioners sharded per parameter at N > 1 (BASELINE configs[3])")
-    ap.add_argument("--comm-sms", type=int, default=8, help="--mode kwns4 at N > 1: SMs left free for the NCCL broadcast kernels (0: none)")
+    ap.add_argument("--exchange", choices=["all_gather", "broadcast"], default="all_gather",
+                    help="--mode kwns4 at N > 1: how updated parameters reach the other ranks (KWNS4(exchange=...))")
+    ap.add_argument("--comm-sms", type=int, default=16, help="--mode kwns4 at N > 1: SMs left free for the NCCL broadcast kernels (0: none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--noise", default="philox", choices=["philox", "torch"],
                     help="philox: damping noise and norm-bound probes drawn inside the engine's kernels (performance mode); torch: drawn by "

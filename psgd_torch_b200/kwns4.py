@@ -49,6 +49,7 @@ class KWNS4(torch.optim.Optimizer):
             shard_preconditioners=False,
             batch_same_shape=False,
             comm_sms=0,
+            exchange="all_gather",
     ):
         # ddp.py:45-62, verbatim
         assert whiten_grad in (False, True)
@@ -103,6 +104,14 @@ class KWNS4(torch.optim.Optimizer):
         # sharded mode: SMs left free for the NCCL broadcast kernels that run beside the engine's persistent kernels (_lib.set_sm_limit)
         self.comm_sms = int(comm_sms)
         self._comm_sms_applied = False
+        # sharded + batched mode: how the updated parameters reach the other ranks.  "all_gather": every rank packs the batch it has
+        # just finished into a flat buffer and ONE all-gather per round moves all ranks' batches at once (every rank sends and receives
+        # concurrently, large messages); "broadcast": one NCCL broadcast per parameter from its owner (roots take turns, so only one
+        # rank sends at a time: measured 16 GB in 120 ms at 8 GPUs / 8 channels, profiles/r02_bench_kwns4_n8.json).
+        assert exchange in ("all_gather", "broadcast")
+        self.exchange = exchange
+        self._xbuf = None
+        self._comm_stream = None
         self._owner = None
         self.dQ = "Q0.5EQ1.5"  # ddp.py:84-86
         self.update_precond = psgd.update_precond_kron_whiten_q0p5eq1p5
@@ -409,6 +418,7 @@ class KWNS4(torch.optim.Optimizer):
             self._comm_sms_applied = True
         my_rank = torch.distributed.get_rank() if sharded else 0
         pending = []
+        self._xbytes_step = 0        # bytes every rank receives through the all-gather exchange this step (padding included)
         for group in self.param_groups:
             momentum = group["momentum"]
             coin = torch.rand([], generator=self._coin_gen) if sharded else torch.rand([])
@@ -458,10 +468,23 @@ class KWNS4(torch.optim.Optimizer):
                         self._resync(p, job["state"], group, momentum)
                 continue
             # sharded + batched: every rank derives every rank's batch list from the shapes and walks the same global sequence
-            # (round-robin over the owners' lists), computing its own batches and posting the broadcasts of all of them in that order
             world = torch.distributed.get_world_size()
             all_params = [p for p in group["params"] if self._local(p).numel() > 0]
             per_rank = [self._make_batches([p for p in all_params if self._owner[id(p)] == r]) for r in range(world)]
+            if self.exchange == "all_gather":
+                # rounds: round i holds the i-th largest batch of every rank (similar sizes per round -> little padding)
+                def nbytes(plist):
+                    return sum((self._local(p).numel() * self._local(p).element_size() + 15) // 16 * 16 for p in plist)
+                for r in range(world):
+                    per_rank[r].sort(key=nbytes, reverse=True)        # stable, shapes only: identical on every rank
+                for i in range(max(len(b) for b in per_rank)):
+                    plists = [per_rank[r][i] if i < len(per_rank[r]) else [] for r in range(world)]
+                    if plists[my_rank]:
+                        self._process([self._head(p, group) for p in plists[my_rank]], group, updateP_first, updateP_last)
+                    self._exchange_round(plists, max(nbytes(pl) for pl in plists), my_rank, world)
+                continue
+            # one broadcast per parameter: round-robin over the owners' lists, computing the own batches and posting the broadcasts of all
+            # of them in that order
             for i in range(max(len(b) for b in per_rank)):
                 for r in range(world):
                     if i >= len(per_rank[r]):
@@ -473,7 +496,59 @@ class KWNS4(torch.optim.Optimizer):
                         pending.append(torch.distributed.broadcast(self._local(p), src=r, async_op=True))
         for w in pending:
             w.wait()
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
         self._rng_exit(external)
+
+    def _exchange_round(self, plists, maxb, my_rank, world):
+        """One all-gather of this round's batches (plists[r] = the parameters rank r has just updated; maxb = the largest packed size).
+        On CUDA everything here runs on a side stream ordered after the compute stream, so that packing, the collective and unpacking
+        of round i overlap the engine calls of round i + 1; step() joins the side stream at its end."""
+        dev = None
+        for pl in plists:
+            if pl:
+                dev = self._local(pl[0]).device
+                break
+        if dev is None or maxb == 0:
+            return
+        need = (world + 1) * maxb
+        if self._xbuf is None or self._xbuf.numel() < need or self._xbuf.device != dev:
+            if self._comm_stream is not None:
+                self._comm_stream.synchronize()
+            self._xbuf = torch.empty(need, dtype=torch.uint8, device=dev)
+        send, recv = self._xbuf[:maxb], self._xbuf[maxb:need]
+        self._xbytes_step += world * maxb
+
+        def views(buf, plist):
+            out, off = [], 0
+            for p in plist:
+                lp = self._local(p)
+                nb = lp.numel() * lp.element_size()
+                out.append(buf[off:off + nb].view(lp.dtype).view(lp.shape))
+                off += (nb + 15) // 16 * 16
+            return out
+
+        def run():
+            with torch.no_grad():
+                if plists[my_rank]:
+                    torch._foreach_copy_(views(send, plists[my_rank]), [self._local(p).detach() for p in plists[my_rank]])
+                torch.distributed.all_gather_into_tensor(recv, send)
+                dst, src = [], []
+                for r in range(world):
+                    if r != my_rank and plists[r]:
+                        dst += [self._local(p).detach() for p in plists[r]]
+                        src += views(recv[r * maxb:(r + 1) * maxb], plists[r])
+                if dst:
+                    torch._foreach_copy_(dst, src)
+
+        if dev.type == "cuda":
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=dev)
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                run()
+        else:
+            run()
 
     def _make_batches(self, plist):
         """Consecutive-in-bucket grouping of parameters by (squeezed shape, dtype, dense/diagonal pattern), at most _lib.MAX_BATCH per

@@ -26,10 +26,11 @@ def loss_fn(ps):
     return tot
 
 
-def run(sharded):
+def run(sharded, batched=False):
     torch.manual_seed(11)
     ps = [torch.nn.Parameter(torch.zeros(*s, device=dev)) for s in shapes]
-    opt = KWNS4(ps, lr_params=0.05, lr_preconditioner=0.3, weight_decay=0.0, preconditioner_dtype=torch.float32, shard_preconditioners=sharded)
+    opt = KWNS4(ps, lr_params=0.05, lr_preconditioner=0.3, weight_decay=0.0, preconditioner_dtype=torch.float32, shard_preconditioners=sharded,
+                batch_same_shape=batched)
     losses = []
     for step in range(60):
         loss = loss_fn(ps)
@@ -50,6 +51,7 @@ def run(sharded):
 
 l_rep, w_rep, n_rep = run(False)
 l_sh, w_sh, n_sh = run(True)
+l_ag, w_ag, n_ag = run(True, batched=True)      # same-shape batches, one all-gather per round of batches
 counts = [torch.zeros(1, device=dev) for _ in range(world)]
 dist.all_gather(counts, torch.tensor([float(n_sh)], device=dev))
 if rank == 0:
@@ -57,6 +59,8 @@ if rank == 0:
     print(f"sharded   : loss {l_sh[0]:.4e} -> {l_sh[-1]:.4e}, max cross-rank param diff {w_sh:.2e}, params with state per rank: {[int(c.item()) for c in counts]} of {len(shapes)}")
     ok = w_sh == 0.0 and l_sh[-1] < 0.2 * l_sh[0] and abs(l_sh[-1] - l_rep[-1]) < 0.3 * max(l_rep[-1], l_sh[-1]) + 1e-6 \
         and sum(int(c.item()) for c in counts) == len(shapes)
+    print(f"sharded + batched (all-gather exchange): loss {l_ag[0]:.4e} -> {l_ag[-1]:.4e}, max cross-rank param diff {w_ag:.2e}")
+    ok = ok and w_ag == 0.0 and l_ag[-1] < 0.2 * l_ag[0] and abs(l_ag[-1] - l_rep[-1]) < 0.3 * max(l_rep[-1], l_ag[-1]) + 1e-6
     print("sharded KWNS4:", "OK" if ok else "MISMATCH")
 dist.barrier()
 dist.destroy_process_group()

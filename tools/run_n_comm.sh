@@ -1,21 +1,23 @@
 #!/bin/bash
-# multi-GPU (run under gpurun --gpus N): the sharded-KWNS4 bench against the SMs left to NCCL, and the broadcasts alone
+# multi-GPU (run under gpurun --gpus N): the sharded-KWNS4 bench (BASELINE configs[3]) per exchange scheme / SMs left to NCCL, the sharded
+# correctness check, and the parameter broadcasts alone
 N=$1
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-for C in default 8 16 32; do
-  if [ "$C" = default ]; then E=""; else E="NCCL_MAX_NCHANNELS=$C"; fi
-  env $E timeout 120 $TR --master-port 29621 tools/bcast_probe.py 2>&1 | grep NCCL_MAX >> gpurun_out/r02_bcast_probe_n$N.log
-done
-cat gpurun_out/r02_bcast_probe_n$N.log
-for C in 16 32; do
-  timeout 300 $TR --master-port 29622 bench.py --mode kwns4 --gpus $N --steps 5 --warmup 3 --comm-sms $C > gpurun_out/r02_bench_kwns4_n${N}_c$C.json 2> gpurun_out/r02_bench_kwns4_n${N}_c$C.err
+timeout 200 $TR --master-port 29614 tools/check_sharded_kwns4.py > gpurun_out/r02_sharded_kwns4_n$N.log 2>&1
+tail -4 gpurun_out/r02_sharded_kwns4_n$N.log
+for CFG in "all_gather 16" "all_gather 32" "broadcast 16"; do
+  set -- $CFG; X=$1; C=$2
+  F=gpurun_out/r02_bench_kwns4_n${N}_${X}_c$C
+  timeout 300 $TR --master-port 29622 bench.py --mode kwns4 --gpus $N --steps 5 --warmup 3 --comm-sms $C --exchange $X > $F.json 2> $F.err
   python - <<PY
 import json
 try:
-    d = json.loads(open("gpurun_out/r02_bench_kwns4_n${N}_c$C.json").read().strip().splitlines()[-1])
-    print("comm_sms $C: value", round(d["value"], 1), "ms", round(d["ms_per_step"], 1), "e2e", round(d["e2e"]["value"], 1))
+    d = json.loads(open("$F.json").read().strip().splitlines()[-1])
+    print("$X comm_sms $C: value", round(d["value"], 1), "ms", round(d["ms_per_step"], 1), "e2e", round(d["e2e"]["value"], 1), "all-gather bytes", d["config"].get("nccl_all_gather_buffer_bytes_per_step"))
 except Exception as e:
-    print("comm_sms $C unreadable", e)
+    print("$X comm_sms $C unreadable", e); print(open("$F.err").read()[-1500:])
 PY
 done
+NCCL_MAX_NCHANNELS=16 timeout 120 $TR --master-port 29621 tools/bcast_probe.py 2>&1 | grep NCCL_MAX >> gpurun_out/r02_bcast_probe_n$N.log
+cat gpurun_out/r02_bcast_probe_n$N.log
