@@ -79,6 +79,22 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, u
   __sincosf(6.283185307179586f * u3, &sb, &cb);
   z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
 }
+// eight standard normals from one Philox block: 16-bit uniforms (enough for noise that is rounded to bf16 -- 8 mantissa bits -- right
+// away; tails to 4.7 sigma).  Halves the integer work per normal: the damping-noise pass is bound by it, not by HBM.
+__device__ __forceinline__ void philox_normal8(uint64_t seed, uint64_t offset, uint32_t strm, uint64_t group, float* z) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), strm, (uint32_t)offset),
+                                make_uint2((uint32_t)seed ^ (uint32_t)(offset >> 32), (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float u0 = ((float)(w[t] & 0xffffu) + 1.0f) * 1.52587890625e-05f;     // (0, 1]
+    const float ang = (float)(w[t] >> 16) * (6.283185307179586f * 1.52587890625e-05f);
+    const float rad = sqrtf(-2.0f * __logf(u0));
+    float sn, cs;
+    __sincosf(ang, &sn, &cs);
+    z[2 * t] = rad * cs; z[2 * t + 1] = rad * sn;
+  }
+}
 
 // ------------------------------ batched forms: blockIdx.y = unit of a same-shape batch, pointers from a table ------------------------------
 constexpr int KB_MAX = 16;   // units per batched call
@@ -126,8 +142,7 @@ __global__ void k_add_noise_philox_multi(CPtrTab G, PtrTab out, size_t numel, fl
     for (; i < nvec; i += stride) {
       float a[8], z[8], r[8];
       ld8(reinterpret_cast<const bf16*>(g) + i * 8, a);
-      philox_normal4(seed, off, 0u, 2 * i, z);
-      philox_normal4(seed, off, 0u, 2 * i + 1, z + 4);
+      philox_normal8(seed, off, 0u, i, z);
 #pragma unroll
       for (int t = 0; t < 8; ++t) { const float d = rbf(damping + rbf(eps * fabsf(a[t]))); r[t] = a[t] + rbf(d * rbf(z[t])); }
       st8(reinterpret_cast<bf16*>(o) + i * 8, r);
