@@ -749,7 +749,9 @@ def run_kwns4(args):
                                        "weight decay, clipping, parameter update; "
                                        + ("single GPU" if world == 1 else f"preconditioners sharded per parameter over {world} GPUs "
                                           "(owner computes; the updated parameters reach the other ranks inside the timed region: "
-                                          + ("one NCCL all-gather per round of batches" if args.exchange == "all_gather" and not args.no_batching
+                                          + ("peer-to-peer copies (copy engines over NVLink) from the owner into every peer's parameter, CUDA IPC"
+                                             if args.exchange == "p2p" else
+                                             "one NCCL all-gather per round of batches" if args.exchange == "all_gather" and not args.no_batching
                                              else "one NCCL broadcast per parameter") + ")"),
                            "noise": args.noise, "batch_same_shape": not args.no_batching, "comm_sms": args.comm_sms if world > 1 else 0,
                            "exchange": args.exchange if world > 1 else None,
@@ -797,7 +799,7 @@ def main():
     ap.add_argument("--mode", default="functional", choices=["functional", "kwns4"],
                     help="functional (default): update + apply per unit through the psgd.* functions (BASELINE configs[2]); kwns4: the same "
                          "set through KWNS4.step(), preconditioners sharded per parameter at N > 1 (BASELINE configs[3])")
-    ap.add_argument("--exchange", choices=["all_gather", "broadcast"], default="all_gather",
+    ap.add_argument("--exchange", choices=["all_gather", "broadcast", "p2p"], default="all_gather",
                     help="--mode kwns4 at N > 1: how updated parameters reach the other ranks (KWNS4(exchange=...))")
     ap.add_argument("--comm-sms", type=int, default=16, help="--mode kwns4 at N > 1: SMs left free for the NCCL broadcast kernels (0: none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -53,6 +53,8 @@ SYMBOLS = {
     "psgd_set_gemm_path": (_i, [_vp, _i]),
     "psgd_launch_count": (_i64, [_vp]),
     "psgd_set_sm_limit": (_i, [_vp, _i]),
+    "psgd_peer_enable": (_i, [_i]),
+    "psgd_peer_copy_async": (_i, [_vp, _vp, _sz, _vp]),
     "psgd_set_fp32_tensor_cores": (_i, [_vp, _i]),
     "psgd_kron_workspace_bytes": (_sz, [_vp, C.POINTER(KronT)]),
     "psgd_kron_whiten_q0p5eq1p5_update": (_i, [_vp, C.POINTER(KronT), _vp, _f, _f, _f, C.POINTER(KronNoiseT), _i, _vp, _sz, _vp]),

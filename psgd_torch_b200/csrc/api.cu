@@ -750,6 +750,24 @@ int psgd_set_sm_limit(psgd_handle_t h, int sms) {
   return PSGD_OK;
 }
 
+int psgd_peer_enable(int peer_device) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) return PSGD_ERR_CUDA;
+  if (peer_device == cur) return PSGD_OK;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, cur, peer_device) != cudaSuccess || !can) { cudaGetLastError(); return PSGD_ERR_UNSUPPORTED; }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return PSGD_ERR_CUDA; }
+  cudaGetLastError();
+  return PSGD_OK;
+}
+
+int psgd_peer_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return PSGD_ERR_INVALID_ARG;
+  if (bytes == 0) return PSGD_OK;
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess ? PSGD_OK : PSGD_ERR_CUDA;
+}
+
 int64_t psgd_launch_count(psgd_handle_t h) { return h ? reinterpret_cast<Ctx*>(h)->launches : 0; }
 
 int psgd_set_fp32_tensor_cores(psgd_handle_t h, int on) {

@@ -108,10 +108,16 @@ class KWNS4(torch.optim.Optimizer):
         # just finished into a flat buffer and ONE all-gather per round moves all ranks' batches at once (every rank sends and receives
         # concurrently, large messages); "broadcast": one NCCL broadcast per parameter from its owner (roots take turns, so only one
         # rank sends at a time: measured 16 GB in 120 ms at 8 GPUs / 8 channels, profiles/r02_bench_kwns4_n8.json).
-        assert exchange in ("all_gather", "broadcast")
+        # "p2p" (CUDA only, one node): an owner pushes each updated parameter with peer-to-peer cudaMemcpyAsync on side streams -- copy
+        # engines over NVLink / NVSwitch, no SMs, beside the engine's kernels -- into staging buffers it allocated on the peers' GPUs; the
+        # peers map those buffers through CUDA IPC and copy the parameters out at the end of step().  One tiny all-reduce at the start
+        # of step() (the peers are done with the previous contents) and one at its end (all pushes have landed) are the only collectives.
+        assert exchange in ("all_gather", "broadcast", "p2p")
         self.exchange = exchange
         self._xbuf = None
         self._comm_stream = None
+        self._peer_views = None
+        self._peer_streams = None
         self._owner = None
         self.dQ = "Q0.5EQ1.5"  # ddp.py:84-86
         self.update_precond = psgd.update_precond_kron_whiten_q0p5eq1p5
@@ -412,6 +418,8 @@ class KWNS4(torch.optim.Optimizer):
         sharded = self._sharding_active()
         if sharded and self._owner is None:
             self._assign_owners()
+        if sharded and self.exchange == "p2p" and self._peer_views is None:
+            self._setup_p2p()
         if sharded and self.comm_sms > 0 and not self._comm_sms_applied:
             total = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
             _lib.set_sm_limit(total - self.comm_sms)
@@ -419,6 +427,9 @@ class KWNS4(torch.optim.Optimizer):
         my_rank = torch.distributed.get_rank() if sharded else 0
         pending = []
         self._xbytes_step = 0        # bytes every rank receives through the all-gather exchange this step (padding included)
+        p2p = sharded and self.exchange == "p2p"
+        if p2p:
+            torch.distributed.all_reduce(self._p2p_flag)    # every rank has finished reading its parameters (forward / backward)
         for group in self.param_groups:
             momentum = group["momentum"]
             coin = torch.rand([], generator=self._coin_gen) if sharded else torch.rand([])
@@ -443,6 +454,12 @@ class KWNS4(torch.optim.Optimizer):
                 if p.grad is None or self._local(p.grad).numel() == 0:  # ddp.py:114-115, dtensor.py:124-125
                     continue
                 mine.append(p)
+            if p2p:
+                # owner computes and pushes; nothing to do for the parameters of other owners
+                for plist in (self._make_batches(mine) if self.batch_same_shape else [[p] for p in mine]):
+                    self._process([self._head(p, group) for p in plist], group, updateP_first, updateP_last)
+                    self._push_round(plist)
+                continue
             if not self.batch_same_shape:
                 # the reference's order: one parameter at a time (ddp.py:112-161)
                 if sharded:
@@ -498,7 +515,104 @@ class KWNS4(torch.optim.Optimizer):
             w.wait()
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+        if p2p:
+            for st in self._peer_streams.values():
+                torch.cuda.current_stream().wait_stream(st)
+            torch.distributed.all_reduce(self._p2p_flag)    # ... and every rank's pushes have landed
+            self._unpack_p2p(my_rank)
         self._rng_exit(external)
+
+    def _setup_p2p(self):
+        """Collective, once.  Every rank allocates, ON EACH PEER'S GPU, a staging buffer for the parameters it owns (so that its pushes
+        are plain peer-to-peer copies into its own allocation: 750 GB/s per direction on the copy engines, measured beside running
+        GEMMs, tools/p2p_probe.py) and hands the peer a CUDA IPC handle of it; the peer maps it as device-local memory (3.2 TB/s copy-out,
+        tools/p2p_probe2.py).  Writing THROUGH an IPC mapping of another GPU's memory is the slow direction here (26 GB/s), hence the
+        staging.  One node, plain CUDA parameters."""
+        from torch.multiprocessing import reductions
+        dist = torch.distributed
+        world, me = dist.get_world_size(), dist.get_rank()
+        plist = [p for group in self.param_groups for p in group["params"] if self._local(p).numel() > 0]
+        dev = self._local(plist[0]).device
+        # layout of every owner's staging buffer: its parameters in parameter order, 16-byte aligned (shapes only: same on every rank)
+        self._stage_off, sizes = {}, [0] * world
+        for p in plist:
+            r = self._owner[id(p)]
+            lp = self._local(p)
+            self._stage_off[id(p)] = sizes[r]
+            sizes[r] += (lp.numel() * lp.element_size() + 15) // 16 * 16
+        # rank k drives GPU devs[k] of this node (torchrun: LOCAL_RANK); every rank takes part in every collective below whatever fails
+        devs = [None] * world
+        dist.all_gather_object(devs, dev.index if dev.type == "cuda" else None)
+        err, args = None, None
+        try:
+            if not all(self._local(p).is_cuda and self._local(p).is_contiguous() for p in plist):
+                raise _lib.EngineError("exchange='p2p' needs contiguous CUDA parameters")
+            if world > torch.cuda.device_count() or len(set(devs)) != world:
+                raise _lib.EngineError("exchange='p2p' works inside one node, one visible GPU per rank")
+            self._stage = {k: torch.empty(max(sizes[me], 16), dtype=torch.uint8, device=torch.device("cuda", devs[k]))
+                           for k in range(world) if k != me}
+            args = {k: reductions.reduce_tensor(t)[1] for k, t in self._stage.items()}
+            lib = _lib.load_library()
+            for k in self._stage:
+                rc = lib.psgd_peer_enable(devs[k])
+                if rc != 0:
+                    raise _lib.EngineError(f"no peer access from GPU {dev.index} to GPU {devs[k]} ({rc})")
+        except Exception as e:
+            err = e
+        gathered = [None] * world
+        dist.all_gather_object(gathered, args)
+        inbox = {}
+        if err is None and all(g is not None for g in gathered):
+            try:
+                for r in range(world):
+                    if r != me:
+                        inbox[r] = reductions.rebuild_cuda_tensor(*gathered[r][me])      # rank r's staging buffer on MY GPU
+                        assert inbox[r].device == dev
+            except Exception as e:
+                err = e
+        ok = torch.tensor([0.0 if err is not None or any(g is None for g in gathered) else 1.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) != 1.0:
+            raise _lib.EngineError(f"exchange='p2p': setting up the peer staging buffers failed on some rank ({err}); use exchange='all_gather'")
+        self._inbox = inbox
+        self._peer_views = True
+        self._peer_streams = {k: torch.cuda.Stream() for k in self._stage}
+        self._p2p_flag = torch.zeros(1, device=dev)
+        self._p2p_plist = plist
+
+    def _stage_view(self, buf, p):
+        lp = self._local(p)
+        off = self._stage_off[id(p)]
+        return buf[off:off + lp.numel() * lp.element_size()].view(lp.dtype).view(lp.shape)
+
+    def _push_round(self, plist):
+        """Copy the parameters this rank has just updated (current stream) into its staging buffer on every peer's GPU: one side stream
+        per peer, ordered after the current stream; psgd_peer_copy_async = cudaMemcpyAsync on THIS device's stream only (copy engines
+        over NVLink).  Not torch's cross-device copy_: that records / waits events on the destination device's stream in this process,
+        and a GPU with work from two processes' contexts time-slices between them (measured: 255 instead of 205 ms per step at 2 GPUs)."""
+        lib = _lib.load_library()
+        ev = torch.cuda.Event()
+        ev.record()
+        for k, st in self._peer_streams.items():
+            st.wait_event(ev)
+            base = self._stage[k].data_ptr()
+            for p in plist:
+                lp = self._local(p)
+                rc = lib.psgd_peer_copy_async(base + self._stage_off[id(p)], lp.data_ptr(), lp.numel() * lp.element_size(), st.cuda_stream)
+                if rc != 0:
+                    raise _lib.EngineError(f"psgd_peer_copy_async failed ({rc})")
+
+    def _unpack_p2p(self, my_rank):
+        """After the end-of-step barrier: the peers' staging buffers on this GPU hold their updated parameters; copy them out (local)."""
+        dst, src = [], []
+        for p in self._p2p_plist:
+            r = self._owner[id(p)]
+            if r != my_rank:
+                dst.append(self._local(p).detach())
+                src.append(self._stage_view(self._inbox[r], p))
+        with torch.no_grad():
+            if dst:
+                torch._foreach_copy_(dst, src)
 
     def _exchange_round(self, plists, maxb, my_rank, world):
         """One all-gather of this round's batches (plists[r] = the parameters rank r has just updated; maxb = the largest packed size).

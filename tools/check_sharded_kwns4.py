@@ -26,11 +26,11 @@ def loss_fn(ps):
     return tot
 
 
-def run(sharded, batched=False):
+def run(sharded, batched=False, exchange="all_gather"):
     torch.manual_seed(11)
     ps = [torch.nn.Parameter(torch.zeros(*s, device=dev)) for s in shapes]
     opt = KWNS4(ps, lr_params=0.05, lr_preconditioner=0.3, weight_decay=0.0, preconditioner_dtype=torch.float32, shard_preconditioners=sharded,
-                batch_same_shape=batched)
+                batch_same_shape=batched, exchange=exchange)
     losses = []
     for step in range(60):
         loss = loss_fn(ps)
@@ -52,6 +52,7 @@ def run(sharded, batched=False):
 l_rep, w_rep, n_rep = run(False)
 l_sh, w_sh, n_sh = run(True)
 l_ag, w_ag, n_ag = run(True, batched=True)      # same-shape batches, one all-gather per round of batches
+l_pp, w_pp, n_pp = run(True, batched=True, exchange="p2p")   # owners push into the peers' parameters (CUDA IPC + peer copies)
 counts = [torch.zeros(1, device=dev) for _ in range(world)]
 dist.all_gather(counts, torch.tensor([float(n_sh)], device=dev))
 if rank == 0:
@@ -61,6 +62,8 @@ if rank == 0:
         and sum(int(c.item()) for c in counts) == len(shapes)
     print(f"sharded + batched (all-gather exchange): loss {l_ag[0]:.4e} -> {l_ag[-1]:.4e}, max cross-rank param diff {w_ag:.2e}")
     ok = ok and w_ag == 0.0 and l_ag[-1] < 0.2 * l_ag[0] and abs(l_ag[-1] - l_rep[-1]) < 0.3 * max(l_rep[-1], l_ag[-1]) + 1e-6
+    print(f"sharded + batched (p2p push exchange): loss {l_pp[0]:.4e} -> {l_pp[-1]:.4e}, max cross-rank param diff {w_pp:.2e}")
+    ok = ok and w_pp == 0.0 and l_pp[-1] < 0.2 * l_pp[0] and abs(l_pp[-1] - l_rep[-1]) < 0.3 * max(l_rep[-1], l_pp[-1]) + 1e-6
     print("sharded KWNS4:", "OK" if ok else "MISMATCH")
 dist.barrier()
 dist.destroy_process_group()

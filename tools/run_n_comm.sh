@@ -6,8 +6,8 @@ mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 200 $TR --master-port 29614 tools/check_sharded_kwns4.py > gpurun_out/r02_sharded_kwns4_n$N.log 2>&1
 tail -4 gpurun_out/r02_sharded_kwns4_n$N.log
-for CFG in "all_gather 16" "all_gather 32" "broadcast 16"; do
-  set -- $CFG; X=$1; C=$2
+for CFG in ${CFGS:-p2p_0}; do
+  X=${CFG%_*}; C=${CFG##*_}
   F=gpurun_out/r02_bench_kwns4_n${N}_${X}_c$C
   timeout 300 $TR --master-port 29622 bench.py --mode kwns4 --gpus $N --steps 5 --warmup 3 --comm-sms $C --exchange $X > $F.json 2> $F.err
   python - <<PY
@@ -19,5 +19,3 @@ except Exception as e:
     print("$X comm_sms $C unreadable", e); print(open("$F.err").read()[-1500:])
 PY
 done
-NCCL_MAX_NCHANNELS=16 timeout 120 $TR --master-port 29621 tools/bcast_probe.py 2>&1 | grep NCCL_MAX >> gpurun_out/r02_bcast_probe_n$N.log
-cat gpurun_out/r02_bcast_probe_n$N.log
