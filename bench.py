@@ -677,6 +677,8 @@ def run_kwns4(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
+    if args.comm_sms < 0:
+        args.comm_sms = 0 if args.exchange == "p2p" else 16
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -799,9 +801,10 @@ def main():
     ap.add_argument("--mode", default="functional", choices=["functional", "kwns4"],
                     help="functional (default): update + apply per unit through the psgd.* functions (BASELINE configs[2]); kwns4: the same "
                          "set through KWNS4.step(), preconditioners sharded per parameter at N > 1 (BASELINE configs[3])")
-    ap.add_argument("--exchange", choices=["all_gather", "broadcast", "p2p"], default="all_gather",
+    ap.add_argument("--exchange", choices=["all_gather", "broadcast", "p2p"], default="p2p",
                     help="--mode kwns4 at N > 1: how updated parameters reach the other ranks (KWNS4(exchange=...))")
-    ap.add_argument("--comm-sms", type=int, default=16, help="--mode kwns4 at N > 1: SMs left free for the NCCL broadcast kernels (0: none)")
+    ap.add_argument("--comm-sms", type=int, default=-1,
+                    help="--mode kwns4 at N > 1: SMs left free for the NCCL kernels of the exchange (0: none; default: 0 for p2p, 16 otherwise)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--noise", default="philox", choices=["philox", "torch"],
                     help="philox: damping noise and norm-bound probes drawn inside the engine's kernels (performance mode); torch: drawn by "
