@@ -1024,7 +1024,9 @@ static int tc2_choice(const Ctx* ctx, const GemmDesc* gs, int n) {
   const double w2 = (double)((t2 + pairs - 1) / pairs);
   const long full = t1 / ctx->num_sms, frac = t1 % ctx->num_sms;
   const double w1 = (double)full + (frac == 0 ? 0.0 : (frac * 2 <= ctx->num_sms ? 0.5 : 1.0));
-  const int pct = (ctx->debug_flags >> 8) & 0xff;     // experiment knob: relative cost of a 1-CTA wave in percent (default 118)
+  static int wave_pct = -1;                            // experiment knob: relative cost of a 1-CTA wave in percent (default 118)
+  if (wave_pct < 0) { const char* e = getenv("PSGD_B200_TC1_WAVE_PCT"); wave_pct = e ? atoi(e) : 0; if (wave_pct < 0 || wave_pct > 1000) wave_pct = 0; }
+  const int pct = wave_pct;
   const double c1 = w1 * (pct ? pct * 0.01 : 1.18);
   double c2 = w2;
   int bn = 256;
