@@ -757,7 +757,7 @@ def run_kwns4(args):
                                              else "one NCCL broadcast per parameter") + ")"),
                            "noise": args.noise, "batch_same_shape": not args.no_batching, "comm_sms": args.comm_sms if world > 1 else 0,
                            "exchange": args.exchange if world > 1 else None,
-                           "nccl_parameter_bytes_per_step": bcast,
+                           "parameter_bytes_exchanged_per_step": bcast,
                            "nccl_all_gather_buffer_bytes_per_step": getattr(opt, "_xbytes_step", 0)},
                 "clocks": clocks,
                 "e2e": {"value": n_units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(tot[1].item()),
